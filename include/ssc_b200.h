@@ -1,0 +1,154 @@
+/*
+ * ssc_b200.h -- C ABI of the B200-native patch subspace-correction preconditioner.
+ *
+ * This is the boundary a maintainer of wence-/ssc binds instead of libssc.c's per-patch loops
+ * (INTEGRATION.md shows the Cython stub).  Plain C: opaque handle, pointers and sizes, int return
+ * (0 = success, otherwise a PETSc-style error code; SSCGetLastError() gives the text), mirroring
+ * `PetscErrorCode` + CHKERR of ssc/PatchPC.pyx:36-47.  No PETSc, torch or CUDA types appear here.
+ *
+ * SSCInt is PetscInt as the reference builds it (`ctypedef long PetscInt`, ssc/PatchPC.pyx:7);
+ * scalars are fp64 (`ctypedef double PetscScalar`, ssc/PatchPC.pyx:8).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef SSC_B200_H
+#define SSC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int64_t SSCInt;
+typedef struct SSCPatchPC_s *SSCPatchPC;
+
+/* memory space of the vector / matrix pointers passed to SetOperator / Apply */
+enum { SSC_MEM_HOST = 0, SSC_MEM_DEVICE = 1 };
+/* patch construction, PCPatchConstructType ssc/libssc.h:11 */
+enum { SSC_PATCH_STAR = 0, SSC_PATCH_VANKA = 1, SSC_PATCH_USER = 2, SSC_PATCH_PYTHON = 3 };
+/* patch sub-solver: -sub_pc_type under -sub_ksp_type preonly (ssc/libssc.c:1240-1241, :1295) */
+enum { SSC_SUB_LU = 0, SSC_SUB_CHOLESKY = 1 };
+
+/* ---- library / device -------------------------------------------------------------------- */
+/* text of the last error raised on this thread (SETERRQ messages of ssc/libssc.c) */
+const char *SSCGetLastError(void);
+/* number of CUDA devices visible; 0 is an error for every compute entry point (there is no CPU fallback) */
+int SSCDeviceCount(int *count);
+/* PCPatchInitializePackage ssc/libssc.c:11-27: registers the six log-event names used by SSCPatchGetEventTime */
+int SSCPatchInitializePackage(void);
+
+/* ---- lifecycle: PC vtable slots of ssc/libssc.c:1714-1722 -------------------------------- */
+/* device = CUDA ordinal of this rank's GPU.  device = -1 creates a host-only handle on which only the patch
+ * construction entry points work (SetPlex .. BuildPatches, GetPatches/GetCells/GetDofs); SetUp/Apply on it fail. */
+int SSCPatchCreate(int device, SSCPatchPC *pc);           /* PCCreate_PATCH   ssc/libssc.c:1687-1725 (defaults :1697-1711) */
+int SSCPatchReset(SSCPatchPC pc);                         /* PCReset_PATCH    ssc/libssc.c:902-985  */
+int SSCPatchDestroy(SSCPatchPC *pc);                      /* PCDestroy_PATCH  ssc/libssc.c:987-1004 */
+
+/* ---- options: PCSetFromOptions_PATCH ssc/libssc.c:1551-1620 ------------------------------- */
+/* name is the option without the prefix and leading dash, e.g. "pc_patch_save_operators", "sub_pc_type";
+ * value is its string form ("true", "1", "lu", ...).  Unknown names and unsupported values return an error
+ * (no silent fallback); "pc_patch_multiplicative true" errors exactly as ssc/libssc.c:1570-1572 does. */
+int SSCPatchSetOption(SSCPatchPC pc, const char *name, const char *value);
+int SSCPatchSetSaveOperators(SSCPatchPC pc, int flg);     /* PCPatchSetSaveOperators     ssc/libssc.c:84-91   */
+int SSCPatchSetPartitionOfUnity(SSCPatchPC pc, int flg);  /* PCPatchSetPartitionOfUnity  ssc/libssc.c:93-100  */
+int SSCPatchSetSubMatType(SSCPatchPC pc, const char *t);  /* PCPatchSetSubMatType        ssc/libssc.c:281-291 */
+
+/* ---- topology + discretisation (host pointers) ------------------------------------------- */
+/* Replaces PCSetDM(mesh._plex) (ssc/patch.py:214) and the DMPlex queries of ssc/libssc.c:472-504:
+ * chart [0,pEnd), cone table, depth strata [depthStart[d], depthEnd[d]) for d = 0..dim, and the
+ * "pyop2_ghost" label as one byte per point (may be NULL = nothing is ghost).  Arrays are copied. */
+int SSCPatchSetPlex(SSCPatchPC pc, SSCInt dim, SSCInt pEnd, const SSCInt *coneOff, const SSCInt *cones,
+                    const SSCInt *depthStart, const SSCInt *depthEnd, const unsigned char *ghost);
+/* PCPatchSetCellNumbering ssc/libssc.c:225-234: the section is passed as its (dof, offset) arrays over the chart. Copied. */
+int SSCPatchSetCellNumbering(SSCPatchPC pc, const SSCInt *dof, const SSCInt *off);
+/* PCPatchSetDiscretisationInfo ssc/libssc.c:237-279 (declared ssc/libssc.h:7).  `DM *dms` becomes the default
+ * section of each DM as (secDof[k], secOff[k]) arrays over the chart.  Ownership follows the reference:
+ * cellNodeMap[k] is BORROWED for the lifetime of the PC (:268); everything else is copied (:265-277). */
+int SSCPatchSetDiscretisationInfo(SSCPatchPC pc, SSCInt nsubspaces, const SSCInt *const *secDof,
+                                  const SSCInt *const *secOff, const SSCInt *bs, const SSCInt *nodesPerCell,
+                                  const SSCInt *const *cellNodeMap, const SSCInt *subspaceOffsets,
+                                  SSCInt numGhostBcs, const SSCInt *ghostBcNodes,
+                                  SSCInt numGlobalBcs, const SSCInt *globalBcNodes);
+/* Result of PCPatchSetUserPatchConstructionOperator's callback (ssc/libssc.c:310, :487; ssc/PatchPC.pyx:74-98):
+ * the user's index sets flattened as offsets/points, and the iteration set.  Copied. */
+int SSCPatchSetUserPatches(SSCPatchPC pc, SSCInt nuserIS, const SSCInt *userOff, const SSCInt *userPoints,
+                           SSCInt niter, const SSCInt *iterationSet);
+/* Alternative to the three calls above for a caller that already holds the dof lists (e.g. a live PETSc
+ * PCPATCH): gtolCounts/gtol of ssc/libssc.c:779-837 as offsets[npatch+1] + gtol[offsets[npatch]], the size of
+ * the local (owned+ghost) vector, the size of the owned vector, and globalBcNodes (:277).  Copied. */
+int SSCPatchSetPatches(SSCPatchPC pc, SSCInt npatch, const SSCInt *offsets, const SSCInt *gtol,
+                       SSCInt nlocal, SSCInt nowned, SSCInt numGlobalBcs, const SSCInt *globalBcNodes);
+
+/* ---- star forest (owner <-> ghost map), replaces PCPatchCreateDefaultSF_Private ssc/libssc.c:102-223 -- */
+/* nowned = roots on this rank (size of x, y); the local vector has nlocal = subspaceOffsets[nsubspaces] leaves.
+ * selfLeaf[i] (i < nself) is a local slot whose root is selfRoot[i] on this rank.  For neighbour k of nneigh:
+ * sendRoot[sendOff[k]..sendOff[k+1]) are owned indices whose values fill ghosts on rank neigh[k] (SFBcast, :1323)
+ * and that receive-and-add the neighbour's contributions (SFReduce, :1399); recvLeaf[recvOff[k]..) are the local
+ * ghost slots owned by rank neigh[k], in the order that rank lists them in its sendRoot.  Copied.
+ * Without this call the SF is the identity on [0, nowned) (one process). */
+int SSCPatchSetStarForest(SSCPatchPC pc, SSCInt nowned, SSCInt nself, const SSCInt *selfLeaf, const SSCInt *selfRoot,
+                          SSCInt nneigh, const int *neigh, const SSCInt *sendOff, const SSCInt *sendRoot,
+                          const SSCInt *recvOff, const SSCInt *recvLeaf);
+/* NCCL communicator over the ranks of one NVSwitch box (the MPI communicator of the reference's PC).
+ * uniqueId is the 128-byte ncclUniqueId produced by SSCCommGetUniqueId on rank 0 and passed around by the host. */
+int SSCCommGetUniqueId(char uniqueId[128]);
+int SSCPatchCommInit(SSCPatchPC pc, int nranks, int rank, const char uniqueId[128]);
+
+/* ---- operator: replaces PCPatchSetComputeOperator ssc/libssc.c:293-308 (declared ssc/libssc.h:8) ------ */
+/* The reference re-assembles every patch matrix through a callback (:1150).  Here the patch blocks are cut out
+ * of the assembled local operator in CSR form: rows for every local dof that lies in a patch, columns in local
+ * numbering.  memspace says where the three arrays live.  The arrays are BORROWED until the next SetUp returns. */
+int SSCPatchSetOperatorCSR(SSCPatchPC pc, SSCInt nrows, const SSCInt *rowptr, const int32_t *colidx,
+                           const double *vals, int memspace);
+
+/* ---- setup and apply ----------------------------------------------------------------------- */
+int SSCPatchSetUp(SSCPatchPC pc);                         /* PCSetUp_PATCH ssc/libssc.c:1201-1299 (+ the lazy factorisation inside :1374) */
+/* PCApply_PATCH ssc/libssc.c:1301-1426: y = sum_p R_p^T B_p^{-1} R_p x on free dofs, y = x on owned Dirichlet dofs,
+ * optionally weighted.  x and y have nowned entries and live in `memspace`. Stream-ordered; returns after y is complete
+ * for SSC_MEM_HOST, after enqueue for SSC_MEM_DEVICE (use SSCPatchSynchronize). */
+int SSCPatchApply(SSCPatchPC pc, const double *x, double *y, int memspace);
+/* slot pc->ops->applytranspose is 0 in the reference (ssc/libssc.c:1715): always an error (PETSC_ERR_SUP) */
+int SSCPatchApplyTranspose(SSCPatchPC pc, const double *x, double *y, int memspace);
+int SSCPatchSynchronize(SSCPatchPC pc);
+/* PCView_PATCH ssc/libssc.c:1622-1685: writes the same lines into buf */
+int SSCPatchView(SSCPatchPC pc, char *buf, SSCInt len);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+/* sizes: "npatch", "nlocal", "nowned", "sum_n", "sum_n2", "max_n", "num_cells", "num_classes", "block_bytes",
+ * "bytes_apply", "bytes_extract", "flops_factor", "failed_patches", "gpu_launches" */
+int SSCPatchGetSize(SSCPatchPC pc, const char *what, SSCInt *value);
+/* run the host-side patch construction now (ssc/libssc.c:1219-1220); needs no device.  SetUp calls it if needed. */
+int SSCPatchBuildPatches(SSCPatchPC pc);
+/* copies of the host-side construction results (ssc/libssc.c:452-900); any pointer may be NULL */
+int SSCPatchGetPatches(SSCPatchPC pc, SSCInt *gtolOffsets, SSCInt *gtol);
+int SSCPatchGetCells(SSCPatchPC pc, SSCInt *cellOffsets, SSCInt *cells);
+int SSCPatchGetDofs(SSCPatchPC pc, SSCInt *dofs);         /* only if option "ssc_keep_dofs_table" is on */
+/* dense operator (which = 0) or stored inverse (which = 1) of patch p, row-major n x n, copied to host */
+int SSCPatchGetPatchMatrix(SSCPatchPC pc, SSCInt p, int which, double *out);
+/* dof weights of ssc/libssc.c:1254-1284 (nowned values, host) */
+int SSCPatchGetDofWeights(SSCPatchPC pc, double *w);
+/* device time in ms of the last completed stage, named as the reference's log events (ssc/libssc.c:19-24):
+ * "PCPATCHCreate", "PCPATCHComputeOp" (extract), "PCPATCHSolve" (factor at setup / fused apply kernel),
+ * "PCPATCHApply", "PCPATCHScatter", "PCPATCHPrealloc". */
+int SSCPatchGetEventTime(SSCPatchPC pc, const char *event, double *ms);
+/* accumulate device time of the fused apply kernel(s) over applies (CUDA events on the apply stream) */
+int SSCPatchKernelTimerReset(SSCPatchPC pc, int enable);
+int SSCPatchKernelTimerRead(SSCPatchPC pc, double *total_ms, SSCInt *napply);
+
+/* ---- device plumbing for callers that keep vectors resident (no torch needed) -------------- */
+int SSCDeviceMalloc(SSCPatchPC pc, SSCInt bytes, void **ptr);
+int SSCDeviceFree(SSCPatchPC pc, void *ptr);
+int SSCHostAlloc(SSCPatchPC pc, SSCInt bytes, void **ptr);  /* pinned */
+int SSCHostFree(SSCPatchPC pc, void *ptr);
+int SSCMemcpy(SSCPatchPC pc, void *dst, const void *src, SSCInt bytes, int dstSpace, int srcSpace);
+int SSCDeviceFlushL2(SSCPatchPC pc);                        /* overwrite a buffer larger than L2 (bench hygiene) */
+/* CUDA events on the PC's stream */
+int SSCEventCreate(SSCPatchPC pc, void **ev);
+int SSCEventRecord(SSCPatchPC pc, void *ev);
+int SSCEventElapsed(SSCPatchPC pc, void *start, void *stop, double *ms);  /* synchronises on stop */
+int SSCEventDestroy(SSCPatchPC pc, void *ev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,40 @@
+"""Builds libssc_b200.so (CUDA engine + host patch builder) and libssc_synth.so (synthetic operators) in-tree."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libssc_b200.so")
+SYNTH = os.path.join(HERE, "libssc_synth.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "patch_builder.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "common.h")] + \
+        [os.path.join(HERE, "..", "include", "ssc_b200.h")]
+    if force or _stale(LIB, deps):
+        cmd = [NVCC] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-O3,-pthread",
+                               "-ccbin", "/usr/bin/g++", "-o", LIB] + srcs + ["-ldl", "-lpthread"]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.check_call(cmd)
+    ssrc = os.path.join(CSRC, "synth.cpp")
+    if os.path.exists(ssrc) and (force or _stale(SYNTH, [ssrc])):
+        subprocess.check_call(["/usr/bin/g++", "-O3", "-march=x86-64-v3", "-std=c++17", "-fopenmp", "-shared", "-fPIC",
+                               "-o", SYNTH, ssrc])
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

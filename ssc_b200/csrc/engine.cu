@@ -1,0 +1,1034 @@
+// C ABI + device engine of the B200 patch preconditioner (include/ssc_b200.h).
+//
+// Stage map (reference loop -> kernel), see DESIGN.md:
+//   PCSetUp_PATCH  ssc/libssc.c:1201-1299  -> host patch builder (patch_builder.cpp), K1 extract, K2 factor, PoU weights
+//   PCApply_PATCH  ssc/libssc.c:1301-1426  -> halo fill, fused gather/solve/scatter-add kernel per size class,
+//                                             overlap sum, BC pass-through, optional weighting
+// There is no CPU fallback: every compute entry point fails if no CUDA device is present.
+#include "../../include/ssc_b200.h"
+#include "common.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
+#include <dlfcn.h>
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+int ssc_set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+extern "C" const char *SSCGetLastError(void) { return g_err; }
+
+#define CUDA_OK(call)                                                                                          \
+    do {                                                                                                       \
+        cudaError_t e_ = (call);                                                                               \
+        if (e_ != cudaSuccess)                                                                                 \
+            return ssc_set_error(SSC_ERR_GPU, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+    } while (0)
+#define CHK(call)                    \
+    do {                             \
+        int ierr_ = (call);          \
+        if (ierr_) return ierr_;     \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen: a one-GPU run never needs the library
+// ---------------------------------------------------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_t;
+struct Nccl {
+    void *h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId_t *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId_t, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static Nccl g_nccl;
+static int nccl_load()
+{
+    if (g_nccl.h) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; names[i] && !g_nccl.h; ++i) g_nccl.h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl.h) return ssc_set_error(SSC_ERR_LIB, "cannot load libnccl: %s", dlerror());
+#define SYM(f, name)                                                                                 \
+    *(void **)(&g_nccl.f) = dlsym(g_nccl.h, name);                                                   \
+    if (!g_nccl.f) return ssc_set_error(SSC_ERR_LIB, "libnccl lacks %s", name);
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return 0;
+}
+#define NCCL_OK(call)                                                                                     \
+    do {                                                                                                  \
+        int r_ = (call);                                                                                  \
+        if (r_ != 0) return ssc_set_error(SSC_ERR_LIB, "NCCL error %s at %s:%d", g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+static const int kNcclFloat64 = 8;   // ncclDouble
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct SizeClass {
+    int n = 0;
+    i64 count = 0, first = 0;     // position in size-sorted order
+    i64 goff = 0;                 // offset of the class in d_gtol (entries)
+    i64 moff = 0;                 // offset of the class in d_blocks (doubles)
+    i64 stride = 0;               // doubles per block
+    int tp = 0, ppb = 0;          // apply launch shape
+};
+
+struct SSCPatchPC_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    // options (defaults: PCCreate_PATCH ssc/libssc.c:1697-1711)
+    bool save_operators = true, partition_of_unity = false, multiplicative = false, print_patches = false;
+    bool symmetrise_sweep = false, keep_operators = false, dim_set = false, codim_set = false;
+    int sub_pc = SSC_SUB_LU;
+    std::string sub_mat_type, sub_ksp_type = "preonly";
+    BuildOptions bopt;
+    // host inputs
+    HostPlex plex;
+    Discretisation disc;
+    UserPatches user;
+    PatchLists lists;
+    bool lists_valid = false, direct_patches = false;
+    i64 nlocal = 0, nowned = 0;
+    std::vector<i64> globalBc;
+    // star forest
+    bool sf_set = false;
+    std::vector<i64> selfLeaf, selfRoot, sendOff, sendRoot, recvOff, recvLeaf;
+    std::vector<int> neigh;
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    // operator (borrowed)
+    i64 csr_nrows = 0;
+    const i64 *csr_rowptr = nullptr;
+    const int32_t *csr_colidx = nullptr;
+    const double *csr_vals = nullptr;
+    int csr_space = SSC_MEM_HOST;
+    bool csr_set = false;
+    // device state
+    bool device_ready = false, setup_done = false;
+    std::vector<SizeClass> classes;
+    std::vector<i64> sorted2orig, orig2sorted;
+    int *d_gtol = nullptr;
+    double *d_blocks = nullptr, *d_blocks0 = nullptr;
+    i64 block_elems = 0, sum_n = 0, sum_n2 = 0, max_n = 0;
+    int *d_fail = nullptr;
+    i64 failed = 0;
+    int *d_bc = nullptr;
+    i64 nbc = 0;
+    double *d_w = nullptr, *d_mult = nullptr;
+    double *d_xl = nullptr, *d_yl = nullptr;      // local (owned+ghost) vectors when the SF is not the identity
+    double *d_xs = nullptr, *d_ys = nullptr;      // staging for host-space applies
+    int *d_selfLeaf = nullptr, *d_selfRoot = nullptr, *d_sendRoot = nullptr, *d_recvLeaf = nullptr;
+    double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
+    // device copies of the operator
+    i64 *d_rowptr = nullptr;
+    int *d_colidx = nullptr;
+    double *d_vals = nullptr;
+    bool csr_owned = false;
+    void *d_flush = nullptr;
+    // timing
+    std::map<std::string, double> event_ms;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ktimer = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;
+    size_t kev_used = 0;
+    double ktimer_ms = 0;
+    i64 ktimer_n = 0;
+    i64 launches = 0;
+};
+typedef SSCPatchPC_s PC;
+
+static int set_device(PC *pc)
+{
+    if (pc->device < 0) return ssc_set_error(SSC_ERR_GPU, "this PC was created without a CUDA device (host-only handle); there is no CPU fallback");
+    CUDA_OK(cudaSetDevice(pc->device));
+    return 0;
+}
+template <class T> static int dev_alloc(T **p, i64 count)
+{
+    if (count <= 0) count = 1;
+    cudaError_t e = cudaMalloc((void **)p, (size_t)count * sizeof(T));
+    if (e != cudaSuccess) return ssc_set_error(SSC_ERR_MEM, "cudaMalloc of %lld bytes failed: %s", (long long)(count * (i64)sizeof(T)), cudaGetErrorString(e));
+    return 0;
+}
+template <class T> static void dev_free(T *&p) { if (p) cudaFree(p); p = nullptr; }
+
+static int upload_i32(PC *pc, const std::vector<i64> &src, int **dst)
+{
+    std::vector<int> tmp(src.size());
+    for (size_t i = 0; i < src.size(); ++i) {
+        if (src[i] < 0 || src[i] > 2147483647LL) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "index %lld does not fit the device's 32-bit dof index", (long long)src[i]);
+        tmp[i] = (int)src[i];
+    }
+    CHK(dev_alloc(dst, (i64)tmp.size()));
+    if (!tmp.empty()) CUDA_OK(cudaMemcpyAsync(*dst, tmp.data(), tmp.size() * sizeof(int), cudaMemcpyHostToDevice, pc->stream));
+    CUDA_OK(cudaStreamSynchronize(pc->stream));
+    return 0;
+}
+
+static inline int grid_for(i64 n, int block) { i64 g = (n + block - 1) / block; return (int)std::min<i64>(std::max<i64>(g, 1), 148 * 32); }
+
+// ---------------------------------------------------------------------------------------------
+// library / lifecycle
+// ---------------------------------------------------------------------------------------------
+extern "C" int SSCDeviceCount(int *count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *count = n;
+    return 0;
+}
+extern "C" int SSCPatchInitializePackage(void) { return 0; }
+
+extern "C" int SSCPatchCreate(int device, SSCPatchPC *out)
+{
+    if (device == -1) {            // host-only handle: patch construction (no arithmetic) without a GPU
+        PC *pc = new PC();
+        pc->device = -1;
+        *out = pc;
+        return 0;
+    }
+    int n = 0;
+    SSCDeviceCount(&n);
+    if (n <= 0) return ssc_set_error(SSC_ERR_GPU, "no CUDA device is visible; this library has no CPU fallback");
+    if (device < 0 || device >= n) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "device %d out of range [0,%d)", device, n);
+    PC *pc = new PC();
+    pc->device = device;
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaStreamCreateWithFlags(&pc->stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    pc->sm_count = prop.multiProcessorCount;
+    CUDA_OK(cudaEventCreate(&pc->ev0));
+    CUDA_OK(cudaEventCreate(&pc->ev1));
+    *out = pc;
+    return 0;
+}
+
+static void free_device_state(PC *pc)
+{
+    if (pc->device < 0) return;
+    dev_free(pc->d_gtol); dev_free(pc->d_blocks); dev_free(pc->d_blocks0); dev_free(pc->d_fail); dev_free(pc->d_bc);
+    dev_free(pc->d_w); dev_free(pc->d_mult); dev_free(pc->d_xl); dev_free(pc->d_yl); dev_free(pc->d_xs); dev_free(pc->d_ys);
+    dev_free(pc->d_selfLeaf); dev_free(pc->d_selfRoot); dev_free(pc->d_sendRoot); dev_free(pc->d_recvLeaf);
+    dev_free(pc->d_sendbuf); dev_free(pc->d_recvbuf);
+    if (pc->csr_owned) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); }
+    pc->d_rowptr = nullptr; pc->d_colidx = nullptr; pc->d_vals = nullptr; pc->csr_owned = false;
+    pc->classes.clear(); pc->device_ready = false; pc->setup_done = false;
+}
+
+extern "C" int SSCPatchReset(SSCPatchPC pc)
+{
+    if (!pc) return ssc_set_error(SSC_ERR_ARG_NULL, "null PC");
+    if (pc->device >= 0) {
+        CHK(set_device(pc));
+        cudaStreamSynchronize(pc->stream);
+        free_device_state(pc);
+    }
+    pc->lists = PatchLists(); pc->lists_valid = false; pc->direct_patches = false;
+    pc->plex = HostPlex(); pc->disc = Discretisation(); pc->user = UserPatches();
+    pc->csr_set = false; pc->sf_set = false;
+    return 0;
+}
+
+extern "C" int SSCPatchDestroy(SSCPatchPC *ppc)
+{
+    if (!ppc || !*ppc) return 0;
+    PC *pc = *ppc;
+    if (pc->device < 0) { delete pc; *ppc = nullptr; return 0; }
+    cudaSetDevice(pc->device);
+    cudaStreamSynchronize(pc->stream);
+    free_device_state(pc);
+    if (pc->d_flush) cudaFree(pc->d_flush);
+    for (auto &e : pc->kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (pc->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(pc->comm);
+    cudaEventDestroy(pc->ev0); cudaEventDestroy(pc->ev1);
+    cudaStreamDestroy(pc->stream);
+    delete pc;
+    *ppc = nullptr;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// options
+// ---------------------------------------------------------------------------------------------
+static int parse_bool(const char *v, bool *out)
+{
+    std::string s(v ? v : "");
+    for (auto &c : s) c = (char)tolower(c);
+    if (s == "" || s == "1" || s == "true" || s == "yes" || s == "on") { *out = true; return 0; }
+    if (s == "0" || s == "false" || s == "no" || s == "off") { *out = false; return 0; }
+    return ssc_set_error(SSC_ERR_USER, "cannot read '%s' as a boolean", v);
+}
+
+extern "C" int SSCPatchSetSaveOperators(SSCPatchPC pc, int flg) { pc->save_operators = flg != 0; return 0; }
+extern "C" int SSCPatchSetPartitionOfUnity(SSCPatchPC pc, int flg) { pc->partition_of_unity = flg != 0; return 0; }
+extern "C" int SSCPatchSetSubMatType(SSCPatchPC pc, const char *t)
+{
+    std::string s(t ? t : "");
+    // every PETSc matrix type the reference could be given stores the same numbers; here they all are dense blocks
+    if (s != "dense" && s != "seqdense" && s != "aij" && s != "seqaij")
+        return ssc_set_error(SSC_ERR_SUP, "pc_patch_sub_mat_type '%s' is not supported (dense, seqdense, aij, seqaij)", s.c_str());
+    pc->sub_mat_type = s;
+    return 0;
+}
+
+extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *value)
+{
+    if (!pc || !name_) return ssc_set_error(SSC_ERR_ARG_NULL, "null argument");
+    std::string name(name_);
+    if (!name.empty() && name[0] == '-') name = name.substr(1);
+    const char *v = value ? value : "";
+    if (name == "pc_patch_save_operators") return parse_bool(v, &pc->save_operators);
+    if (name == "pc_patch_partition_of_unity") return parse_bool(v, &pc->partition_of_unity);
+    if (name == "pc_patch_multiplicative") {
+        CHK(parse_bool(v, &pc->multiplicative));
+        if (pc->multiplicative) {   // ssc/libssc.c:1570-1572
+            pc->multiplicative = false;
+            return ssc_set_error(SSC_ERR_USER, "We've removed multiplicative to do BC condensation (for now)");
+        }
+        return 0;
+    }
+    if (name == "pc_patch_construction_dim") {
+        pc->bopt.dim = atoll(v); pc->dim_set = true;
+        if (pc->codim_set) return ssc_set_error(SSC_ERR_USER, "Can only set one of dimension or co-dimension");   // :1576-1578
+        return 0;
+    }
+    if (name == "pc_patch_construction_codim") {
+        pc->bopt.codim = atoll(v); pc->codim_set = true;
+        if (pc->dim_set) return ssc_set_error(SSC_ERR_USER, "Can only set one of dimension or co-dimension");
+        return 0;
+    }
+    if (name == "pc_patch_construction_type") {             // :1580-1603
+        std::string s(v);
+        if (s == "star") pc->bopt.construct_type = SSC_PATCH_STAR;
+        else if (s == "vanka") pc->bopt.construct_type = SSC_PATCH_VANKA;
+        else if (s == "user") pc->bopt.construct_type = SSC_PATCH_USER;
+        else if (s == "python") pc->bopt.construct_type = SSC_PATCH_PYTHON;
+        else return ssc_set_error(SSC_ERR_USER, "Unknown patch construction type");
+        return 0;
+    }
+    if (name == "pc_patch_vanka_dim") { pc->bopt.vankadim = atoll(v); return 0; }
+    if (name == "pc_patch_vanka_space")                       // :1589-1592
+        return ssc_set_error(SSC_ERR_USER, "-pc_patch_vanka_space has been renamed to -pc_patch_exclude_subspace");
+    if (name == "pc_patch_exclude_subspace") { pc->bopt.exclude_subspace = atoll(v); return 0; }
+    if (name == "pc_patch_sub_mat_type") return SSCPatchSetSubMatType(pc, v);
+    if (name == "pc_patch_print_patches") return parse_bool(v, &pc->print_patches);
+    if (name == "pc_patch_symmetrise_sweep") return parse_bool(v, &pc->symmetrise_sweep);
+    if (name == "sub_ksp_type") {
+        if (std::string(v) != "preonly") return ssc_set_error(SSC_ERR_SUP, "sub_ksp_type '%s' is not supported: patch problems are solved directly (preonly)", v);
+        return 0;
+    }
+    if (name == "sub_pc_type") {
+        std::string s(v);
+        if (s == "lu") pc->sub_pc = SSC_SUB_LU;
+        else if (s == "cholesky") pc->sub_pc = SSC_SUB_CHOLESKY;
+        else return ssc_set_error(SSC_ERR_SUP, "sub_pc_type '%s' is not supported (lu, cholesky)", v);
+        return 0;
+    }
+    if (name == "sub_pc_factor_mat_solver_type" || name == "sub_pc_factor_mat_ordering_type") return 0;   // orderings do not change a dense solve
+    if (name == "ssc_keep_dofs_table") return parse_bool(v, &pc->bopt.keep_dofs);
+    if (name == "ssc_keep_patch_operators") return parse_bool(v, &pc->keep_operators);
+    if (name == "ssc_builder_threads") { pc->bopt.nthreads = atoi(v); return 0; }
+    return ssc_set_error(SSC_ERR_USER, "unknown option '%s'", name.c_str());
+}
+
+// ---------------------------------------------------------------------------------------------
+// host inputs
+// ---------------------------------------------------------------------------------------------
+extern "C" int SSCPatchSetPlex(SSCPatchPC pc, SSCInt dim, SSCInt pEnd, const SSCInt *coneOff, const SSCInt *cones,
+                               const SSCInt *depthStart, const SSCInt *depthEnd, const unsigned char *ghost)
+{
+    if (!pc || !coneOff || !depthStart || !depthEnd) return ssc_set_error(SSC_ERR_ARG_NULL, "null argument");
+    HostPlex &P = pc->plex;
+    P.dim = dim; P.pEnd = pEnd;
+    P.coneOff.assign(coneOff, coneOff + pEnd + 1);
+    P.cones.assign(cones, cones + coneOff[pEnd]);
+    P.depthStart.assign(depthStart, depthStart + dim + 1);
+    P.depthEnd.assign(depthEnd, depthEnd + dim + 1);
+    if (ghost) P.ghost.assign(ghost, ghost + pEnd); else P.ghost.clear();
+    // supports = transpose of the cone table
+    P.suppOff.assign(pEnd + 1, 0);
+    for (i64 k = 0; k < (i64)P.cones.size(); ++k) {
+        if (P.cones[k] < 0 || P.cones[k] >= pEnd) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "cone entry outside the chart");
+        P.suppOff[P.cones[k] + 1]++;
+    }
+    for (i64 p = 0; p < pEnd; ++p) P.suppOff[p + 1] += P.suppOff[p];
+    P.supports.resize(P.cones.size());
+    std::vector<i64> fill(P.suppOff.begin(), P.suppOff.end() - 1);
+    for (i64 p = 0; p < pEnd; ++p)
+        for (i64 k = P.coneOff[p]; k < P.coneOff[p + 1]; ++k) P.supports[fill[P.cones[k]]++] = p;
+    P.set = true;
+    pc->lists_valid = false;
+    return 0;
+}
+
+extern "C" int SSCPatchSetCellNumbering(SSCPatchPC pc, const SSCInt *dof, const SSCInt *off)
+{
+    if (!pc->plex.set) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "set the plex before the cell numbering");
+    pc->disc.cnDof.assign(dof, dof + pc->plex.pEnd);
+    pc->disc.cnOff.assign(off, off + pc->plex.pEnd);
+    pc->disc.cn_set = true;
+    pc->lists_valid = false;
+    return 0;
+}
+
+extern "C" int SSCPatchSetDiscretisationInfo(SSCPatchPC pc, SSCInt nsubspaces, const SSCInt *const *secDof,
+                                             const SSCInt *const *secOff, const SSCInt *bs, const SSCInt *nodesPerCell,
+                                             const SSCInt *const *cellNodeMap, const SSCInt *subspaceOffsets,
+                                             SSCInt numGhostBcs, const SSCInt *ghostBcNodes,
+                                             SSCInt numGlobalBcs, const SSCInt *globalBcNodes)
+{
+    if (!pc->plex.set) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "set the plex before the discretisation info");
+    Discretisation &D = pc->disc;
+    D.nsub = nsubspaces; D.totalDofsPerCell = 0;
+    D.secDof.resize(nsubspaces); D.secOff.resize(nsubspaces);
+    D.bs.assign(bs, bs + nsubspaces);
+    D.nodesPerCell.assign(nodesPerCell, nodesPerCell + nsubspaces);
+    D.subspaceOffsets.assign(subspaceOffsets, subspaceOffsets + nsubspaces + 1);
+    D.cellNodeMap.assign(cellNodeMap, cellNodeMap + nsubspaces);
+    for (i64 k = 0; k < nsubspaces; ++k) {
+        D.secDof[k].assign(secDof[k], secDof[k] + pc->plex.pEnd);
+        D.secOff[k].assign(secOff[k], secOff[k] + pc->plex.pEnd);
+        D.totalDofsPerCell += nodesPerCell[k] * bs[k];
+    }
+    D.ghostBcNodes.assign(ghostBcNodes, ghostBcNodes + numGhostBcs);
+    D.globalBcNodes.assign(globalBcNodes, globalBcNodes + numGlobalBcs);
+    D.set = true;
+    pc->globalBc = D.globalBcNodes;
+    pc->nlocal = subspaceOffsets[nsubspaces];
+    if (!pc->sf_set) pc->nowned = pc->nlocal;
+    pc->lists_valid = false; pc->direct_patches = false;
+    return 0;
+}
+
+extern "C" int SSCPatchSetUserPatches(SSCPatchPC pc, SSCInt nuserIS, const SSCInt *userOff, const SSCInt *userPoints,
+                                      SSCInt niter, const SSCInt *iterationSet)
+{
+    pc->user.off.assign(userOff, userOff + nuserIS + 1);
+    pc->user.pts.assign(userPoints, userPoints + userOff[nuserIS]);
+    pc->user.iterationSet.assign(iterationSet, iterationSet + niter);
+    for (i64 v : pc->user.iterationSet)
+        if (v < 0 || v >= nuserIS) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "iteration set entry %lld outside [0,%lld)", (long long)v, (long long)nuserIS);
+    pc->user.set = true;
+    pc->lists_valid = false;
+    return 0;
+}
+
+extern "C" int SSCPatchSetPatches(SSCPatchPC pc, SSCInt npatch, const SSCInt *offsets, const SSCInt *gtol,
+                                  SSCInt nlocal, SSCInt nowned, SSCInt numGlobalBcs, const SSCInt *globalBcNodes)
+{
+    if (!pc || !offsets) return ssc_set_error(SSC_ERR_ARG_NULL, "null argument");
+    PatchLists &L = pc->lists;
+    L = PatchLists();
+    L.npatch = npatch; L.vStart = 0;
+    L.gtolOff.assign(offsets, offsets + npatch + 1);
+    L.gtol.assign(gtol, gtol + offsets[npatch]);
+    L.cellOff.assign(npatch + 1, 0);
+    for (i64 g : L.gtol) if (g < 0 || g >= nlocal) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "patch dof %lld outside [0,%lld)", (long long)g, (long long)nlocal);
+    pc->nlocal = nlocal;
+    if (!pc->sf_set) pc->nowned = nowned;
+    pc->globalBc.assign(globalBcNodes, globalBcNodes + numGlobalBcs);
+    pc->lists_valid = true; pc->direct_patches = true;
+    free_device_state(pc);
+    return 0;
+}
+
+extern "C" int SSCPatchSetStarForest(SSCPatchPC pc, SSCInt nowned, SSCInt nself, const SSCInt *selfLeaf, const SSCInt *selfRoot,
+                                     SSCInt nneigh, const int *neigh, const SSCInt *sendOff, const SSCInt *sendRoot,
+                                     const SSCInt *recvOff, const SSCInt *recvLeaf)
+{
+    pc->nowned = nowned;
+    pc->selfLeaf.assign(selfLeaf, selfLeaf + nself);
+    pc->selfRoot.assign(selfRoot, selfRoot + nself);
+    pc->neigh.assign(neigh, neigh + nneigh);
+    pc->sendOff.assign(sendOff, sendOff + nneigh + 1);
+    pc->sendRoot.assign(sendRoot, sendRoot + sendOff[nneigh]);
+    pc->recvOff.assign(recvOff, recvOff + nneigh + 1);
+    pc->recvLeaf.assign(recvLeaf, recvLeaf + recvOff[nneigh]);
+    pc->sf_set = true;
+    free_device_state(pc);
+    return 0;
+}
+
+extern "C" int SSCCommGetUniqueId(char uniqueId[128])
+{
+    CHK(nccl_load());
+    ncclUniqueId_t id;
+    NCCL_OK(g_nccl.GetUniqueId(&id));
+    memcpy(uniqueId, id.internal, 128);
+    return 0;
+}
+
+extern "C" int SSCPatchCommInit(SSCPatchPC pc, int nranks, int rank, const char uniqueId[128])
+{
+    CHK(nccl_load());
+    CHK(set_device(pc));
+    ncclUniqueId_t id;
+    memcpy(id.internal, uniqueId, 128);
+    NCCL_OK(g_nccl.CommInitRank(&pc->comm, nranks, id, rank));
+    pc->nranks = nranks; pc->rank = rank;
+    return 0;
+}
+
+extern "C" int SSCPatchSetOperatorCSR(SSCPatchPC pc, SSCInt nrows, const SSCInt *rowptr, const int32_t *colidx,
+                                      const double *vals, int memspace)
+{
+    if (!rowptr || !colidx || !vals) return ssc_set_error(SSC_ERR_ARG_NULL, "null CSR array");
+    pc->csr_nrows = nrows; pc->csr_rowptr = rowptr; pc->csr_colidx = colidx; pc->csr_vals = vals;
+    pc->csr_space = memspace; pc->csr_set = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// setup
+// ---------------------------------------------------------------------------------------------
+static void choose_launch_shape(SizeClass &c)
+{
+    const int n = c.n;
+    if (n >= 1024) { c.tp = 1024; c.ppb = 1; return; }
+    if (n > 96) { c.tp = (n + 31) / 32 * 32; c.ppb = 1; return; }
+    c.tp = n <= 8 ? 8 : (n + 7) / 8 * 8;       // sub-warp groups for small patches
+    c.ppb = std::max(1, 192 / c.tp);
+}
+
+// first-time part of PCSetUp_PATCH (ssc/libssc.c:1210-1250): dof lists -> size classes -> device arrays
+static int build_device_lists(PC *pc)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    if (!pc->lists_valid) {
+        CHK(ssc_build_patches(pc->plex, pc->disc, pc->user, pc->bopt, pc->lists));
+        pc->lists_valid = true;
+    }
+    pc->event_ms["PCPATCHCreate"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const PatchLists &L = pc->lists;
+    const i64 np = L.npatch;
+    // stable sort of the non-empty patches by size
+    std::vector<i64> order;
+    order.reserve(np);
+    for (i64 p = 0; p < np; ++p) if (L.gtolOff[p + 1] - L.gtolOff[p] > 0) order.push_back(p);   // ssc/libssc.c:1355-1358
+    std::stable_sort(order.begin(), order.end(), [&](i64 a, i64 b) { return L.gtolOff[a + 1] - L.gtolOff[a] < L.gtolOff[b + 1] - L.gtolOff[b]; });
+    pc->sorted2orig = order;
+    pc->orig2sorted.assign(np, -1);
+    pc->classes.clear();
+    pc->sum_n = 0; pc->sum_n2 = 0; pc->max_n = 0;
+    i64 goff = 0, moff = 0;
+    for (i64 q = 0; q < (i64)order.size(); ++q) {
+        const i64 p = order[q], n = L.gtolOff[p + 1] - L.gtolOff[p];
+        pc->orig2sorted[p] = q;
+        if (pc->classes.empty() || pc->classes.back().n != (int)n) {
+            SizeClass c;
+            c.n = (int)n; c.first = q; c.goff = goff; c.moff = moff;
+            c.stride = (n * n + 15) / 16 * 16;
+            choose_launch_shape(c);
+            pc->classes.push_back(c);
+        }
+        SizeClass &c = pc->classes.back();
+        c.count++;
+        goff += n; moff += c.stride;
+        pc->sum_n += n; pc->sum_n2 += n * n; pc->max_n = std::max(pc->max_n, n);
+    }
+    pc->block_elems = moff;
+    if (pc->nlocal > 2147483647LL) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "local vector too long for 32-bit device indices");
+    // dof lists in sorted order, int32
+    std::vector<int> g32((size_t)pc->sum_n);
+    i64 w = 0;
+    for (i64 q = 0; q < (i64)order.size(); ++q) {
+        const i64 p = order[q];
+        for (i64 k = L.gtolOff[p]; k < L.gtolOff[p + 1]; ++k) g32[w++] = (int)L.gtol[k];
+    }
+    CHK(dev_alloc(&pc->d_gtol, pc->sum_n));
+    if (pc->sum_n) CUDA_OK(cudaMemcpyAsync(pc->d_gtol, g32.data(), (size_t)pc->sum_n * sizeof(int), cudaMemcpyHostToDevice, pc->stream));
+    CUDA_OK(cudaStreamSynchronize(pc->stream));
+    CHK(dev_alloc(&pc->d_fail, (i64)order.size()));
+    // Dirichlet pass-through list, ssc/libssc.c:1408-1413 (only idx < local size)
+    std::vector<i64> bc;
+    for (i64 d : pc->globalBc) if (d >= 0 && d < pc->nowned) bc.push_back(d);
+    pc->nbc = (i64)bc.size();
+    CHK(upload_i32(pc, bc, &pc->d_bc));
+    // iteration multiplicity for user patches (the iteration set may repeat or omit patches, :1347-1351)
+    if (pc->bopt.construct_type >= 2 && pc->user.set && !pc->direct_patches) {
+        std::vector<double> mult(order.size(), 0.0);
+        for (i64 v : pc->user.iterationSet) if (pc->orig2sorted[v] >= 0) mult[pc->orig2sorted[v]] += 1.0;
+        CHK(dev_alloc(&pc->d_mult, (i64)mult.size()));
+        if (!mult.empty()) CUDA_OK(cudaMemcpy(pc->d_mult, mult.data(), mult.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    // star forest
+    const bool identity = !pc->sf_set;
+    if (!identity) {
+        CHK(upload_i32(pc, pc->selfLeaf, &pc->d_selfLeaf));
+        CHK(upload_i32(pc, pc->selfRoot, &pc->d_selfRoot));
+        CHK(upload_i32(pc, pc->sendRoot, &pc->d_sendRoot));
+        CHK(upload_i32(pc, pc->recvLeaf, &pc->d_recvLeaf));
+        CHK(dev_alloc(&pc->d_sendbuf, (i64)std::max(pc->sendRoot.size(), pc->recvLeaf.size())));
+        CHK(dev_alloc(&pc->d_recvbuf, (i64)std::max(pc->sendRoot.size(), pc->recvLeaf.size())));
+        CHK(dev_alloc(&pc->d_xl, pc->nlocal));
+        CHK(dev_alloc(&pc->d_yl, pc->nlocal));
+        if (!pc->neigh.empty() && !pc->comm) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "the star forest names neighbour ranks but SSCPatchCommInit() has not been called");
+    } else if (pc->nowned != pc->nlocal) {
+        return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "nowned (%lld) != nlocal (%lld) but no star forest was set", (long long)pc->nowned, (long long)pc->nlocal);
+    }
+    pc->device_ready = true;
+    return 0;
+}
+
+// halo fill: SFBcast of ssc/libssc.c:1323-1324 (owner values -> local vector incl. ghosts)
+static int sf_bcast(PC *pc, const double *x, double *xl)
+{
+    const i64 nself = (i64)pc->selfLeaf.size();
+    if (nself) { ssc_copy_indexed_kernel<<<grid_for(nself, 256), 256, 0, pc->stream>>>(nself, pc->d_selfLeaf, pc->d_selfRoot, x, xl, 0); pc->launches++; }
+    const i64 ns = (i64)pc->sendRoot.size(), nr = (i64)pc->recvLeaf.size();
+    if (pc->neigh.empty()) return 0;
+    if (ns) { ssc_gather_kernel<<<grid_for(ns, 256), 256, 0, pc->stream>>>(ns, pc->d_sendRoot, x, pc->d_sendbuf); pc->launches++; }
+    NCCL_OK(g_nccl.GroupStart());
+    for (size_t k = 0; k < pc->neigh.size(); ++k) {
+        const i64 s0 = pc->sendOff[k], s1 = pc->sendOff[k + 1], r0 = pc->recvOff[k], r1 = pc->recvOff[k + 1];
+        if (s1 > s0) NCCL_OK(g_nccl.Send(pc->d_sendbuf + s0, (size_t)(s1 - s0), kNcclFloat64, pc->neigh[k], pc->comm, pc->stream));
+        if (r1 > r0) NCCL_OK(g_nccl.Recv(pc->d_recvbuf + r0, (size_t)(r1 - r0), kNcclFloat64, pc->neigh[k], pc->comm, pc->stream));
+    }
+    NCCL_OK(g_nccl.GroupEnd());
+    if (nr) { ssc_scatter_kernel<<<grid_for(nr, 256), 256, 0, pc->stream>>>(nr, pc->d_recvLeaf, pc->d_recvbuf, xl, 0); pc->launches++; }
+    return 0;
+}
+
+// overlap sum: SFReduce(MPI_SUM) of ssc/libssc.c:1399-1400 (local contributions, ghosts included -> owners); y zeroed first (:1396)
+static int sf_reduce(PC *pc, const double *yl, double *y)
+{
+    CUDA_OK(cudaMemsetAsync(y, 0, (size_t)pc->nowned * sizeof(double), pc->stream));
+    const i64 nself = (i64)pc->selfLeaf.size();
+    if (nself) { ssc_copy_indexed_kernel<<<grid_for(nself, 256), 256, 0, pc->stream>>>(nself, pc->d_selfRoot, pc->d_selfLeaf, yl, y, 1); pc->launches++; }
+    if (pc->neigh.empty()) return 0;
+    const i64 ns = (i64)pc->sendRoot.size(), nr = (i64)pc->recvLeaf.size();
+    if (nr) { ssc_gather_kernel<<<grid_for(nr, 256), 256, 0, pc->stream>>>(nr, pc->d_recvLeaf, yl, pc->d_recvbuf); pc->launches++; }
+    NCCL_OK(g_nccl.GroupStart());
+    for (size_t k = 0; k < pc->neigh.size(); ++k) {
+        const i64 s0 = pc->sendOff[k], s1 = pc->sendOff[k + 1], r0 = pc->recvOff[k], r1 = pc->recvOff[k + 1];
+        if (r1 > r0) NCCL_OK(g_nccl.Send(pc->d_recvbuf + r0, (size_t)(r1 - r0), kNcclFloat64, pc->neigh[k], pc->comm, pc->stream));
+        if (s1 > s0) NCCL_OK(g_nccl.Recv(pc->d_sendbuf + s0, (size_t)(s1 - s0), kNcclFloat64, pc->neigh[k], pc->comm, pc->stream));
+    }
+    NCCL_OK(g_nccl.GroupEnd());
+    if (ns) { ssc_scatter_kernel<<<grid_for(ns, 256), 256, 0, pc->stream>>>(ns, pc->d_sendRoot, pc->d_sendbuf, y, 1); pc->launches++; }
+    return 0;
+}
+
+static int upload_csr(PC *pc)
+{
+    if (!pc->csr_set) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "Must call SSCPatchSetOperatorCSR() to set the operator");   // cf. ssc/libssc.c:1131-1133
+    if (pc->csr_owned) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); pc->csr_owned = false; }
+    if (pc->csr_nrows < pc->nlocal) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "operator has %lld rows but the local vector has %lld dofs", (long long)pc->csr_nrows, (long long)pc->nlocal);
+    if (pc->csr_space == SSC_MEM_DEVICE) {
+        pc->d_rowptr = const_cast<i64 *>(pc->csr_rowptr); pc->d_colidx = const_cast<int *>(pc->csr_colidx); pc->d_vals = const_cast<double *>(pc->csr_vals);
+        return 0;
+    }
+    const i64 nnz = pc->csr_rowptr[pc->csr_nrows];
+    CHK(dev_alloc(&pc->d_rowptr, pc->csr_nrows + 1));
+    CHK(dev_alloc(&pc->d_colidx, nnz));
+    CHK(dev_alloc(&pc->d_vals, nnz));
+    pc->csr_owned = true;
+    CUDA_OK(cudaMemcpyAsync(pc->d_rowptr, pc->csr_rowptr, (size_t)(pc->csr_nrows + 1) * sizeof(i64), cudaMemcpyHostToDevice, pc->stream));
+    CUDA_OK(cudaMemcpyAsync(pc->d_colidx, pc->csr_colidx, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, pc->stream));
+    CUDA_OK(cudaMemcpyAsync(pc->d_vals, pc->csr_vals, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, pc->stream));
+    return 0;
+}
+
+static size_t invert_smem_bytes(int n, bool shared)
+{
+    const size_t ld = (size_t)(n | 1);
+    return (2 * (size_t)n + 32 + ((34 + (size_t)n + 1) / 2 + 1) + (shared ? (size_t)n * ld : 0)) * sizeof(double);
+}
+
+// extract + factor for patches [q0, q1) of class c into `blocks` (class-relative addressing through moff)
+static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double *blocks, int *fail, bool time_it)
+{
+    const i64 cnt = q1 - q0;
+    if (cnt <= 0) return 0;
+    const int n = c.n;
+    int H = 32;
+    while (H < 2 * n) H <<= 1;
+    const int bd = 128, nw = bd / 32;
+    const size_t smem_e = (size_t)H * 2 * sizeof(int) + (size_t)nw * n * sizeof(double);
+    if (smem_e > 200 * 1024) return ssc_set_error(SSC_ERR_SUP, "patch with %d dofs is too large for the extract kernel", n);
+    if (smem_e > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+    if (time_it) CUDA_OK(cudaEventRecord(pc->ev0, pc->stream));
+    const int grid_e = (int)std::min<i64>(cnt, (i64)pc->sm_count * 64);
+    ssc_extract_kernel<<<grid_e, bd, smem_e, pc->stream>>>((const ll *)pc->d_rowptr, pc->d_colidx, pc->d_vals, pc->d_gtol + c.goff + (q0 - c.first) * n,
+                                                          blocks, n, c.stride, cnt, H);
+    pc->launches++;
+    CUDA_OK(cudaGetLastError());
+    if (time_it) {
+        CUDA_OK(cudaEventRecord(pc->ev1, pc->stream));
+        CUDA_OK(cudaEventSynchronize(pc->ev1));
+        float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, pc->ev0, pc->ev1));
+        pc->event_ms["PCPATCHComputeOp"] += ms;
+    }
+    if (pc->keep_operators && pc->d_blocks0 && blocks == pc->d_blocks + c.moff)
+        CUDA_OK(cudaMemcpyAsync(pc->d_blocks0 + c.moff, blocks, (size_t)cnt * c.stride * sizeof(double), cudaMemcpyDeviceToDevice, pc->stream));
+    // factor
+    const bool shared = n <= 168;
+    const size_t smem_f = invert_smem_bytes(n, shared);
+    const int bdf = !shared ? 1024 : (n <= 32 ? 128 : (n <= 64 ? 256 : 512));
+    const bool pivot = pc->sub_pc == SSC_SUB_LU;
+    if (time_it) CUDA_OK(cudaEventRecord(pc->ev0, pc->stream));
+    const int grid_f = (int)std::min<i64>(cnt, (i64)pc->sm_count * 16);
+#define LAUNCH_INV(P, S)                                                                                              \
+    do {                                                                                                              \
+        if (smem_f > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_invert_kernel<P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
+        ssc_invert_kernel<P, S><<<grid_f, bdf, smem_f, pc->stream>>>(blocks, n, c.stride, cnt, fail);                   \
+    } while (0)
+    if (pivot && shared) LAUNCH_INV(true, true);
+    else if (pivot) LAUNCH_INV(true, false);
+    else if (shared) LAUNCH_INV(false, true);
+    else LAUNCH_INV(false, false);
+#undef LAUNCH_INV
+    pc->launches++;
+    CUDA_OK(cudaGetLastError());
+    if (time_it) {
+        CUDA_OK(cudaEventRecord(pc->ev1, pc->stream));
+        CUDA_OK(cudaEventSynchronize(pc->ev1));
+        float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, pc->ev0, pc->ev1));
+        pc->event_ms["PCPATCHSolve"] += ms;
+    }
+    return 0;
+}
+
+static int compute_weights(PC *pc)
+{
+    // ssc/libssc.c:1254-1284: scatter ones through every patch, reduce to owners, reciprocal
+    dev_free(pc->d_w);
+    CHK(dev_alloc(&pc->d_w, pc->nowned));
+    double *ml = pc->sf_set ? pc->d_yl : pc->d_w;
+    CUDA_OK(cudaMemsetAsync(ml, 0, (size_t)pc->nlocal * sizeof(double), pc->stream));
+    if (pc->sum_n) { ssc_count_kernel<<<grid_for(pc->sum_n, 256), 256, 0, pc->stream>>>(pc->d_gtol, pc->sum_n, ml); pc->launches++; }
+    if (pc->sf_set) CHK(sf_reduce(pc, ml, pc->d_w));
+    ssc_reciprocal_kernel<<<grid_for(pc->nowned, 256), 256, 0, pc->stream>>>(pc->nowned, pc->d_w);
+    pc->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int SSCPatchSetUp(SSCPatchPC pc)
+{
+    if (!pc) return ssc_set_error(SSC_ERR_ARG_NULL, "null PC");
+    CHK(set_device(pc));
+    if (pc->sub_ksp_type != "preonly") return ssc_set_error(SSC_ERR_SUP, "only preonly patch solves are supported");
+    const bool first = !pc->device_ready;
+    if (first) CHK(build_device_lists(pc));
+    if (first && pc->partition_of_unity) CHK(compute_weights(pc));      // only on the first setup, ssc/libssc.c:1254
+    CHK(upload_csr(pc));
+    pc->event_ms["PCPATCHComputeOp"] = 0; pc->event_ms["PCPATCHSolve"] = 0;
+    if (pc->save_operators) {
+        if (!pc->d_blocks) CHK(dev_alloc(&pc->d_blocks, pc->block_elems));
+        if (pc->keep_operators && !pc->d_blocks0) CHK(dev_alloc(&pc->d_blocks0, pc->block_elems));
+        for (const SizeClass &c : pc->classes)
+            CHK(extract_and_invert(pc, c, c.first, c.first + c.count, pc->d_blocks + c.moff, pc->d_fail + c.first, true));
+        CUDA_OK(cudaStreamSynchronize(pc->stream));
+        // per-patch failure flags: the reference would surface KSP_DIVERGED_PCSETUP_FAILED (dead code ssc/libssc.c:1439-1442)
+        std::vector<int> fail(pc->sorted2orig.size());
+        if (!fail.empty()) CUDA_OK(cudaMemcpy(fail.data(), pc->d_fail, fail.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        pc->failed = 0;
+        i64 firstbad = -1;
+        for (size_t q = 0; q < fail.size(); ++q) if (fail[q]) { if (firstbad < 0) firstbad = pc->sorted2orig[q]; pc->failed++; }
+        if (pc->csr_owned) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); pc->csr_owned = false; }
+        if (pc->failed) return ssc_set_error(SSC_ERR_MAT_LU_ZRPVT, "%lld patch operators could not be factorised (first: patch %lld)%s", (long long)pc->failed,
+                                             (long long)firstbad, pc->sub_pc == SSC_SUB_CHOLESKY ? "; sub_pc_type cholesky needs SPD blocks" : "");
+    } else {
+        CUDA_OK(cudaStreamSynchronize(pc->stream));
+    }
+    pc->setup_done = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// apply
+// ---------------------------------------------------------------------------------------------
+static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const double *blocks, const double *xl, double *yl, double scale)
+{
+    const i64 cnt = q1 - q0;
+    if (cnt <= 0) return 0;
+    const int threads = std::max(32, (c.tp * c.ppb + 31) / 32 * 32);
+    const size_t smem = (size_t)c.ppb * c.n * sizeof(double);
+    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const i64 grid = (cnt + c.ppb - 1) / c.ppb;
+    ssc_apply_kernel<<<(unsigned)grid, threads, smem, pc->stream>>>(blocks, c.stride, pc->d_gtol + c.goff + (q0 - c.first) * c.n, c.n, cnt, c.tp, c.ppb,
+                                                                   xl, yl, scale, pc->d_mult ? pc->d_mult + q0 : nullptr);
+    pc->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int apply_device(PC *pc, const double *x, double *y)
+{
+    if (!pc->setup_done) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "SSCPatchSetUp() has not been called");
+    const bool identity = !pc->sf_set;
+    const double *xl = x;
+    double *yl = y;
+    if (!identity) {                                        // ssc/libssc.c:1321-1326
+        CHK(sf_bcast(pc, x, pc->d_xl));
+        xl = pc->d_xl; yl = pc->d_yl;
+    }
+    CUDA_OK(cudaMemsetAsync(yl, 0, (size_t)pc->nlocal * sizeof(double), pc->stream));   // :1334
+    const double scale = pc->symmetrise_sweep ? 2.0 : 1.0;   // the second sweep re-adds the same corrections, :1336-1343
+    cudaEvent_t k0 = nullptr, k1 = nullptr;
+    if (pc->ktimer) {
+        if (pc->kev_used == pc->kev.size()) {
+            cudaEvent_t a, b;
+            CUDA_OK(cudaEventCreate(&a)); CUDA_OK(cudaEventCreate(&b));
+            pc->kev.push_back({a, b});
+        }
+        k0 = pc->kev[pc->kev_used].first; k1 = pc->kev[pc->kev_used].second; pc->kev_used++;
+        CUDA_OK(cudaEventRecord(k0, pc->stream));
+    }
+    if (pc->save_operators) {
+        for (const SizeClass &c : pc->classes) CHK(launch_apply_class(pc, c, c.first, c.first + c.count, pc->d_blocks + c.moff, xl, yl, scale));
+    } else {
+        // -pc_patch_save_operators false: rebuild, factorise, use and drop every patch operator inside the apply
+        // (ssc/libssc.c:1363-1382), in batches that fit a bounded scratch buffer
+        const i64 budget = (i64)1 << 27;   // doubles (1 GiB)
+        for (const SizeClass &c : pc->classes) {
+            const i64 per = std::max<i64>(1, budget / c.stride);
+            if (!pc->d_blocks) CHK(dev_alloc(&pc->d_blocks, std::max<i64>(budget, pc->max_n * pc->max_n + 16)));
+            for (i64 q0 = c.first; q0 < c.first + c.count; q0 += per) {
+                const i64 q1 = std::min(c.first + c.count, q0 + per);
+                SizeClass sub = c; sub.first = q0; sub.goff = c.goff + (q0 - c.first) * c.n; sub.moff = 0;
+                CHK(extract_and_invert(pc, sub, q0, q1, pc->d_blocks, pc->d_fail + q0, false));
+                CHK(launch_apply_class(pc, sub, q0, q1, pc->d_blocks, xl, yl, scale));
+            }
+        }
+    }
+    if (pc->ktimer) CUDA_OK(cudaEventRecord(k1, pc->stream));
+    if (!identity) CHK(sf_reduce(pc, yl, y));                // :1396-1401
+    if (pc->nbc) { ssc_bc_kernel<<<grid_for(pc->nbc, 256), 256, 0, pc->stream>>>(pc->d_bc, pc->nbc, x, y); pc->launches++; }   // :1404-1413
+    if (pc->partition_of_unity) {                            // :1418-1421
+        if (!pc->d_w) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "partition of unity was switched on after the first setup");
+        ssc_scale_kernel<<<grid_for(pc->nowned, 256), 256, 0, pc->stream>>>(pc->nowned, pc->d_w, y); pc->launches++;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int SSCPatchApply(SSCPatchPC pc, const double *x, double *y, int memspace)
+{
+    if (!pc || !x || !y) return ssc_set_error(SSC_ERR_ARG_NULL, "null argument");
+    CHK(set_device(pc));
+    if (memspace == SSC_MEM_DEVICE) return apply_device(pc, x, y);
+    if (!pc->d_xs) { CHK(dev_alloc(&pc->d_xs, pc->nowned)); CHK(dev_alloc(&pc->d_ys, pc->nowned)); }
+    CUDA_OK(cudaMemcpyAsync(pc->d_xs, x, (size_t)pc->nowned * sizeof(double), cudaMemcpyHostToDevice, pc->stream));
+    CHK(apply_device(pc, pc->d_xs, pc->d_ys));
+    CUDA_OK(cudaMemcpyAsync(y, pc->d_ys, (size_t)pc->nowned * sizeof(double), cudaMemcpyDeviceToHost, pc->stream));
+    CUDA_OK(cudaStreamSynchronize(pc->stream));
+    return 0;
+}
+
+extern "C" int SSCPatchApplyTranspose(SSCPatchPC, const double *, double *, int)
+{
+    // pc->ops->applytranspose = 0 in the reference (ssc/libssc.c:1715) => PETSc raises PETSC_ERR_SUP
+    return ssc_set_error(SSC_ERR_SUP, "PC does not have apply transpose");
+}
+
+extern "C" int SSCPatchSynchronize(SSCPatchPC pc)
+{
+    CHK(set_device(pc));
+    CUDA_OK(cudaStreamSynchronize(pc->stream));
+    return 0;
+}
+
+extern "C" int SSCPatchView(SSCPatchPC pc, char *buf, SSCInt len)
+{
+    // the lines of PCView_PATCH ssc/libssc.c:1637-1667
+    std::string s;
+    char line[256];
+    snprintf(line, sizeof line, "  Subspace Correction preconditioner with %lld patches\n", (long long)pc->lists.npatch); s += line;
+    s += pc->multiplicative ? "  Schwarz type: multiplicative\n" : "  Schwarz type: additive\n";
+    s += pc->partition_of_unity ? "  Weighting by partition of unity\n" : "  Not weighting by partition of unity\n";
+    s += pc->symmetrise_sweep ? "  Symmetrising sweep (start->end, then end->start)\n" : "  Not symmetrising sweep\n";
+    s += !pc->save_operators ? "  Not saving patch operators (rebuilt every PCApply)\n" : "  Saving patch operators (rebuilt every PCSetUp)\n";
+    if (pc->bopt.construct_type == SSC_PATCH_STAR) s += "  Patch construction operator: star\n";
+    else if (pc->bopt.construct_type == SSC_PATCH_VANKA) s += "  Patch construction operator: Vanka\n";
+    else s += "  Patch construction operator: user-specified\n";
+    s += "  KSP on patches (all same):\n";
+    if (pc->setup_done) {
+        snprintf(line, sizeof line, "    KSP Object: type preonly; PC Object: type %s (dense fp64 blocks, stored inverse, sm_100a)\n", pc->sub_pc == SSC_SUB_LU ? "lu" : "cholesky"); s += line;
+        snprintf(line, sizeof line, "    %zu size classes, max patch size %lld, %lld patch dofs, %.3f GB of blocks on device %d\n", pc->classes.size(), (long long)pc->max_n,
+                 (long long)pc->sum_n, pc->block_elems * 8.0 / 1e9, pc->device); s += line;
+    } else {
+        s += "    KSP not yet set.\n";
+    }
+    if (len > 0) { strncpy(buf, s.c_str(), (size_t)len - 1); buf[len - 1] = 0; }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------------
+extern "C" int SSCPatchGetSize(SSCPatchPC pc, const char *what, SSCInt *value)
+{
+    std::string w(what);
+    i64 nnz = 0;
+    if (w == "npatch") *value = pc->lists.npatch;
+    else if (w == "nlocal") *value = pc->nlocal;
+    else if (w == "nowned") *value = pc->nowned;
+    else if (w == "sum_n") *value = pc->sum_n;
+    else if (w == "sum_n2") *value = pc->sum_n2;
+    else if (w == "max_n") *value = pc->max_n;
+    else if (w == "num_cells") *value = (i64)pc->lists.cells.size();
+    else if (w == "num_gtol") *value = (i64)pc->lists.gtol.size();
+    else if (w == "num_dofs") *value = (i64)pc->lists.dofs.size();
+    else if (w == "num_classes") *value = (i64)pc->classes.size();
+    else if (w == "block_bytes") *value = pc->block_elems * 8;
+    else if (w == "bytes_apply") *value = 8 * pc->sum_n2 + (4 + 8 + 8) * pc->sum_n + 16 * pc->nowned;
+    else if (w == "bytes_extract") { if (pc->csr_set && pc->csr_space == SSC_MEM_HOST) nnz = pc->csr_rowptr[pc->csr_nrows]; *value = 12 * nnz + 8 * (pc->nlocal + 1) + 4 * pc->sum_n + 8 * pc->sum_n2; }
+    else if (w == "flops_factor") { i64 f = 0; for (auto &c : pc->classes) f += 2 * c.count * (i64)c.n * c.n * c.n; *value = f; }
+    else if (w == "failed_patches") *value = pc->failed;
+    else if (w == "gpu_launches") *value = pc->launches;
+    else return ssc_set_error(SSC_ERR_USER, "unknown size '%s'", what);
+    return 0;
+}
+
+static int need_lists(PC *pc)
+{
+    if (pc->lists_valid) return 0;
+    CHK(ssc_build_patches(pc->plex, pc->disc, pc->user, pc->bopt, pc->lists));
+    pc->lists_valid = true;
+    return 0;
+}
+// host-only: build (if needed) the dof lists without touching the device
+extern "C" int SSCPatchBuildPatches(SSCPatchPC pc) { return need_lists(pc); }
+
+extern "C" int SSCPatchGetPatches(SSCPatchPC pc, SSCInt *gtolOffsets, SSCInt *gtol)
+{
+    CHK(need_lists(pc));
+    if (gtolOffsets) std::copy(pc->lists.gtolOff.begin(), pc->lists.gtolOff.end(), gtolOffsets);
+    if (gtol) std::copy(pc->lists.gtol.begin(), pc->lists.gtol.end(), gtol);
+    return 0;
+}
+extern "C" int SSCPatchGetCells(SSCPatchPC pc, SSCInt *cellOffsets, SSCInt *cells)
+{
+    CHK(need_lists(pc));
+    if (cellOffsets) std::copy(pc->lists.cellOff.begin(), pc->lists.cellOff.end(), cellOffsets);
+    if (cells) std::copy(pc->lists.cells.begin(), pc->lists.cells.end(), cells);
+    return 0;
+}
+extern "C" int SSCPatchGetDofs(SSCPatchPC pc, SSCInt *dofs)
+{
+    if (!pc->bopt.keep_dofs) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "option ssc_keep_dofs_table is off");
+    CHK(need_lists(pc));
+    std::copy(pc->lists.dofs.begin(), pc->lists.dofs.end(), dofs);
+    return 0;
+}
+
+extern "C" int SSCPatchGetPatchMatrix(SSCPatchPC pc, SSCInt p, int which, double *out)
+{
+    CHK(set_device(pc));
+    if (!pc->setup_done || !pc->save_operators) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "patch blocks are only held after SetUp with save_operators");
+    if (p < 0 || p >= pc->lists.npatch) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "Asked for operator index is invalid");   // ssc/libssc.c:1069-1071
+    const i64 q = pc->orig2sorted[p];
+    if (q < 0) return 0;
+    const double *src = which == 0 ? pc->d_blocks0 : pc->d_blocks;
+    if (!src) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "unfactored blocks are only kept with option ssc_keep_patch_operators");
+    for (const SizeClass &c : pc->classes) {
+        if (q >= c.first && q < c.first + c.count) {
+            const i64 n = c.n;
+            std::vector<double> tmp((size_t)(n * n));
+            CUDA_OK(cudaStreamSynchronize(pc->stream));
+            CUDA_OK(cudaMemcpy(tmp.data(), src + c.moff + (q - c.first) * c.stride, (size_t)(n * n) * sizeof(double), cudaMemcpyDeviceToHost));
+            if (which == 0) std::copy(tmp.begin(), tmp.end(), out);
+            else for (i64 i = 0; i < n; ++i) for (i64 j = 0; j < n; ++j) out[i * n + j] = tmp[(size_t)(j * n + i)];   // stored transposed
+            return 0;
+        }
+    }
+    return ssc_set_error(SSC_ERR_LIB, "patch %lld not found in any size class", (long long)p);
+}
+
+extern "C" int SSCPatchGetDofWeights(SSCPatchPC pc, double *w)
+{
+    CHK(set_device(pc));
+    if (!pc->d_w) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "partition of unity is off");
+    CUDA_OK(cudaStreamSynchronize(pc->stream));
+    CUDA_OK(cudaMemcpy(w, pc->d_w, (size_t)pc->nowned * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int SSCPatchGetEventTime(SSCPatchPC pc, const char *event, double *ms)
+{
+    auto it = pc->event_ms.find(event);
+    *ms = it == pc->event_ms.end() ? 0.0 : it->second;
+    return 0;
+}
+
+extern "C" int SSCPatchKernelTimerReset(SSCPatchPC pc, int enable)
+{
+    CHK(set_device(pc));
+    CUDA_OK(cudaStreamSynchronize(pc->stream));
+    pc->ktimer = enable != 0; pc->kev_used = 0; pc->ktimer_ms = 0; pc->ktimer_n = 0;
+    return 0;
+}
+extern "C" int SSCPatchKernelTimerRead(SSCPatchPC pc, double *total_ms, SSCInt *napply)
+{
+    CHK(set_device(pc));
+    CUDA_OK(cudaStreamSynchronize(pc->stream));
+    double tot = 0;
+    for (size_t i = 0; i < pc->kev_used; ++i) { float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, pc->kev[i].first, pc->kev[i].second)); tot += ms; }
+    *total_ms = tot; *napply = (i64)pc->kev_used;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device plumbing
+// ---------------------------------------------------------------------------------------------
+extern "C" int SSCDeviceMalloc(SSCPatchPC pc, SSCInt bytes, void **ptr) { CHK(set_device(pc)); unsigned char *p = nullptr; CHK(dev_alloc(&p, bytes)); *ptr = p; return 0; }
+extern "C" int SSCDeviceFree(SSCPatchPC pc, void *ptr) { CHK(set_device(pc)); CUDA_OK(cudaFree(ptr)); return 0; }
+extern "C" int SSCHostAlloc(SSCPatchPC pc, SSCInt bytes, void **ptr) { CHK(set_device(pc)); CUDA_OK(cudaMallocHost(ptr, (size_t)std::max<i64>(bytes, 1))); return 0; }
+extern "C" int SSCHostFree(SSCPatchPC pc, void *ptr) { CHK(set_device(pc)); CUDA_OK(cudaFreeHost(ptr)); return 0; }
+extern "C" int SSCMemcpy(SSCPatchPC pc, void *dst, const void *src, SSCInt bytes, int dstSpace, int srcSpace)
+{
+    CHK(set_device(pc));
+    cudaMemcpyKind kind = dstSpace == SSC_MEM_DEVICE ? (srcSpace == SSC_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
+                                                     : (srcSpace == SSC_MEM_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
+    CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)bytes, kind, pc->stream));
+    CUDA_OK(cudaStreamSynchronize(pc->stream));
+    return 0;
+}
+extern "C" int SSCDeviceFlushL2(SSCPatchPC pc)
+{
+    CHK(set_device(pc));
+    const size_t bytes = (size_t)256 << 20;
+    if (!pc->d_flush) CUDA_OK(cudaMalloc(&pc->d_flush, bytes));
+    ssc_fill_kernel<<<148 * 8, 256, 0, pc->stream>>>((ll)(bytes / 8), (double *)pc->d_flush, 1.0);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" int SSCEventCreate(SSCPatchPC pc, void **ev) { CHK(set_device(pc)); cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); *ev = e; return 0; }
+extern "C" int SSCEventRecord(SSCPatchPC pc, void *ev) { CHK(set_device(pc)); CUDA_OK(cudaEventRecord((cudaEvent_t)ev, pc->stream)); return 0; }
+extern "C" int SSCEventElapsed(SSCPatchPC pc, void *start, void *stop, double *ms)
+{
+    CHK(set_device(pc));
+    CUDA_OK(cudaEventSynchronize((cudaEvent_t)stop));
+    float f = 0; CUDA_OK(cudaEventElapsedTime(&f, (cudaEvent_t)start, (cudaEvent_t)stop));
+    *ms = f;
+    return 0;
+}
+extern "C" int SSCEventDestroy(SSCPatchPC pc, void *ev) { CHK(set_device(pc)); CUDA_OK(cudaEventDestroy((cudaEvent_t)ev)); return 0; }

@@ -1,0 +1,282 @@
+// sm_100a kernels of the patch preconditioner.  One file so that every launch site sees the same layouts.
+//
+// Layout in HBM (DESIGN.md "data layout"):
+//   * patches are sorted by size n into classes; inside a class patch q has its dof list at
+//     gtol[goff + q*n .. +n) (int32) and its dense block at blocks[moff + q*stride .. + n*n) (fp64),
+//     stride = n*n rounded up to 16 doubles so every block starts on a 128-byte line.
+//   * after setup a block holds S = (B^-1)^T row-major, i.e. S[j*n + i] = (B^-1)[i][j]: in the apply kernel
+//     thread i of a patch reads S[j*n + i] for j = 0..n-1, so a warp reads consecutive doubles (coalesced),
+//     every byte of the block is read exactly once, and no cross-thread reduction is needed.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+typedef long long ll;
+
+__device__ __forceinline__ unsigned hash_dof(int key) { return (unsigned)key * 2654435761u; }
+
+// ---------------------------------------------------------------------------------------------
+// K1 extract: B_p[i][j] = A[gtol_p[i], gtol_p[j]]   (replaces MatZeroEntries + callback assembly,
+// ssc/libssc.c:1286-1291, :1120-1156).  One CTA per patch; a shared-memory hash maps global column -> patch
+// column; each warp owns one output row at a time, accumulates it in shared memory and stores it coalesced.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ssc_extract_kernel(const ll *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals,
+                   const int *__restrict__ gtol, double *__restrict__ blocks, int n, ll stride, ll count, int H)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *keys = reinterpret_cast<int *>(smem_raw);
+    int *slotval = keys + H;
+    double *rowbuf = reinterpret_cast<double *>(slotval + H);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
+        const int *g = gtol + p * n;
+        for (int t = tid; t < H; t += blockDim.x) keys[t] = -1;
+        __syncthreads();
+        for (int t = tid; t < n; t += blockDim.x) {
+            const int key = g[t];
+            unsigned s = hash_dof(key) & (H - 1);
+            while (true) {
+                const int prev = atomicCAS(&keys[s], -1, key);
+                if (prev == -1 || prev == key) { slotval[s] = t; break; }
+                s = (s + 1) & (H - 1);
+            }
+        }
+        __syncthreads();
+        double *B = blocks + p * stride;
+        double *rb = rowbuf + warp * n;
+        for (int i = warp; i < n; i += nwarps) {
+            for (int t = lane; t < n; t += 32) rb[t] = 0.0;
+            __syncwarp();
+            const int grow = g[i];
+            const ll a = rowptr[grow], b = rowptr[grow + 1];
+            for (ll k = a + lane; k < b; k += 32) {
+                const int col = colidx[k];
+                unsigned s = hash_dof(col) & (H - 1);
+                int kk;
+                while ((kk = keys[s]) != -1) {
+                    if (kk == col) { atomicAdd(&rb[slotval[s]], vals[k]); break; }
+                    s = (s + 1) & (H - 1);
+                }
+            }
+            __syncwarp();
+            for (int t = lane; t < n; t += 32) B[(ll)i * n + t] = rb[t];
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 factor: in-place Gauss-Jordan inversion, one CTA per patch.  With kPivot the pivot of step k is the
+// largest entry of column k among rows >= k (partial pivoting: -sub_pc_type lu); without it the diagonal is
+// used (SPD blocks: -sub_pc_type cholesky).  The block is loaded TRANSPOSED, so what is inverted is B^T and
+// what is stored back is S = (B^T)^-1 = (B^-1)^T, the layout the apply kernel streams.
+// kShared: the working copy lives in shared memory (n <= 168); otherwise the block is inverted in place in
+// global memory (L2-resident) and transposed afterwards.
+// ---------------------------------------------------------------------------------------------
+template <bool kPivot>
+__device__ __forceinline__ int gauss_jordan(double *A, int n, int ld, double *rowv, double *colv, int *piv,
+                                            double *redv, int *redi)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    // thread -> fixed column, strided rows: the pivot-row entry stays in a register, the multiplier is a broadcast
+    const int ncol_threads = n < (int)blockDim.x ? n : (int)blockDim.x;
+    const int rgroups = blockDim.x / ncol_threads;          // >= 1
+    const int mycol = tid % ncol_threads, myrg = tid / ncol_threads;
+    int fail = 0;
+    for (int k = 0; k < n; ++k) {
+        int p = k;
+        if (kPivot) {
+            double best = -1.0; int bi = k;
+            for (int i = k + tid; i < n; i += blockDim.x) {
+                const double v = fabs(A[(ll)i * ld + k]);
+                if (v > best) { best = v; bi = i; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, best, o);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) { redv[warp] = best; redi[warp] = bi; }
+            __syncthreads();
+            if (warp == 0) {
+                best = lane < nwarps ? redv[lane] : -1.0; bi = lane < nwarps ? redi[lane] : n;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_down_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                }
+                if (lane == 0) { redi[32] = bi; piv[k] = bi; }
+            }
+            __syncthreads();
+            p = redi[32];
+            if (p != k) {
+                for (int j = tid; j < n; j += blockDim.x) {
+                    const double a = A[(ll)k * ld + j];
+                    A[(ll)k * ld + j] = A[(ll)p * ld + j];
+                    A[(ll)p * ld + j] = a;
+                }
+                __syncthreads();
+            }
+        }
+        const double d = A[(ll)k * ld + k];
+        if (!(fabs(d) > 0.0) || (!kPivot && !(d > 0.0))) { fail = 1; break; }   // uniform across the CTA
+        const double dinv = 1.0 / d;
+        __syncthreads();
+        for (int j = tid; j < n; j += blockDim.x) {
+            rowv[j] = A[(ll)k * ld + j] * dinv;
+            colv[j] = A[(ll)j * ld + k];
+        }
+        __syncthreads();
+        for (int j = mycol; j < n && myrg < rgroups; j += ncol_threads) {
+            const double r = rowv[j];
+            if (j == k) {
+                for (int i = myrg; i < n; i += rgroups) A[(ll)i * ld + j] = (i == k) ? dinv : -colv[i] * dinv;
+            } else {
+                for (int i = myrg; i < n; i += rgroups) {
+                    if (i == k) A[(ll)i * ld + j] = r;
+                    else A[(ll)i * ld + j] = fma(-colv[i], r, A[(ll)i * ld + j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (kPivot && !fail) {
+        // (P M)^-1 = M^-1 P^T: undo the row exchanges as column exchanges, last first
+        for (int k = n - 1; k >= 0; --k) {
+            const int p = piv[k];
+            if (p != k) {
+                for (int i = tid; i < n; i += blockDim.x) {
+                    const double a = A[(ll)i * ld + k];
+                    A[(ll)i * ld + k] = A[(ll)i * ld + p];
+                    A[(ll)i * ld + p] = a;
+                }
+                __syncthreads();
+            }
+        }
+    }
+    return fail;
+}
+
+template <bool kPivot, bool kShared>
+__global__ void __launch_bounds__(1024)
+ssc_invert_kernel(double *__restrict__ blocks, int n, ll stride, ll count, int *__restrict__ fail_flags)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ld = kShared ? (n | 1) : n;
+    double *rowv = reinterpret_cast<double *>(smem_raw);
+    double *colv = rowv + n;
+    double *redv = colv + n;
+    int *redi = reinterpret_cast<int *>(redv + 32);
+    int *piv = redi + 34;
+    double *As = reinterpret_cast<double *>(smem_raw) + 2 * n + 32 + ((34 + n + 1) / 2 + 1);
+    const int tid = threadIdx.x;
+    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
+        double *B = blocks + p * stride;
+        double *A = kShared ? As : B;
+        if (kShared) {
+            for (int e = tid; e < n * n; e += blockDim.x) { const int i = e / n, j = e - i * n; As[(ll)j * ld + i] = B[e]; }
+        }
+        __syncthreads();
+        const int fail = gauss_jordan<kPivot>(A, n, ld, rowv, colv, piv, redv, redi);
+        __syncthreads();
+        if (tid == 0) fail_flags[p] = fail;
+        if (kShared) {
+            for (int e = tid; e < n * n; e += blockDim.x) { const int i = e / n, j = e - i * n; B[e] = As[(ll)i * ld + j]; }
+        } else {
+            // in-place transpose of the n x n block
+            for (ll e = tid; e < (ll)n * n; e += blockDim.x) {
+                const int i = (int)(e / n), j = (int)(e - (ll)i * n);
+                if (i < j) { const double a = B[(ll)i * n + j]; B[(ll)i * n + j] = B[(ll)j * n + i]; B[(ll)j * n + i] = a; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3+K4+K5 apply: gather -> stored-inverse product -> scatter-add, fused (ssc/libssc.c:1359-1386).
+// `ppb` patches per CTA, `tp` threads per patch (tp >= n except for very large patches, where a thread
+// owns several rows).  The residual entries of a patch are gathered into shared memory (one index load and
+// one x load per patch dof), then thread i streams column i of S with evict-first loads and adds its
+// result into y with one fp64 reduction (RED.E.ADD.F64 at L2).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+ssc_apply_kernel(const double *__restrict__ S, ll stride, const int *__restrict__ gtol, int n, ll count, int tp, int ppb,
+                 const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult)
+{
+    extern __shared__ __align__(16) double xs_all[];
+    const int lp = threadIdx.x / tp, t = threadIdx.x - lp * tp;
+    const ll p = (ll)blockIdx.x * ppb + lp;
+    const bool active = lp < ppb && p < count;
+    double *xs = xs_all + (size_t)lp * n;
+    const int *g = gtol + p * n;
+    if (active) for (int i = t; i < n; i += tp) xs[i] = __ldg(x + g[i]);
+    __syncthreads();
+    if (!active) return;
+    const double sc = mult ? scale * mult[p] : scale;
+    for (int i = t; i < n; i += tp) {
+        const double *M = S + p * stride + i;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int j = 0;
+#pragma unroll 1
+        for (; j + 8 <= n; j += 8) {
+            const double m0 = __ldcs(M + (ll)(j + 0) * n), m1 = __ldcs(M + (ll)(j + 1) * n);
+            const double m2 = __ldcs(M + (ll)(j + 2) * n), m3 = __ldcs(M + (ll)(j + 3) * n);
+            const double m4 = __ldcs(M + (ll)(j + 4) * n), m5 = __ldcs(M + (ll)(j + 5) * n);
+            const double m6 = __ldcs(M + (ll)(j + 6) * n), m7 = __ldcs(M + (ll)(j + 7) * n);
+            a0 = fma(m0, xs[j + 0], a0); a1 = fma(m1, xs[j + 1], a1); a2 = fma(m2, xs[j + 2], a2); a3 = fma(m3, xs[j + 3], a3);
+            a0 = fma(m4, xs[j + 4], a0); a1 = fma(m5, xs[j + 5], a1); a2 = fma(m6, xs[j + 6], a2); a3 = fma(m7, xs[j + 7], a3);
+        }
+        for (; j < n; ++j) a0 = fma(__ldcs(M + (ll)j * n), xs[j], a0);
+        atomicAdd(y + g[i], ((a0 + a1) + (a2 + a3)) * sc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small vector kernels of PCApply_PATCH / PCSetUp_PATCH
+// ---------------------------------------------------------------------------------------------
+// y[idx] = x[idx] on owned Dirichlet dofs, ssc/libssc.c:1408-1413
+__global__ void ssc_bc_kernel(const int *__restrict__ bc, ll nbc, const double *__restrict__ x, double *__restrict__ y)
+{
+    const ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nbc) { const int d = bc[i]; y[d] = x[d]; }
+}
+// y *= w, ssc/libssc.c:1418-1421
+__global__ void ssc_scale_kernel(ll n, const double *__restrict__ w, double *__restrict__ y)
+{
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) y[i] *= w[i];
+}
+// multiplicity: scatter ones through every patch's dof list, ssc/libssc.c:1263-1273
+__global__ void ssc_count_kernel(const int *__restrict__ gtol, ll total, double *__restrict__ m)
+{
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (ll)gridDim.x * blockDim.x) atomicAdd(m + gtol[i], 1.0);
+}
+// VecReciprocal (:1282): zero entries stay zero
+__global__ void ssc_reciprocal_kernel(ll n, double *__restrict__ w)
+{
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) { const double v = w[i]; w[i] = v != 0.0 ? 1.0 / v : 0.0; }
+}
+// star-forest pieces: dst[di[i]] (=|+=) src[si[i]]
+__global__ void ssc_gather_kernel(ll n, const int *__restrict__ si, const double *__restrict__ src, double *__restrict__ dst)
+{
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) dst[i] = src[si[i]];
+}
+__global__ void ssc_scatter_kernel(ll n, const int *__restrict__ di, const double *__restrict__ src, double *__restrict__ dst, int add)
+{
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) {
+        if (add) atomicAdd(dst + di[i], src[i]); else dst[di[i]] = src[i];
+    }
+}
+__global__ void ssc_copy_indexed_kernel(ll n, const int *__restrict__ di, const int *__restrict__ si, const double *__restrict__ src,
+                                        double *__restrict__ dst, int add)
+{
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) {
+        if (add) atomicAdd(dst + di[i], src[si[i]]); else dst[di[i]] = src[si[i]];
+    }
+}
+__global__ void ssc_fill_kernel(ll n, double *__restrict__ a, double v)
+{
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) a[i] = v;
+}

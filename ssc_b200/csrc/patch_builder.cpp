@@ -1,0 +1,244 @@
+// Host-side patch construction: which cells and which dofs make up each patch.
+//
+// Produces what PCPatchCreateCellPatches (ssc/libssc.c:452-580) and
+// PCPatchCreateCellPatchDiscretisationInfo (ssc/libssc.c:598-900) produce -- cellCounts/cells,
+// gtolCounts/gtol and the per-cell `dofs` table -- for the star (:1447), Vanka (:1471) and user (:1522)
+// constructions.  north_star keeps this stage on the host ("PatchPC.pyx and the patch.py setup logic").
+//
+// The reference walks the mesh three times per patch with PETSc hash tables.  Here each worker thread owns
+// a set of stamp arrays over mesh points and local dofs (stamp == current patch means "member"), so set
+// union, membership and difference are O(1) array probes, every patch is visited once, and contiguous
+// ranges of patches are built in parallel and concatenated.
+//
+// Ordering contract (DESIGN.md "dof-list order"): cells of a patch ascend by mesh point number; local dof
+// numbers are handed out in first-encounter order walking subspaces -> patch cells -> cell nodes ->
+// components (ssc/libssc.c:731-773).
+#include "common.h"
+
+#include <algorithm>
+#include <thread>
+#include <atomic>
+
+namespace {
+
+struct Scratch {
+    std::vector<int32_t> ptOwned, ptStar, ptSeen;      // stamps over mesh points
+    std::vector<int32_t> dofOwned, dofSeen, dofLocal;   // stamps over local dofs
+    std::vector<int32_t> localIdx;
+    std::vector<i64> owned, star, seen, cells;
+    void init(i64 pEnd, i64 nlocal) {
+        ptOwned.assign(pEnd, 0); ptStar.assign(pEnd, 0); ptSeen.assign(pEnd, 0);
+        dofOwned.assign(nlocal, 0); dofSeen.assign(nlocal, 0); dofLocal.assign(nlocal, 0);
+        localIdx.assign(nlocal, 0);
+    }
+};
+
+struct Chunk {
+    std::vector<i64> cellCount, gtolCount, cells, gtol, dofs;
+    int err = 0;
+    std::string msg;
+};
+
+// grow `list` by everything reachable from list[from..] through `off/adj`, marking with `stamp`
+inline void bfs(const std::vector<i64> &off, const std::vector<i64> &adj, std::vector<int32_t> &mark,
+                int32_t stamp, std::vector<i64> &list, size_t from) {
+    for (size_t head = from; head < list.size(); ++head) {
+        i64 q = list[head];
+        for (i64 k = off[q]; k < off[q + 1]; ++k) {
+            i64 r = adj[k];
+            if (mark[r] != stamp) { mark[r] = stamp; list.push_back(r); }
+        }
+    }
+}
+
+inline void push(std::vector<int32_t> &mark, int32_t stamp, std::vector<i64> &list, i64 p) {
+    if (mark[p] != stamp) { mark[p] = stamp; list.push_back(p); }
+}
+
+struct Builder {
+    const HostPlex &plex;
+    const Discretisation &disc;
+    const UserPatches &user;
+    const BuildOptions &opt;
+    i64 vStart, vEnd, cStart, cEnd, nlocal;
+    std::vector<unsigned char> isGlobalBc;
+
+    // owned points of patch `v` -> s.owned (marks ptOwned)
+    int owned_points(i64 v, int32_t stamp, Scratch &s, std::string &msg) const {
+        s.owned.clear();
+        if (opt.construct_type == 0) {                       // star, ssc/libssc.c:1447-1469
+            push(s.ptOwned, stamp, s.owned, v);
+            bfs(plex.suppOff, plex.supports, s.ptOwned, stamp, s.owned, 0);
+        } else if (opt.construct_type == 1) {                // Vanka, ssc/libssc.c:1471-1519
+            push(s.ptOwned, stamp, s.owned, v);
+            i64 iStart = 0, iEnd = 0;
+            bool ignore = opt.vankadim >= 0;
+            if (ignore) { iStart = plex.depthStart[opt.vankadim]; iEnd = plex.depthEnd[opt.vankadim]; }
+            // star(v) and the closure of its cells, both through the ptStar stamps (reset below by restamping)
+            s.star.clear();
+            push(s.ptStar, stamp, s.star, v);
+            bfs(plex.suppOff, plex.supports, s.ptStar, stamp, s.star, 0);
+            s.seen.clear();
+            for (i64 c : s.star) if (c >= cStart && c < cEnd) push(s.ptSeen, stamp, s.seen, c);
+            bfs(plex.coneOff, plex.cones, s.ptSeen, stamp, s.seen, 0);
+            for (i64 e : s.seen) {
+                if (ignore && iStart <= e && e < iEnd) continue;
+                push(s.ptOwned, stamp, s.owned, e);
+            }
+        } else {                                             // user, ssc/libssc.c:1522-1547
+            for (i64 i = user.off[v]; i < user.off[v + 1]; ++i) {
+                i64 e = user.pts[i];
+                if (e < 0 || e >= plex.pEnd) { msg = "Entities need to be between the bounds of DMPlexGetChart()"; return SSC_ERR_USER; }
+                push(s.ptOwned, stamp, s.owned, e);
+            }
+        }
+        return 0;
+    }
+
+    template <class F> void for_point_dofs(i64 k, i64 p, F f) const {
+        i64 ldof = disc.secDof[k][p], loff = disc.secOff[k][p], bs = disc.bs[k], so = disc.subspaceOffsets[k];
+        for (i64 j = loff; j < loff + ldof; ++j)
+            for (i64 l = 0; l < bs; ++l) f(bs * j + l + so);
+    }
+
+    int build_one(i64 v, int32_t stamp, int32_t stamp2, Scratch &s, Chunk &out) const {
+        int ierr = owned_points(v, stamp, s, out.msg);
+        if (ierr) return ierr;
+        // PCPatchCompleteCellPatch ssc/libssc.c:325-363: union over owned points of closure(star(.)).
+        // Two multi-source sweeps: supports from every owned point, then cones from everything reached.
+        // (stamp2 keeps the Vanka helper marks above from leaking into these sets.)
+        s.star.clear();
+        for (i64 e : s.owned) push(s.ptStar, stamp2, s.star, e);
+        bfs(plex.suppOff, plex.supports, s.ptStar, stamp2, s.star, 0);
+        s.seen.clear();
+        for (i64 e : s.star) push(s.ptSeen, stamp2, s.seen, e);
+        bfs(plex.coneOff, plex.cones, s.ptSeen, stamp2, s.seen, 0);
+        s.cells.clear();
+        for (i64 e : s.seen) if (cStart <= e && e < cEnd) s.cells.push_back(e);
+        std::sort(s.cells.begin(), s.cells.end());
+        i64 ncell = (i64)s.cells.size();
+        out.cellCount.push_back(ncell);
+        if (ncell == 0) { out.gtolCount.push_back(0); return 0; }
+        // owned / seen dofs: PCPatchGetPointDofs ssc/libssc.c:370-416; artificial BCs = seen \ owned (:420-440)
+        for (i64 k = 0; k < disc.nsub; ++k) {
+            if (k == opt.exclude_subspace) {
+                for_point_dofs(k, v, [&](i64 g) { s.dofOwned[g] = stamp; });
+            } else {
+                for (i64 p : s.owned) for_point_dofs(k, p, [&](i64 g) { s.dofOwned[g] = stamp; });
+            }
+            for (i64 p : s.seen) for_point_dofs(k, p, [&](i64 g) { s.dofSeen[g] = stamp; });
+        }
+        // first-encounter numbering, ssc/libssc.c:731-778
+        size_t g0 = out.gtol.size(), d0 = out.dofs.size();
+        int32_t next = 0;
+        for (i64 k = 0; k < disc.nsub; ++k) {
+            const i64 npc = disc.nodesPerCell[k], so = disc.subspaceOffsets[k], bs = disc.bs[k];
+            const i64 *cnm = disc.cellNodeMap[k];
+            for (i64 c : s.cells) {
+                if (disc.cnDof[c] <= 0) { out.msg = "Cell doesn't appear in cell numbering map"; return SSC_ERR_ARG_OUTOFRANGE; }
+                const i64 cell = disc.cnOff[c];
+                for (i64 j = 0; j < npc; ++j) {
+                    const i64 base = cnm[cell * npc + j] * bs + so;
+                    for (i64 l = 0; l < bs; ++l) {
+                        const i64 g = base + l;
+                        if (g < 0 || g >= nlocal) { out.msg = "cell node map entry outside the local dof range"; return SSC_ERR_ARG_OUTOFRANGE; }
+                        i64 loc;
+                        if (isGlobalBc[g] || (s.dofSeen[g] == stamp && s.dofOwned[g] != stamp)) loc = -1;
+                        else if (s.dofLocal[g] == stamp) loc = s.localIdx[g];
+                        else { s.dofLocal[g] = stamp; s.localIdx[g] = next; loc = next++; out.gtol.push_back(g); }
+                        if (opt.keep_dofs && disc.nsub == 1) out.dofs.push_back(loc);
+                    }
+                }
+            }
+        }
+        out.gtolCount.push_back((i64)(out.gtol.size() - g0));
+        if (opt.keep_dofs && disc.nsub > 1) {                // cell-major table, ssc/libssc.c:846-872
+            (void)d0;
+            for (i64 c : s.cells) {
+                const i64 cell = disc.cnOff[c];
+                for (i64 k = 0; k < disc.nsub; ++k) {
+                    const i64 npc = disc.nodesPerCell[k], so = disc.subspaceOffsets[k], bs = disc.bs[k];
+                    const i64 *cnm = disc.cellNodeMap[k];
+                    for (i64 j = 0; j < npc; ++j) for (i64 l = 0; l < bs; ++l) {
+                        const i64 g = cnm[cell * npc + j] * bs + so + l;
+                        out.dofs.push_back(s.dofLocal[g] == stamp ? s.localIdx[g] : -1);
+                    }
+                }
+            }
+        }
+        for (i64 c : s.cells) out.cells.push_back(disc.cnOff[c]);   // renumbered, ssc/libssc.c:747, :887
+        return 0;
+    }
+};
+
+}  // namespace
+
+int ssc_build_patches(const HostPlex &plex, const Discretisation &disc, const UserPatches &user,
+                      const BuildOptions &opt, PatchLists &out) {
+    if (!plex.set) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "DM not yet set on patch PC");      // ssc/libssc.c:474-476
+    if (!disc.set) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "PCPatchSetDiscretisationInfo() has not been called");
+    if (!disc.cn_set) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "PCPatchSetCellNumbering() has not been called");
+    Builder b{plex, disc, user, opt, 0, 0, 0, 0, 0, {}};
+    b.cStart = plex.depthStart[plex.dim]; b.cEnd = plex.depthEnd[plex.dim];
+    if (opt.construct_type >= 2) {                                                                    // ssc/libssc.c:485-489
+        if (!user.set) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "user patch construction requested but no patches were supplied");
+        b.vStart = 0; b.vEnd = (i64)user.off.size() - 1;
+    } else if (opt.codim < 0) {                                                                       // :490-495
+        i64 d = opt.dim < 0 ? 0 : opt.dim;
+        if (d > plex.dim) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "construction dim %lld exceeds mesh dimension", (long long)d);
+        b.vStart = plex.depthStart[d]; b.vEnd = plex.depthEnd[d];
+    } else {                                                                                          // :496-498
+        if (opt.codim > plex.dim) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "construction codim %lld exceeds mesh dimension", (long long)opt.codim);
+        b.vStart = plex.depthStart[plex.dim - opt.codim]; b.vEnd = plex.depthEnd[plex.dim - opt.codim];
+    }
+    b.nlocal = disc.subspaceOffsets[disc.nsub];
+    b.isGlobalBc.assign(b.nlocal, 0);
+    for (i64 g : disc.ghostBcNodes) {                                                                 // ssc/libssc.c:642-648
+        if (g < 0 || g >= b.nlocal) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "ghost BC node %lld outside the local dof range", (long long)g);
+        b.isGlobalBc[g] = 1;
+    }
+    const i64 np = b.vEnd - b.vStart;
+    int T = opt.nthreads > 0 ? opt.nthreads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    if (np < 4096) T = 1;
+    T = (int)std::min<i64>(T, std::max<i64>(np, 1));
+    std::vector<Chunk> chunks(T);
+    auto worker = [&](int t) {
+        Scratch s; s.init(plex.pEnd, b.nlocal);
+        i64 lo = b.vStart + np * t / T, hi = b.vStart + np * (t + 1) / T;
+        Chunk &c = chunks[t];
+        int32_t stamp = 0;
+        for (i64 v = lo; v < hi; ++v) {
+            stamp += 2;
+            bool ghost = opt.construct_type < 2 && !plex.ghost.empty() && plex.ghost[v];             // :515-521
+            if (ghost) { c.cellCount.push_back(0); c.gtolCount.push_back(0); continue; }
+            int ierr = b.build_one(v, stamp, stamp + 1, s, c);
+            if (ierr) { c.err = ierr; return; }
+        }
+    };
+    if (T == 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t) th.emplace_back(worker, t);
+        for (auto &x : th) x.join();
+    }
+    for (auto &c : chunks) if (c.err) return ssc_set_error(c.err, "%s", c.msg.c_str());
+    out.npatch = np; out.vStart = b.vStart;
+    out.cellOff.assign(np + 1, 0); out.gtolOff.assign(np + 1, 0);
+    i64 i = 0, ncells = 0, ngtol = 0, ndofs = 0;
+    for (auto &c : chunks) {
+        for (size_t k = 0; k < c.cellCount.size(); ++k, ++i) {
+            out.cellOff[i + 1] = out.cellOff[i] + c.cellCount[k];
+            out.gtolOff[i + 1] = out.gtolOff[i] + c.gtolCount[k];
+        }
+        ncells += (i64)c.cells.size(); ngtol += (i64)c.gtol.size(); ndofs += (i64)c.dofs.size();
+    }
+    out.cells.resize(ncells); out.gtol.resize(ngtol); out.dofs.resize(ndofs);
+    i64 a = 0, g = 0, d = 0;
+    for (auto &c : chunks) {
+        std::copy(c.cells.begin(), c.cells.end(), out.cells.begin() + a); a += (i64)c.cells.size();
+        std::copy(c.gtol.begin(), c.gtol.end(), out.gtol.begin() + g); g += (i64)c.gtol.size();
+        std::copy(c.dofs.begin(), c.dofs.end(), out.dofs.begin() + d); d += (i64)c.dofs.size();
+        Chunk().cells.swap(c.cells); Chunk().gtol.swap(c.gtol); Chunk().dofs.swap(c.dofs);
+    }
+    return 0;
+}

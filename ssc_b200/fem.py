@@ -427,3 +427,96 @@ class Discretisation(object):
 
     def block_diag(self, mats):
         return sp.block_diag(mats, format="csr")
+
+
+# ----------------------------------------------------------------------
+# stand-ins for the Firedrake objects ssc/patch.py:231-253 digs the form and BCs out of
+# ----------------------------------------------------------------------
+class DirichletBC(object):
+    """Homogeneous Dirichlet condition on ``nodes`` of subspace ``index`` (all components)."""
+
+    def __init__(self, index, nodes):
+        self.index = int(index)
+        self.nodes = np.asarray(nodes, dtype=IntType)
+
+    def __eq__(self, other):
+        return isinstance(other, DirichletBC) and self.index == other.index and np.array_equal(self.nodes, other.nodes)
+
+    def __ne__(self, other):
+        return not self == other
+
+
+class Form(object):
+    """A bilinear form on a (mixed) space: knows its function spaces and how to assemble itself to CSR."""
+
+    def __init__(self, spaces, assemble, owned_nodes=None):
+        self.spaces = list(spaces)
+        self._assemble = assemble
+        self.owned_nodes = owned_nodes
+
+    def ufl_domain(self):
+        return self.spaces[0].mesh
+
+    def assemble(self, bcs=()):
+        """Local operator (rows for all local dofs) with Dirichlet rows/columns replaced by the identity."""
+        return self._assemble(bcs)
+
+
+class ImplicitMatrixContext(object):
+    """What a matfree Firedrake operator carries (ssc/patch.py:233-243)."""
+
+    def __init__(self, a, row_bcs, col_bcs=None):
+        self.a = a
+        self.row_bcs = list(row_bcs)
+        self.col_bcs = list(row_bcs if col_bcs is None else col_bcs)
+        self._csr = None
+
+    def mult(self, mat, x, y):
+        if self._csr is None:
+            self._csr = self.a.assemble(self.row_bcs)
+        y.array[:] = self._csr @ x.array
+
+
+class _Problem(object):
+    def __init__(self, bcs):
+        self.bcs = list(bcs)
+
+
+class SNESContext(object):
+    """What sits in the DM's appctx for an assembled operator (ssc/patch.py:245-253)."""
+
+    def __init__(self, J, bcs, Jp=None):
+        self.J = J
+        self.Jp = Jp
+        self._problem = _Problem(bcs)
+
+
+def discretisation_from_form(J, bcs):
+    nodes = [[] for _ in J.spaces]
+    for bc in bcs:
+        nodes[bc.index].append(bc.nodes)
+    merged = [np.unique(np.concatenate(n)) if n else np.zeros(0, dtype=IntType) for n in nodes]
+    return Discretisation(J.spaces, bc_nodes=merged, owned_nodes=J.owned_nodes)
+
+
+def poisson_problem(mesh, degree, kind="scalar"):
+    """inner(grad u, grad v)*dx with zero Dirichlet data on the whole boundary, as in tests/test_jacobi_equivalent.py:25-50.
+    kind: scalar | vector | tensor | mixed (P x Q x R).  Returns (Form, bcs)."""
+    d = mesh.dim
+    sizes = {"scalar": [1], "vector": [d], "tensor": [d * d], "mixed": [1, d, d * d]}[kind]
+    spaces = [FunctionSpace(mesh, degree, bs) for bs in sizes]
+    V0 = spaces[0]
+    for W in spaces[1:]:                      # same scalar layout, different block size
+        assert np.array_equal(W.cell_node_list, V0.cell_node_list)
+    if mesh.cell_type == "simplex":
+        A0, _ = assemble_poisson_simplex(V0)
+    else:
+        A0 = assemble_poisson_tensor_scipy(V0)
+    bcs = [DirichletBC(i, W.boundary_nodes()) for i, W in enumerate(spaces)]
+
+    def assemble(bcs_):
+        A = sp.block_diag([expand_block(A0, W.bs) for W in spaces], format="csr")
+        disc = discretisation_from_form(form, bcs_)
+        return apply_bcs(A, disc.ghost_bc_nodes)
+    form = Form(spaces, assemble)
+    return form, bcs

@@ -1,0 +1,44 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    # build the product library and the oracle if they are missing (no-op when up to date)
+    from ssc_b200 import build
+    build.build()
+    from oracle import oracle
+    oracle.build()
+
+
+def meshes():
+    """The three meshes of the reference's tests (tests/test_jacobi_equivalent.py:11-15)."""
+    from ssc_b200 import plex
+    return {"Interval": plex.IntervalMesh(10, 5.0), "Rectangle": plex.RectangleMesh(10, 20, 2, 3),
+            "Box": plex.BoxMesh(5, 3, 5, 1, 2, 3)}
+
+
+@pytest.fixture(params=["Interval", "Rectangle", "Box"])
+def mesh(request):
+    return meshes()[request.param]
+
+
+@pytest.fixture(params=["scalar", "vector", "tensor", "mixed"])
+def problem_type(request):
+    return request.param
+
+
+def rhs_vector(n, seed=20260101):
+    """i.i.d. uniform(-1, 1), numpy default_rng(20260101)."""
+    return np.random.default_rng(seed).uniform(-1.0, 1.0, n)

@@ -1,0 +1,146 @@
+"""GPU parity: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star): PCApply within 1e-12 relative of the reference path in fp64, identical
+Krylov iteration counts; patch dof lists bit-exact.
+"""
+import numpy as np
+import pytest
+
+from conftest import meshes, rhs_vector
+from helpers import make_gpu, make_oracle, relerr
+from ssc_b200 import fem, plex
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _problem(mesh, p, kind):
+    form, bcs = fem.poisson_problem(mesh, p, kind)
+    disc = fem.discretisation_from_form(form, bcs)
+    A = form.assemble(bcs)
+    return form, bcs, disc, A
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_apply_matches_oracle(mesh, problem_type, p):
+    if problem_type in ("tensor", "mixed") and p == 3 and mesh.dim == 3:
+        pytest.skip("large on the CPU oracle side; covered by vector")
+    form, bcs, disc, A = _problem(mesh, p, problem_type)
+    o = make_oracle(disc, A)
+    pc = make_gpu(form, bcs)
+    pc.setUp()
+    assert all(np.array_equal(a, b) for a, b in zip(o.patches(), pc.getPatches()))
+    x = rhs_vector(disc.total_dofs)
+    y = np.zeros_like(x)
+    pc.apply(x, y)
+    assert relerr(y, o.apply(x)) < TOL
+
+
+@pytest.mark.parametrize("shape,p", [((6, 5), 2), ((5, 4), 4), ((3, 4, 3), 2), ((4, 4, 4), 3), ((2, 2, 2), 4), ((2, 2, 2), 5)])
+def test_tensor_apply_and_blocks(shape, p):
+    form, bcs, disc, A = _problem(plex.TensorPlex(shape), p, "scalar")
+    o = make_oracle(disc, A)
+    pc = make_gpu(form, bcs, ssc_keep_patch_operators=True)
+    pc.setUp()
+    off, _ = pc.getPatches()
+    sizes = np.diff(off)
+    for n in np.unique(sizes[sizes > 0]):
+        i = int(np.nonzero(sizes == n)[0][len(np.nonzero(sizes == n)[0]) // 2])
+        B = pc.getPatchMatrix(i)
+        assert np.array_equal(B, o.patchMatrix(i))                  # extraction copies values: bit-exact
+        Binv = pc.getPatchMatrix(i, inverse=True)
+        assert np.abs(Binv @ B - np.eye(n)).max() < 1e-10
+    x = rhs_vector(disc.total_dofs)
+    y = np.zeros_like(x)
+    pc.apply(x, y)
+    assert relerr(y, o.apply(x)) < TOL
+    # a second right-hand side through device-resident vectors
+    from ssc_b200 import DeviceVec
+    x2 = rhs_vector(disc.total_dofs, 20260102)
+    dx, dy = DeviceVec(pc, x2.size), DeviceVec(pc, x2.size)
+    dx.set(x2)
+    pc.apply(dx, dy)
+    pc.synchronize()
+    assert relerr(dy.get(), o.apply(x2)) < TOL
+
+
+@pytest.mark.parametrize("opts", [dict(partition_of_unity=1), dict(symmetrise_sweep=1), dict(construct_type=1),
+                                  dict(dim=1), dict(codim=0), dict(partition_of_unity=1, symmetrise_sweep=1)])
+def test_options_match_oracle(opts):
+    form, bcs, disc, A = _problem(plex.RectangleMesh(6, 5, 1, 1), 3, "vector")
+    o = make_oracle(disc, A, **opts)
+    pc = make_gpu(form, bcs, **opts)
+    pc.setUp()
+    assert all(np.array_equal(a, b) for a, b in zip(o.patches(), pc.getPatches()))
+    x = rhs_vector(disc.total_dofs)
+    y = np.zeros_like(x)
+    pc.apply(x, y)
+    assert relerr(y, o.apply(x)) < TOL
+
+
+def test_cholesky_and_unsaved_operators():
+    form, bcs, disc, A = _problem(plex.TensorPlex((4, 4, 4)), 2, "scalar")
+    o = make_oracle(disc, A)
+    x = rhs_vector(disc.total_dofs)
+    ref = o.apply(x)
+    for opts in (dict(sub_pc_type="cholesky"), dict(pc_patch_save_operators=False), dict(pc_patch_sub_mat_type="dense")):
+        pc = make_gpu(form, bcs, **opts)
+        pc.setUp()
+        y = np.zeros_like(x)
+        pc.apply(x, y)
+        assert relerr(y, ref) < TOL, opts
+
+
+def test_elasticity_tets():
+    """3D vector P2 elasticity on tets (BASELINE.json config 4, reduced): non-diagonal blocks, n = 45."""
+    mesh = plex.BoxMesh(4, 4, 4)
+    V = fem.FunctionSpace(mesh, 2, 3)
+    A, _ = fem.assemble_elasticity_simplex(V)
+    bcs = [fem.DirichletBC(0, V.boundary_nodes())]
+    form = fem.Form([V], lambda b: fem.apply_bcs(A, fem.discretisation_from_form(form, b).ghost_bc_nodes))
+    disc = fem.discretisation_from_form(form, bcs)
+    Abc = form.assemble(bcs)
+    o = make_oracle(disc, Abc)
+    pc = make_gpu(form, bcs)
+    pc.setUp()
+    x = rhs_vector(disc.total_dofs)
+    y = np.zeros_like(x)
+    pc.apply(x, y)
+    assert np.diff(pc.getPatches()[0]).max() == 45
+    assert relerr(y, o.apply(x)) < TOL
+
+
+def test_setup_is_repeatable_and_tracks_operator_values():
+    """PatchPC.update re-runs PCSetUp (ssc/patch.py:269-270): new operator values must be picked up."""
+    form, bcs, disc, A = _problem(plex.RectangleMesh(5, 5, 1, 1), 2, "scalar")
+    pc = make_gpu(form, bcs)
+    pc._compute_op = None            # feed CSR values by hand below
+    x = rhs_vector(disc.total_dofs)
+    for scale in (1.0, 3.0):
+        As = fem.apply_bcs(A * scale, disc.ghost_bc_nodes)
+        pc.setOperatorCSR(As.indptr, As.indices, As.data)
+        pc.setUp()
+        o = make_oracle(disc, As)
+        y = np.zeros_like(x)
+        pc.apply(x, y)
+        assert relerr(y, o.apply(x)) < TOL
+
+
+def test_errors():
+    from ssc_b200 import SSCError
+    form, bcs, disc, A = _problem(plex.IntervalMesh(4), 1, "scalar")
+    pc = make_gpu(form, bcs)
+    with pytest.raises(SSCError) as e:
+        pc.setOption("pc_patch_multiplicative", True)                  # ssc/libssc.c:1570-1572
+    assert e.value.ierr == 83
+    with pytest.raises(SSCError):
+        pc.applyTranspose(None, None)                                  # ssc/libssc.c:1715
+    with pytest.raises(SSCError):
+        pc.setOption("sub_pc_type", "ilu")
+    x = np.zeros(disc.total_dofs)
+    with pytest.raises(SSCError):
+        pc.apply(x, x.copy())                                          # before setUp
+    pc2 = make_gpu(form, bcs)
+    pc2.setOption("pc_patch_construction_dim", 0)
+    with pytest.raises(SSCError):
+        pc2.setOption("pc_patch_construction_codim", 0)                # ssc/libssc.c:1576-1578
