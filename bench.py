@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- PCApply throughput of the vertex-star patch preconditioner (BASELINE.json metric).
+
+Workload (config.workload): 3D Q3 Poisson on a 64^3 hex mesh per GPU, vertex-star patches, additive, fp64
+(BASELINE.json configs[2]).  With N GPUs the mesh is (64, 64, 64*N) split into N z-slabs (weak scaling): every rank
+builds its own slab (owned vertices + one cell layer of ghosts), patches never cross ranks, and the only exchange is
+the halo fill before and the overlap sum after the patch kernel (SFBcast/SFReduce of ssc/libssc.c:1323, :1399).
+
+A "step" is one PCApply.  value = dofs of the global problem / max-over-ranks device time per step, vectors resident in
+HBM.  e2e = the same through PatchPC.apply with pinned HOST vectors (H2D of x and D2H of y inside the timed region).
+roofline = algorithmic bytes of SURVEY.md 8(d) / device time of the fused apply kernel(s), CUDA events on the PC's stream.
+Inputs (31.7 GB of patch blocks) are far larger than the 126 MB L2, so no L2 flush is needed between steps.
+
+--impl reference times the CPU restatement of libssc's PCApply loop (oracle/, all host threads) on a bounded sample
+of the same workload: the reference itself needs PETSc and cannot be built here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "PCApply dofs/s (3D Q3 Poisson vertex-star patches, additive, fp64)"
+
+
+# ----------------------------------------------------------------------------------------------
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ssc_b200", choices=["ssc_b200", "reference"])
+    ap.add_argument("--cells", type=int, default=64, help="hex cells per direction per GPU")
+    ap.add_argument("--degree", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=16384, help="patches in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+def build_problem(args, rank, nranks):
+    """Local slab of the (c, c, c*nranks) Q_p problem: discretisation, CSR provider, SF description."""
+    from ssc_b200 import fem, plex
+    from ssc_b200 import partition
+    t0 = time.time()
+    c, p = args.cells, args.degree
+    if nranks == 1:
+        mesh = plex.TensorPlex((c, c, c))
+        V = fem.FunctionSpace(mesh, p)
+        disc = fem.Discretisation([V])
+        slab = None
+    else:
+        slab = partition.ZSlab((c, c, c * nranks), p, rank, nranks)
+        V, disc = slab.space, slab.discretisation
+    info = {"t_mesh": time.time() - t0}
+    return V, disc, slab, info
+
+
+def operator_csr(V, disc):
+    from ssc_b200 import synth
+    return synth.tensor_poisson_csr(V, disc.ghost_bc_nodes)
+
+
+def cpu_baseline(V, disc, csr, args, nthreads=None):
+    """The oracle's PCApply loop (gather, LU solve with precomputed factors, scatter-add) on a contiguous sample of the
+    workload's patches, all host threads; scaled to the whole vector by sum(n^2) (the loop is bound by streaming factors)."""
+    from oracle import oracle
+    from ssc_b200 import PC
+    from ssc_b200.patch import setup_patch_pc
+    nthreads = nthreads or os.cpu_count()
+    h = PC(device=-1)                         # host-only handle: dof lists only
+    setup_patch_pc(h, disc, None)
+    off, gtol = h.getPatches()
+    sizes = np.diff(off)
+    np_all = sizes.size
+    S = min(args.cpu_sample, np_all)
+    lo = (np_all - S) // 2                     # middle of the mesh: the interior (n = (2p-1)^3) patches that dominate
+    o = oracle.OraclePatchPC()
+    soff = off[lo:lo + S + 1] - off[lo]
+    o.setPatches(soff, gtol[off[lo]:off[lo + S]], disc.total_dofs)
+    o.setOperatorCSRArrays(*csr)
+    o.setUpOperators(nthreads=nthreads)
+    x = np.random.default_rng(20260101).uniform(-1, 1, disc.total_dofs)
+    o.applyLocal(x, nthreads=nthreads)         # warm-up
+    reps, t = 0, 0.0
+    while t < 10.0 and reps < 20:
+        t0 = time.perf_counter()
+        o.applyLocal(x, nthreads=nthreads)
+        t += time.perf_counter() - t0
+        reps += 1
+    per = t / reps
+    frac = float((sizes[lo:lo + S].astype(np.float64) ** 2).sum() / (sizes.astype(np.float64) ** 2).sum())
+    full = per / frac
+    return {"value": disc.total_dofs / full, "unit": "dofs/s", "cores": int(nthreads), "kind": "port",
+            "sample": "%d contiguous mid-mesh patches of %d (%.2f%% of sum n^2), %d applies, scaled by sum n^2; CPU restatement of libssc PCApply (oracle/ssc_oracle.c), factors precomputed"
+                      % (S, np_all, 100 * frac, reps),
+            "ms_per_step_full_estimate": full * 1e3}
+
+
+# ----------------------------------------------------------------------------------------------
+def run_reference(args, rank, nranks):
+    if rank != 0:
+        return
+    V, disc, slab, info = build_problem(args, 0, 1)
+    csr = operator_csr(V, disc)
+    vals = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_baseline(V, disc, csr, args) if base is None or i >= args.warmup else base
+        if i >= args.warmup:
+            vals.append(base["value"])
+        if i == 0:
+            args.cpu_sample = min(args.cpu_sample, 8192)
+        if len(vals) >= 3:           # bounded: a step here is seconds of CPU work
+            break
+    v = float(np.median(vals)) if vals else base["value"]
+    out = {"impl": "reference", "metric": METRIC, "value": v * nranks, "unit": "dofs/s", "n_gpus": args.gpus, "steps": len(vals),
+           "warmup": args.warmup, "ms_per_step": disc.total_dofs / v * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args, nranks),
+           "cpu_baseline": dict(base, value=v),
+           "e2e": {"value": v * nranks, "unit": "dofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "reference (ssc/libssc.c) needs PETSc and cannot be built here; this is the CPU restatement (oracle port) on the host cores"}
+    print(json.dumps(out))
+
+
+def workload_config(args, nranks):
+    c, p = args.cells, args.degree
+    return {"workload": "3D Q%d Poisson, %dx%dx%d hex cells%s, vertex-star patches, additive, stored inverse (sub_pc_type lu)"
+                        % (p, c, c, c * nranks, " (z-slabs of %d^3 per GPU)" % c if nranks > 1 else ""),
+            "cells_per_gpu": c ** 3, "degree": p, "parallelism": "patches by mesh slab x%d" % nranks,
+            "l2": "inputs larger than L2 (patch blocks %.1f GB per GPU), no flush" % (8 * ((2 * p - 1) ** 3) ** 2 * (c - 1) ** 3 / 1e9)}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    nranks = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, nranks)
+        return
+    dist = None
+    if nranks > 1:
+        import torch.distributed as dist          # rendezvous + barrier only (gloo); the data path is the library's own NCCL
+        dist.init_process_group("gloo", rank=rank, world_size=nranks)
+
+    from ssc_b200 import PC, DeviceVec, PinnedArray, partition
+    from ssc_b200.patch import setup_patch_pc
+    from ssc_b200.pcpatch import get_unique_id
+
+    V, disc, slab, info = build_problem(args, rank, nranks)
+    t0 = time.time()
+    csr = operator_csr(V, disc)
+    info["t_assemble"] = time.time() - t0
+
+    pc = PC(device=local_rank)
+    setup_patch_pc(pc, disc, None)
+    pc._compute_op = None
+    pc.setOperatorCSR(*csr)
+    if nranks > 1:
+        uid = [get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        pc.commInit(nranks, rank, uid[0])
+        sf = partition.star_forest(slab.global_ids, slab.nowned, rank, nranks,
+                                   lambda obj: _allgather(dist, obj, nranks))
+        pc.setStarForest(slab.nowned, *sf)
+    t0 = time.time()
+    pc.setUp()
+    pc.synchronize()
+    info["t_setup_wall"] = time.time() - t0
+    setup = {"create_patches_ms": pc.eventTime("PCPATCHCreate"), "extract_ms": pc.eventTime("PCPATCHComputeOp"),
+             "factor_ms": pc.eventTime("PCPATCHSolve"), "setup_wall_s": info["t_setup_wall"],
+             "assemble_wall_s": info["t_assemble"], "mesh_wall_s": info["t_mesh"]}
+    nowned = pc.size("nowned")
+    nglobal = nowned
+    if nranks > 1:
+        tot = [None] * nranks
+        dist.all_gather_object(tot, nowned)
+        nglobal = int(sum(tot))
+
+    rng = np.random.default_rng(20260101 + rank)
+    xh = PinnedArray(pc, nowned)
+    yh = PinnedArray(pc, nowned)
+    xh.array[:] = rng.uniform(-1, 1, nowned)
+    dx, dy = DeviceVec(pc, nowned), DeviceVec(pc, nowned)
+    dx.set(xh.array)
+
+    def barrier():
+        pc.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        pc.apply(dx, dy)
+    barrier()
+    e0, e1 = pc.eventCreate(), pc.eventCreate()
+    launches0 = pc.size("gpu_launches")
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    pc.kernelTimerReset(True)
+    barrier()
+    pc.eventRecord(e0)
+    for _ in range(args.steps):
+        pc.apply(dx, dy)
+    pc.eventRecord(e1)
+    ms = pc.eventElapsed(e0, e1)
+    barrier()
+    kms, kn = pc.kernelTimerRead()
+    pc.kernelTimerReset(False)
+    launches = pc.size("gpu_launches") - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_all = _max_over_ranks(dist, ms, nranks)
+    ms_step = ms_all / args.steps
+
+    # ---- end to end through the python PC surface with host vectors -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(args.warmup):
+            pc.apply(xh.array, yh.array)
+        barrier()
+        pc.eventRecord(e0)
+        for _ in range(args.steps):
+            pc.apply(xh.array, yh.array)
+        pc.eventRecord(e1)
+        ems = _max_over_ranks(dist, pc.eventElapsed(e0, e1), nranks) / args.steps
+        barrier()
+        e2e = {"value": nglobal / (ems * 1e-3), "unit": "dofs/s", "h2d_bytes_per_step": 8 * nowned, "d2h_bytes_per_step": 8 * nowned,
+               "ms_per_step": ems, "api": "ssc_b200.PC.apply(x, y) on pinned host vectors (SSCPatchApply, SSC_MEM_HOST)"}
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_apply = pc.size("bytes_apply")
+    kernel_ms = kms / max(kn, 1)
+    achieved = bytes_apply / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "ssc_apply_kernel (all size classes of one apply)", "kernel_ms": kernel_ms,
+                "algorithmic_bytes": bytes_apply, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
+    out = {"metric": METRIC, "value": nglobal / (ms_step * 1e-3), "unit": "dofs/s", "n_gpus": nranks, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "config": workload_config(args, nranks),
+           "dofs": nglobal, "patches_per_gpu": pc.size("npatch"), "hbm_gbs_step": bytes_apply * nranks / (ms_step * 1e-3) / 1e9,
+           "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "setup": setup}
+    if nranks == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(V, disc, csr, args)
+    print(json.dumps(out))
+
+
+def _allgather(dist, obj, nranks):
+    out = [None] * nranks
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def _max_over_ranks(dist, v, nranks):
+    if dist is None:
+        return v
+    out = [None] * nranks
+    dist.all_gather_object(out, float(v))
+    return max(out)
+
+
+if __name__ == "__main__":
+    main()

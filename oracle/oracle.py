@@ -164,6 +164,14 @@ class OraclePatchPC(object):
         self._keep += [rowptr, col, val]
         self._chk(self.L.oracle_set_operator_csr(self.h, C.c_int64(A.shape[0]), _ip(rowptr), _ip(col), _dp(val)))
 
+    def setOperatorCSRArrays(self, rowptr, col32, val):
+        rowptr = _i64(rowptr)
+        col32 = np.ascontiguousarray(col32, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        self._keep += [rowptr, col32, val]
+        self._chk(self.L.oracle_set_operator_csr32(self.h, C.c_int64(rowptr.size - 1), _ip(rowptr),
+                                                   col32.ctypes.data_as(C.c_void_p), _dp(val)))
+
     def setUpOperators(self, keep_mat=False, nthreads=0):
         self._chk(self.L.oracle_setup_operators(self.h, int(keep_mat), int(nthreads)))
 

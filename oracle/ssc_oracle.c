@@ -111,7 +111,7 @@ typedef struct {
     i64 *gtolDof, *gtolOff, *gtol, numGtol;
     i64 *dofs, numDofs;
     /* operator */
-    i64 nrows; const i64 *rowptr, *colidx; const double *vals;
+    i64 nrows; const i64 *rowptr, *colidx; const int32_t *colidx32; const double *vals;
     double **mat; double **lu; i64 **piv;
     double *dof_weights; i64 nowned;
     char err[256];
@@ -451,7 +451,11 @@ int oracle_set_patches(OraclePC *pc, i64 npatch, const i64 *gtolOff, const i64 *
 /* patch operators                                                     */
 /* ------------------------------------------------------------------ */
 int oracle_set_operator_csr(OraclePC *pc, i64 nrows, const i64 *rowptr, const i64 *colidx, const double *vals) {
-    pc->nrows = nrows; pc->rowptr = rowptr; pc->colidx = colidx; pc->vals = vals; return 0;
+    pc->nrows = nrows; pc->rowptr = rowptr; pc->colidx = colidx; pc->colidx32 = NULL; pc->vals = vals; return 0;
+}
+/* same with 32-bit column indices (benchmark-size operators) */
+int oracle_set_operator_csr32(OraclePC *pc, i64 nrows, const i64 *rowptr, const int32_t *colidx, const double *vals) {
+    pc->nrows = nrows; pc->rowptr = rowptr; pc->colidx = NULL; pc->colidx32 = colidx; pc->vals = vals; return 0;
 }
 
 /* B_p = A[gtol_p, gtol_p]: equal to the element-wise assembly of ssc/libssc.c:1120-1156 for star patches */
@@ -462,7 +466,7 @@ static void extract_patch(const OraclePC *pc, i64 p, double *B, hmap *g2l) {
     memset(B, 0, n * n * sizeof(double));
     for (i64 i = 0; i < n; i++)
         for (i64 k = pc->rowptr[g[i]]; k < pc->rowptr[g[i] + 1]; k++) {
-            i64 j = hmap_get(g2l, pc->colidx[k]);
+            i64 j = hmap_get(g2l, pc->colidx ? pc->colidx[k] : (i64)pc->colidx32[k]);
             if (j >= 0) B[i * n + j] += pc->vals[k];
         }
 }

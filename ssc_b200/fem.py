@@ -22,10 +22,14 @@ from .plex import IntType, TensorPlex
 # ----------------------------------------------------------------------
 # section numbering shared by both cell types
 # ----------------------------------------------------------------------
-def _number_points(pEnd, first_cell, rank_in_cell, ndof):
+def _number_points(pEnd, first_cell, rank_in_cell, ndof, ghost=None):
     """PetscSection (dof, off) over the chart: points are numbered in the order a
-    cell-by-cell closure traversal first meets them (what Firedrake does for locality)."""
-    order = np.lexsort((rank_in_cell, first_cell))
+    cell-by-cell closure traversal first meets them (what Firedrake does for locality);
+    points labelled ghost come after all owned ones (Firedrake: nodes < dof_dset.size are owned)."""
+    if ghost is None or not np.any(ghost):
+        order = np.lexsort((rank_in_cell, first_cell))
+    else:
+        order = np.lexsort((rank_in_cell, first_cell, ghost.astype(np.int64)))
     off = np.zeros(pEnd, dtype=IntType)
     c = np.cumsum(ndof[order])
     off[order] = c - ndof[order]
@@ -56,6 +60,7 @@ class FunctionSpace(object):
             self._init_tensor()
         self.node_count = int(self.sec_dof.sum())
         self.dof_count = self.node_count * self.bs
+        self.owned_node_count = int(self.sec_dof[mesh.ghost == 0].sum())
 
     # -- simplices -----------------------------------------------------
     def _init_simplex(self):
@@ -82,7 +87,7 @@ class FunctionSpace(object):
                 hit = first_cell[ce[:, j]] == cells
                 rank[ce[hit, j]] = base + j
             base += ce.shape[1]
-        self.sec_dof, self.sec_off = _number_points(m.pEnd, first_cell, rank, ndof)
+        self.sec_dof, self.sec_off = _number_points(m.pEnd, first_cell, rank, ndof, m.ghost)
         # local lattice: basis functions ordered by entity dimension, entity, local dof
         alphas, ent = [], []
         for k in range(d + 1):
@@ -169,7 +174,7 @@ class FunctionSpace(object):
                     side = side * 2 + (idx[a] - cmin[a])
             rank[start:start + idx.shape[1]] = gi * (1 << d) + side
             gi += 1
-        self.sec_dof, self.sec_off = _number_points(m.pEnd, first_cell, rank, ndof)
+        self.sec_dof, self.sec_off = _number_points(m.pEnd, first_cell, rank, ndof, m.ghost)
         self.lattice_shape = lshape
         self.lattice_node = (self.sec_off[point] + ldof).reshape(lshape)
         self.nodes_per_cell = (p + 1) ** d

@@ -1,0 +1,101 @@
+"""Mesh partitions for one-process-per-GPU runs: who owns which patch, and the owner<->ghost dof map.
+
+The reference shards by mesh partition: a rank builds patches only around the points it owns
+(ssc/libssc.c:500-521), needs one layer of vertex overlap so every owned star is local
+(tests/test_jacobi_equivalent.py:9), fills ghost values before the patch loop (SFBcast, :1323-1324) and sums
+overlap contributions into the owners after it (SFReduce, :1399-1400).  PetscSF is replaced by explicit
+per-neighbour index lists (``star_forest``), handed to SSCPatchSetStarForest.
+"""
+import numpy as np
+
+from . import fem, plex
+from .plex import IntType
+
+
+class ZSlab(object):
+    """Rank ``rank`` of ``nranks`` z-slabs of a structured (cx, cy, cz) box of tensor cells, degree p.
+
+    Vertex planes are dealt out in contiguous ranges; the local mesh holds every cell that touches an owned
+    vertex.  Local dofs are numbered owned first, then ghosts.  ``global_ids`` maps local node -> node of the
+    global lattice (used only to match ghosts with their owners at set-up).
+    """
+
+    def __init__(self, cells, p, rank, nranks):
+        cx, cy, cz = cells
+        k0 = rank * cz // nranks
+        k1 = (rank + 1) * cz // nranks if rank < nranks - 1 else cz + 1     # owned vertex planes [k0, k1)
+        lo, hi = max(k0 - 1, 0), min(k1 - 1, cz - 1)                        # local cell layers [lo, hi]
+        nl = hi - lo + 1
+        h = 1.0 / cx
+        mesh = plex.TensorPlex((cx, cy, nl), lengths=(cx * h, cy * h, nl * h))
+        mesh.mark_ghost_vertices(2, k0 - lo, k1 - 1 - lo)
+        V = fem.FunctionSpace(mesh, p)
+        self.mesh, self.space, self.rank, self.nranks = mesh, V, rank, nranks
+        self.nowned = V.owned_node_count
+        L = np.indices(V.lattice_shape).reshape(3, -1)
+        gz = L[2] + p * lo
+        gshape = (p * cx + 1, p * cy + 1, p * cz + 1)
+        gid = np.ravel_multi_index((L[0], L[1], gz), gshape)
+        self.global_ids = np.empty(V.node_count, dtype=IntType)
+        self.global_ids[V.lattice_node.ravel()] = gid
+        onb = (L[0] == 0) | (L[0] == gshape[0] - 1) | (L[1] == 0) | (L[1] == gshape[1] - 1) | (gz == 0) | (gz == gshape[2] - 1)
+        bc_nodes = np.sort(V.lattice_node.ravel()[onb])
+        self.discretisation = fem.Discretisation([V], bc_nodes=[bc_nodes], owned_nodes=[self.nowned])
+        self.global_shape = gshape
+
+
+def star_forest(global_ids, nowned, rank, nranks, allgather):
+    """Per-neighbour send/receive lists from local->global dof ids.
+
+    ``allgather(obj)`` returns the list of every rank's ``obj`` (torch.distributed.all_gather_object in real runs).
+    Returns (self_leaf, self_root, neigh, send_off, send_root, recv_off, recv_leaf) in the layout of
+    SSCPatchSetStarForest: the ghosts a rank receives from neighbour q appear in the order of that rank's own ghost
+    list, and the owner lists its send indices in the same order.
+    """
+    global_ids = np.asarray(global_ids, dtype=IntType)
+    nlocal = global_ids.size
+    ghost_gid = global_ids[nowned:]
+    all_ghosts = allgather(ghost_gid)
+    owned_gid = global_ids[:nowned]
+    order = np.argsort(owned_gid, kind="stable")
+    sorted_owned = owned_gid[order]
+    found = {}
+    send = {}
+    for q in range(nranks):
+        if q == rank or all_ghosts[q].size == 0:
+            continue
+        pos = np.searchsorted(sorted_owned, all_ghosts[q])
+        pos[pos >= nowned] = max(nowned - 1, 0)
+        hit = sorted_owned[pos] == all_ghosts[q] if nowned else np.zeros(all_ghosts[q].size, dtype=bool)
+        if hit.any():
+            found[q] = hit
+            send[q] = order[pos[hit]].astype(IntType)
+    all_found = allgather(found)
+    recv = {}
+    for q in range(nranks):
+        if q != rank and rank in all_found[q]:
+            recv[q] = (nowned + np.nonzero(all_found[q][rank])[0]).astype(IntType)
+    claimed = np.zeros(nlocal - nowned, dtype=np.int64)
+    for q, idx in recv.items():
+        claimed[idx - nowned] += 1
+    if nlocal > nowned and not np.all(claimed == 1):
+        raise ValueError("rank %d: %d ghost dofs have no unique owner" % (rank, int((claimed != 1).sum())))
+    neigh = sorted(set(send) | set(recv))
+    send_off, recv_off = [0], [0]
+    send_root, recv_leaf = [], []
+    for q in neigh:
+        s = send.get(q, np.zeros(0, dtype=IntType))
+        r = recv.get(q, np.zeros(0, dtype=IntType))
+        send_root.append(s)
+        recv_leaf.append(r)
+        send_off.append(send_off[-1] + s.size)
+        recv_off.append(recv_off[-1] + r.size)
+    cat = lambda xs: np.concatenate(xs).astype(IntType) if xs else np.zeros(0, dtype=IntType)   # noqa: E731
+    ident = np.arange(nowned, dtype=IntType)
+    return (ident, ident.copy(), np.array(neigh, dtype=np.int32), np.array(send_off, dtype=IntType), cat(send_root),
+            np.array(recv_off, dtype=IntType), cat(recv_leaf))
+
+
+def simulate_allgather(objs_by_rank):
+    """In-process stand-in for all_gather_object: call with the list of per-rank objects."""
+    return lambda obj, _all=objs_by_rank: list(_all)
