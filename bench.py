@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16384, help="patches in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--apply-variant", type=int, default=None, help="ssc_apply_variant (kernel selection; default = library default)")
     return ap.parse_args()
 
 
@@ -212,6 +213,8 @@ def main():
     setup_patch_pc(pc, disc, None)
     pc._compute_op = None
     pc.setOperatorCSR(*csr)
+    if args.apply_variant is not None:
+        pc.setOption("ssc_apply_variant", args.apply_variant)
     if nranks > 1:
         uid = [get_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)

@@ -93,6 +93,7 @@ struct SizeClass {
     i64 goff = 0;                 // offset of the class in d_gtol (entries)
     i64 moff = 0;                 // offset of the class in d_blocks (doubles)
     i64 stride = 0;               // doubles per block
+    int ld = 0;                   // row stride inside a block (doubles)
     int tp = 0, ppb = 0;          // apply launch shape
 };
 
@@ -104,6 +105,7 @@ struct SSCPatchPC_s {
     bool save_operators = true, partition_of_unity = false, multiplicative = false, print_patches = false;
     bool symmetrise_sweep = false, keep_operators = false, dim_set = false, codim_set = false;
     int sub_pc = SSC_SUB_LU;
+    int apply_variant = 1;        // 0: simple loop, 1: pipelined LDG.64, 2: pipelined LDG.128 (even row stride)
     std::string sub_mat_type, sub_ksp_type = "preonly";
     BuildOptions bopt;
     // host inputs
@@ -354,6 +356,13 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_keep_dofs_table") return parse_bool(v, &pc->bopt.keep_dofs);
     if (name == "ssc_keep_patch_operators") return parse_bool(v, &pc->keep_operators);
     if (name == "ssc_builder_threads") { pc->bopt.nthreads = atoi(v); return 0; }
+    if (name == "ssc_apply_variant") {
+        const int a = atoi(v);
+        if (a < 0 || a > 2) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "ssc_apply_variant must be 0, 1 or 2");
+        if (pc->device_ready && (a == 2) != (pc->apply_variant == 2)) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "the block layout of variant 2 must be chosen before the first SetUp");
+        pc->apply_variant = a;
+        return 0;
+    }
     return ssc_set_error(SSC_ERR_USER, "unknown option '%s'", name.c_str());
 }
 
@@ -507,9 +516,10 @@ extern "C" int SSCPatchSetOperatorCSR(SSCPatchPC pc, SSCInt nrows, const SSCInt 
 // ---------------------------------------------------------------------------------------------
 // setup
 // ---------------------------------------------------------------------------------------------
-static void choose_launch_shape(SizeClass &c)
+static void choose_launch_shape(SizeClass &c, int variant)
 {
-    const int n = c.n;
+    int n = c.n;
+    if (variant == 2) n = (c.n + 1) / 2;            // one thread per pair of rows
     if (n >= 1024) { c.tp = 1024; c.ppb = 1; return; }
     if (n > 96) { c.tp = (n + 31) / 32 * 32; c.ppb = 1; return; }
     c.tp = n <= 8 ? 8 : (n + 7) / 8 * 8;       // sub-warp groups for small patches
@@ -543,8 +553,9 @@ static int build_device_lists(PC *pc)
         if (pc->classes.empty() || pc->classes.back().n != (int)n) {
             SizeClass c;
             c.n = (int)n; c.first = q; c.goff = goff; c.moff = moff;
-            c.stride = (n * n + 15) / 16 * 16;
-            choose_launch_shape(c);
+            c.ld = pc->apply_variant == 2 ? (int)((n + 1) / 2 * 2) : (int)n;
+            c.stride = (n * c.ld + 15) / 16 * 16;
+            choose_launch_shape(c, pc->apply_variant);
             pc->classes.push_back(c);
         }
         SizeClass &c = pc->classes.back();
@@ -676,7 +687,7 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
     if (time_it) CUDA_OK(cudaEventRecord(pc->ev0, pc->stream));
     const int grid_e = (int)std::min<i64>(cnt, (i64)pc->sm_count * 64);
     ssc_extract_kernel<<<grid_e, bd, smem_e, pc->stream>>>((const ll *)pc->d_rowptr, pc->d_colidx, pc->d_vals, pc->d_gtol + c.goff + (q0 - c.first) * n,
-                                                          blocks, n, c.stride, cnt, H);
+                                                          blocks, n, c.ld, c.stride, cnt, H);
     pc->launches++;
     CUDA_OK(cudaGetLastError());
     if (time_it) {
@@ -697,7 +708,7 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
 #define LAUNCH_INV(P, S)                                                                                              \
     do {                                                                                                              \
         if (smem_f > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_invert_kernel<P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
-        ssc_invert_kernel<P, S><<<grid_f, bdf, smem_f, pc->stream>>>(blocks, n, c.stride, cnt, fail);                   \
+        ssc_invert_kernel<P, S><<<grid_f, bdf, smem_f, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail);                   \
     } while (0)
     if (pivot && shared) LAUNCH_INV(true, true);
     else if (pivot) LAUNCH_INV(true, false);
@@ -771,10 +782,18 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
     if (cnt <= 0) return 0;
     const int threads = std::max(32, (c.tp * c.ppb + 31) / 32 * 32);
     const size_t smem = (size_t)c.ppb * c.n * sizeof(double);
-    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 grid = (cnt + c.ppb - 1) / c.ppb;
-    ssc_apply_kernel<<<(unsigned)grid, threads, smem, pc->stream>>>(blocks, c.stride, pc->d_gtol + c.goff + (q0 - c.first) * c.n, c.n, cnt, c.tp, c.ppb,
-                                                                   xl, yl, scale, pc->d_mult ? pc->d_mult + q0 : nullptr);
+    const int *gt = pc->d_gtol + c.goff + (q0 - c.first) * c.n;
+    const double *mult = pc->d_mult ? pc->d_mult + q0 : nullptr;
+#define LAUNCH_APPLY(K)                                                                                                  \
+    do {                                                                                                                 \
+        if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        K<<<(unsigned)grid, threads, smem, pc->stream>>>(blocks, c.stride, c.ld, gt, c.n, cnt, c.tp, c.ppb, xl, yl, scale, mult); \
+    } while (0)
+    if (pc->apply_variant == 2 && threads <= 256) LAUNCH_APPLY((ssc_apply_pipe_kernel<2, 8>));
+    else if (pc->apply_variant == 1 && threads <= 256) LAUNCH_APPLY((ssc_apply_pipe_kernel<1, 8>));
+    else LAUNCH_APPLY(ssc_apply_kernel);
+#undef LAUNCH_APPLY
     pc->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -952,11 +971,12 @@ extern "C" int SSCPatchGetPatchMatrix(SSCPatchPC pc, SSCInt p, int which, double
     for (const SizeClass &c : pc->classes) {
         if (q >= c.first && q < c.first + c.count) {
             const i64 n = c.n;
-            std::vector<double> tmp((size_t)(n * n));
+            const i64 ld = c.ld;
+            std::vector<double> tmp((size_t)(n * ld));
             CUDA_OK(cudaStreamSynchronize(pc->stream));
-            CUDA_OK(cudaMemcpy(tmp.data(), src + c.moff + (q - c.first) * c.stride, (size_t)(n * n) * sizeof(double), cudaMemcpyDeviceToHost));
-            if (which == 0) std::copy(tmp.begin(), tmp.end(), out);
-            else for (i64 i = 0; i < n; ++i) for (i64 j = 0; j < n; ++j) out[i * n + j] = tmp[(size_t)(j * n + i)];   // stored transposed
+            CUDA_OK(cudaMemcpy(tmp.data(), src + c.moff + (q - c.first) * c.stride, (size_t)(n * ld) * sizeof(double), cudaMemcpyDeviceToHost));
+            for (i64 i = 0; i < n; ++i) for (i64 j = 0; j < n; ++j)
+                out[i * n + j] = which == 0 ? tmp[(size_t)(i * ld + j)] : tmp[(size_t)(j * ld + i)];   // the inverse is stored transposed
             return 0;
         }
     }

@@ -144,3 +144,19 @@ def test_errors():
     pc2.setOption("pc_patch_construction_dim", 0)
     with pytest.raises(SSCError):
         pc2.setOption("pc_patch_construction_codim", 0)                # ssc/libssc.c:1576-1578
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("shape,p,kind", [((4, 4, 4), 3, "scalar"), ((3, 3), 4, "vector"), ((2, 2, 2), 2, "mixed")])
+def test_apply_kernel_variants(variant, shape, p, kind):
+    """Every apply kernel variant (simple / pipelined LDG.64 / pipelined LDG.128 with padded rows) gives the same answer."""
+    form, bcs, disc, A = _problem(plex.TensorPlex(shape), p, kind)
+    o = make_oracle(disc, A)
+    pc = make_gpu(form, bcs, ssc_apply_variant=variant, ssc_keep_patch_operators=True)
+    pc.setUp()
+    x = rhs_vector(disc.total_dofs)
+    y = np.zeros_like(x)
+    pc.apply(x, y)
+    assert relerr(y, o.apply(x)) < TOL
+    i = int(np.argmax(np.diff(pc.getPatches()[0])))
+    assert np.array_equal(pc.getPatchMatrix(i), o.patchMatrix(i))
