@@ -1,0 +1,95 @@
+"""The product's host patch builder (csrc/patch_builder.cpp, through the C ABI on a host-only handle) against the
+oracle's restatement of ssc/libssc.c:452-900: cells, gtol and the per-cell dofs table, bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import meshes
+from helpers import OPT_NAMES, make_oracle
+from ssc_b200 import PC, fem, plex
+from ssc_b200.patch import setup_patch_pc
+
+
+def both(mesh, p, kind, threads=0, **opts):
+    form, bcs = fem.poisson_problem(mesh, p, kind)
+    disc = fem.discretisation_from_form(form, bcs)
+    o = make_oracle(disc, **opts)
+    pc = PC(device=-1)
+    setup_patch_pc(pc, form, bcs)
+    pc.setOption("ssc_keep_dofs_table", True)
+    if threads:
+        pc.setOption("ssc_builder_threads", threads)
+    for k, v in opts.items():
+        pc.setOption(OPT_NAMES[k], ["star", "vanka", "user"][v] if k == "construct_type" else v)
+    return o, pc
+
+
+def assert_same(o, pc):
+    for a, b in zip(o.patches(), pc.getPatches()):
+        assert np.array_equal(a, b)
+    for a, b in zip(o.cells(), pc.getCells()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(o.dofs(), pc.getDofs())
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_star_patches_reference_meshes(mesh, problem_type, p):
+    if p == 3 and mesh.dim == 3 and problem_type in ("tensor", "mixed"):
+        pytest.skip("slow on the oracle side")
+    assert_same(*both(mesh, p, problem_type))
+
+
+@pytest.mark.parametrize("opts", [dict(construct_type=1), dict(construct_type=1, vankadim=0), dict(dim=1), dict(codim=0),
+                                  dict(codim=1), dict(construct_type=1, exclude_subspace=1)])
+@pytest.mark.parametrize("name", ["Rectangle", "Box"])
+def test_other_constructions(name, opts):
+    mesh = meshes()[name]
+    assert_same(*both(mesh, 2, "mixed", **opts))
+
+
+@pytest.mark.parametrize("shape,p", [((5, 4), 3), ((3, 4, 2), 2), ((3, 3, 3), 4), ((7,), 5)])
+def test_tensor_meshes(shape, p):
+    assert_same(*both(plex.TensorPlex(shape), p, "vector"))
+
+
+def test_threaded_builder_is_deterministic():
+    """> 4096 patches switches the builder to worker threads; chunks must concatenate to the serial answer."""
+    mesh = plex.TensorPlex((20, 20, 12))
+    o, pc = both(mesh, 2, "scalar", threads=5)
+    assert pc.size("npatch") if pc.getPatches() else True
+    assert_same(o, pc)
+    _, pc1 = both(mesh, 2, "scalar", threads=1)
+    assert all(np.array_equal(a, b) for a, b in zip(pc.getPatches(), pc1.getPatches()))
+
+
+def test_ghost_vertices_get_no_patch():
+    """Only owned vertices get patches (ssc/libssc.c:500-521)."""
+    mesh = plex.TensorPlex((3, 3, 4))
+    mesh.mark_ghost_vertices(2, 1, 3)
+    V = fem.FunctionSpace(mesh, 2)
+    disc = fem.Discretisation([V], owned_nodes=[V.owned_node_count])
+    o = make_oracle(disc)
+    pc = PC(device=-1)
+    setup_patch_pc(pc, disc, None)
+    off, gtol = pc.getPatches()
+    assert all(np.array_equal(a, b) for a, b in zip(o.patches(), (off, gtol)))
+    vs, ve = mesh.depth_stratum(0)
+    sizes = np.diff(off)
+    assert np.all(sizes[mesh.ghost[vs:ve] == 1] == 0) and np.any(sizes > 0)
+
+
+def test_user_patches_through_the_python_hook():
+    """-pc_patch_construction_type python + -pc_patch_construction_python_type (ssc/patch.py:169-181, ssc/libssc.c:1594-1598)."""
+    from ssc_b200 import petsc_lite as pl
+    mesh = plex.RectangleMesh(4, 3, 1, 1)
+    form, bcs = fem.poisson_problem(mesh, 2, "scalar")
+    disc = fem.discretisation_from_form(form, bcs)
+    star = make_oracle(disc)
+    pl.Options.clear()
+    pl.Options("t_").setValue("pc_patch_construction_type", "python")
+    pl.Options("t_").setValue("pc_patch_construction_python_type", "user_patch_example.vertex_stars")
+    pc = PC(device=-1)
+    pc.setOptionsPrefix("t_")
+    setup_patch_pc(pc, form, bcs)
+    pc.setFromOptions()
+    pl.Options.clear()
+    assert all(np.array_equal(a, b) for a, b in zip(star.patches(), pc.getPatches()))

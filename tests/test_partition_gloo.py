@@ -1,0 +1,108 @@
+"""The N>1 host logic on CPU: world_size-2 (and 3) `gloo` processes build their z-slabs, derive the star forest with
+all_gather_object exactly as bench.py does, run the patch loop with the oracle, exchange halos over gloo, and must
+reproduce the single-rank result ("oracle with k partitions must equal the 1-partition result")."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+C, P = 4, 2
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _oracle_for(disc, V):
+    import scipy.sparse as sp
+    from oracle.oracle import OraclePatchPC
+    from ssc_b200 import synth
+    o = OraclePatchPC()
+    o.setFromDiscretisation(disc)
+    o.setOptions()
+    o.setUpPatches()
+    r, c, v = synth.tensor_poisson_csr(V, disc.ghost_bc_nodes)
+    o.setOperatorCSR(sp.csr_matrix((v, c, r), shape=(V.node_count,) * 2))
+    o.setUpOperators()
+    return o
+
+
+def _worker(rank, nranks, port, outdir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from ssc_b200 import partition
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=nranks)
+
+    def allgather(obj):
+        out = [None] * nranks
+        dist.all_gather_object(out, obj)
+        return out
+    slab = partition.ZSlab((C, C, C * nranks), P, rank, nranks)
+    sl, sr, neigh, so, sroot, ro, rleaf = partition.star_forest(slab.global_ids, slab.nowned, rank, nranks, allgather)
+    o = _oracle_for(slab.discretisation, slab.space)
+    xlat = np.random.default_rng(7).uniform(-1, 1, int(np.prod(slab.global_shape)))     # same on every rank
+    x = xlat[slab.global_ids[:slab.nowned]]
+    xl = np.zeros(slab.space.node_count)
+    xl[sl] = x[sr]
+
+    def exchange(send_chunks, recv_sizes):
+        reqs, bufs = [], []
+        for k, q in enumerate(neigh):
+            t = torch.from_numpy(np.ascontiguousarray(send_chunks[k]))
+            reqs.append(dist.isend(t, int(q)))
+            b = torch.zeros(recv_sizes[k], dtype=torch.float64)
+            reqs.append(dist.irecv(b, int(q)))
+            bufs.append(b)
+        for r in reqs:
+            r.wait()
+        return [b.numpy() for b in bufs]
+    # halo fill (SFBcast, ssc/libssc.c:1323): owners send, ghosts receive
+    got = exchange([x[sroot[so[k]:so[k + 1]]] for k in range(len(neigh))], [int(ro[k + 1] - ro[k]) for k in range(len(neigh))])
+    for k in range(len(neigh)):
+        xl[rleaf[ro[k]:ro[k + 1]]] = got[k]
+    yl = o.applyLocal(xl)
+    # overlap sum (SFReduce, :1399): ghosts send, owners add
+    y = np.zeros(slab.nowned)
+    y[sr] += yl[sl]
+    got = exchange([yl[rleaf[ro[k]:ro[k + 1]]] for k in range(len(neigh))], [int(so[k + 1] - so[k]) for k in range(len(neigh))])
+    for k in range(len(neigh)):
+        np.add.at(y, sroot[so[k]:so[k + 1]], got[k])
+    bc = slab.discretisation.global_bc_nodes
+    y[bc] = x[bc]
+    np.savez(os.path.join(outdir, "rank%d.npz" % rank), y=y, gid=slab.global_ids[:slab.nowned])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_slabs_over_gloo_match_single_rank(nranks, tmp_path):
+    import torch.multiprocessing as mp
+    from ssc_b200 import fem, plex
+    mp.spawn(_worker, args=(nranks, _free_port(), str(tmp_path)), nprocs=nranks, join=True)
+    mesh = plex.TensorPlex((C, C, C * nranks), lengths=(1, 1, nranks))
+    V = fem.FunctionSpace(mesh, P)
+    disc = fem.Discretisation([V])
+    o = _oracle_for(disc, V)
+    lat_of_node = np.empty(V.node_count, dtype=np.int64)
+    lat_of_node[V.lattice_node.ravel()] = np.arange(V.node_count)
+    xlat = np.random.default_rng(7).uniform(-1, 1, V.node_count)
+    y = o.apply(xlat[lat_of_node])
+    ylat = np.empty_like(y)
+    ylat[lat_of_node] = y
+    seen = np.zeros(V.node_count, dtype=int)
+    for r in range(nranks):
+        d = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        seen[d["gid"]] += 1
+        assert np.abs(d["y"] - ylat[d["gid"]]).max() <= 1e-14 * np.abs(ylat).max()
+    assert np.all(seen == 1)          # every global dof is owned by exactly one rank
