@@ -105,6 +105,7 @@ struct SSCPatchPC_s {
     bool save_operators = true, partition_of_unity = false, multiplicative = false, print_patches = false;
     bool symmetrise_sweep = false, keep_operators = false, dim_set = false, codim_set = false;
     int sub_pc = SSC_SUB_LU;
+    int factor_variant = 1;       // 1: register-resident Gauss-Jordan for n <= 128, 0: shared-memory kernel
     int apply_variant = 1;        // 0: simple loop, 1: pipelined LDG.64, 2: pipelined LDG.128 (even row stride)
     std::string sub_mat_type, sub_ksp_type = "preonly";
     BuildOptions bopt;
@@ -356,6 +357,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_keep_dofs_table") return parse_bool(v, &pc->bopt.keep_dofs);
     if (name == "ssc_keep_patch_operators") return parse_bool(v, &pc->keep_operators);
     if (name == "ssc_builder_threads") { pc->bopt.nthreads = atoi(v); return 0; }
+    if (name == "ssc_factor_variant") { pc->factor_variant = atoi(v); return 0; }
     if (name == "ssc_apply_variant") {
         const int a = atoi(v);
         if (a < 0 || a > 2) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "ssc_apply_variant must be 0, 1 or 2");
@@ -708,9 +710,16 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
 #define LAUNCH_INV(P, S)                                                                                              \
     do {                                                                                                              \
         if (smem_f > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_invert_kernel<P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
-        ssc_invert_kernel<P, S><<<grid_f, bdf, smem_f, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail);                   \
+        ssc_invert_kernel<P, S><<<grid_f, bdf, smem_f, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail);             \
     } while (0)
-    if (pivot && shared) LAUNCH_INV(true, true);
+    if (n <= 128 && pc->factor_variant == 1) {
+        // register-resident tiles: (n/8) x (n/4) threads
+        const int TC = (n + 3) / 4, TR = (n + 7) / 8;
+        const int threads = (TR * TC + 31) / 32 * 32;
+        if (pivot) ssc_invert_reg_kernel<true><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC);
+        else ssc_invert_reg_kernel<false><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC);
+    }
+    else if (pivot && shared) LAUNCH_INV(true, true);
     else if (pivot) LAUNCH_INV(true, false);
     else if (shared) LAUNCH_INV(false, true);
     else LAUNCH_INV(false, false);

@@ -160,3 +160,59 @@ def test_apply_kernel_variants(variant, shape, p, kind):
     assert relerr(y, o.apply(x)) < TOL
     i = int(np.argmax(np.diff(pc.getPatches()[0])))
     assert np.array_equal(pc.getPatchMatrix(i), o.patchMatrix(i))
+
+
+@pytest.mark.parametrize("factor_variant", [0, 1])
+@pytest.mark.parametrize("n", [5, 33, 64, 100, 128, 150])
+def test_general_blocks_need_pivoting(n, factor_variant):
+    """Non-symmetric operator with zero diagonal entries: -sub_pc_type lu must pivot.  Patches are arbitrary dof sets
+    handed over with SSCPatchSetPatches; the oracle solves with LAPACK-style partial-pivot LU."""
+    import scipy.sparse as sp
+    from ssc_b200 import PC
+    from oracle.oracle import OraclePatchPC
+    rng = np.random.default_rng(n)
+    N = 4 * n
+    A = sp.random(N, N, density=min(1.0, 40.0 / N), random_state=rng, format="lil")
+    A.setdiag(0.0)
+    perm = rng.permutation(N)
+    for i in range(N):                      # a permutation matrix + noise: nonsingular, zero diagonal
+        A[i, perm[i]] = 4.0 + rng.uniform()
+    A = A.tocsr()
+    A.sort_indices()
+    npatch = 6
+    lists = [np.sort(rng.choice(N, size=n, replace=False)) for _ in range(npatch)]
+    # make every block nonsingular: include, for each row dof, the column where its big entry sits
+    lists = [np.unique(np.concatenate([l[: n // 2], perm[l[: n // 2]]]))[:n] for l in lists]
+    lists = [l for l in lists if np.linalg.cond(A[l][:, l].toarray()) < 1e6]
+    assert lists
+    off = np.concatenate(([0], np.cumsum([l.size for l in lists])))
+    gtol = np.concatenate(lists)
+    o = OraclePatchPC()
+    o.setPatches(off, gtol, N)
+    o.setOperatorCSR(A)
+    o.setUpOperators()
+    pc = PC(device=0)
+    pc.setOption("ssc_factor_variant", factor_variant)
+    pc.setPatches(off, gtol, N)
+    pc.setOperatorCSR(A.indptr, A.indices, A.data)
+    pc.setUp()
+    x = rhs_vector(N)
+    y = np.zeros(N)
+    pc.apply(x, y)
+    ref = o.applyLocal(x)
+    assert relerr(y, ref) < 1e-9
+    for i, l in enumerate(lists):
+        B = A[l][:, l].toarray()
+        assert np.abs(pc.getPatchMatrix(i, inverse=True) @ B - np.eye(l.size)).max() < 1e-8
+
+
+def test_singular_block_is_reported():
+    import scipy.sparse as sp
+    from ssc_b200 import PC, SSCError
+    A = sp.csr_matrix(np.array([[1.0, 2.0, 0.0], [2.0, 4.0, 0.0], [0.0, 0.0, 1.0]]))
+    pc = PC(device=0)
+    pc.setPatches([0, 2, 3], [0, 1, 2], 3)
+    pc.setOperatorCSR(A.indptr, A.indices, A.data)
+    with pytest.raises(SSCError) as e:
+        pc.setUp()
+    assert e.value.ierr == 71 and pc.size("failed_patches") == 1
