@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--apply-variant", type=int, default=None, help="ssc_apply_variant (kernel selection; default = library default)")
+    ap.add_argument("--host-pipeline", type=int, default=None, help="ssc_host_pipeline (slabs of the overlapped host-space apply)")
     return ap.parse_args()
 
 
@@ -215,6 +216,8 @@ def main():
     pc.setOperatorCSR(*csr)
     if args.apply_variant is not None:
         pc.setOption("ssc_apply_variant", args.apply_variant)
+    if args.host_pipeline is not None:
+        pc.setOption("ssc_host_pipeline", args.host_pipeline)
     if nranks > 1:
         uid = [get_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -298,8 +301,15 @@ def main():
     bytes_apply = pc.size("bytes_apply")
     kernel_ms = kms / max(kn, 1)
     achieved = bytes_apply / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:            # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this workload (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "apply_traffic.json")))
+        if tj.get("cells") == args.cells and tj.get("degree") == args.degree:
+            traffic = tj["dram_bytes_per_apply"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "ssc_apply_kernel (all size classes of one apply)", "kernel_ms": kernel_ms,
+                "traffic": traffic, "kernel": "ssc_apply_kernel (all size classes of one apply)", "kernel_ms": kernel_ms,
                 "algorithmic_bytes": bytes_apply, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
     out = {"metric": METRIC, "value": nglobal / (ms_step * 1e-3), "unit": "dofs/s", "n_gpus": nranks, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

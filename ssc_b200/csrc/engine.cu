@@ -152,6 +152,14 @@ struct SSCPatchPC_s {
     double *d_vals = nullptr;
     bool csr_owned = false;
     void *d_flush = nullptr;
+    // pipelined host-space apply: H2D of x, patch kernels and D2H of y overlap slab by slab
+    int pipe_slabs = 8;
+    bool pipe_force = false;
+    bool pipe_ready = false;
+    std::vector<std::vector<std::pair<i64, i64>>> pipe_ranges;   // [slab][class] -> sorted positions [q0, q1)
+    std::vector<i64> pipe_in, pipe_out, pipe_bc;                 // x piece bounds, y piece bounds, bc list offsets per y piece
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_k;
     // timing
     std::map<std::string, double> event_ms;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -241,7 +249,7 @@ static void free_device_state(PC *pc)
     dev_free(pc->d_sendbuf); dev_free(pc->d_recvbuf);
     if (pc->csr_owned) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); }
     pc->d_rowptr = nullptr; pc->d_colidx = nullptr; pc->d_vals = nullptr; pc->csr_owned = false;
-    pc->classes.clear(); pc->device_ready = false; pc->setup_done = false;
+    pc->classes.clear(); pc->device_ready = false; pc->setup_done = false; pc->pipe_ready = false;
 }
 
 extern "C" int SSCPatchReset(SSCPatchPC pc)
@@ -267,6 +275,9 @@ extern "C" int SSCPatchDestroy(SSCPatchPC *ppc)
     cudaStreamSynchronize(pc->stream);
     free_device_state(pc);
     if (pc->d_flush) cudaFree(pc->d_flush);
+    if (pc->s_in) { cudaStreamDestroy(pc->s_in); cudaStreamDestroy(pc->s_out); }
+    for (auto &ev : pc->ev_in) cudaEventDestroy(ev);
+    for (auto &ev : pc->ev_k) cudaEventDestroy(ev);
     for (auto &e : pc->kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (pc->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(pc->comm);
     cudaEventDestroy(pc->ev0); cudaEventDestroy(pc->ev1);
@@ -358,6 +369,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_keep_patch_operators") return parse_bool(v, &pc->keep_operators);
     if (name == "ssc_builder_threads") { pc->bopt.nthreads = atoi(v); return 0; }
     if (name == "ssc_factor_variant") { pc->factor_variant = atoi(v); return 0; }
+    if (name == "ssc_host_pipeline") { const int s = atoi(v); pc->pipe_force = s < 0; pc->pipe_slabs = s < 0 ? -s : s; pc->pipe_ready = false; return 0; }   // negative: use it whatever the problem size
     if (name == "ssc_apply_variant") {
         const int a = atoi(v);
         if (a < 0 || a > 2) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "ssc_apply_variant must be 0, 1 or 2");
@@ -735,6 +747,7 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
     return 0;
 }
 
+static int build_host_pipeline(PC *pc);
 static int compute_weights(PC *pc)
 {
     // ssc/libssc.c:1254-1284: scatter ones through every patch, reduce to owners, reciprocal
@@ -778,6 +791,7 @@ extern "C" int SSCPatchSetUp(SSCPatchPC pc)
     } else {
         CUDA_OK(cudaStreamSynchronize(pc->stream));
     }
+    if (!pc->pipe_ready) CHK(build_host_pipeline(pc));
     pc->setup_done = true;
     return 0;
 }
@@ -858,12 +872,102 @@ static int apply_device(PC *pc, const double *x, double *y)
     return 0;
 }
 
+// Slab schedule for host-space applies.  Patches keep their construction (mesh) order inside a size class, and dof
+// numbers follow the mesh too, so consecutive patches touch a moving window of x and y.  The patch list is cut into
+// S slabs by original patch number; slab s can start once x[0, in[s+1]) has arrived and, once it is done,
+// y[out[s], out[s+1]) is final.  With an unrelated numbering the bounds collapse to "everything first" and the path
+// degenerates to the serial one -- it is never wrong, only not overlapped.
+static int build_host_pipeline(PC *pc)
+{
+    pc->pipe_ready = false;
+    const int S = pc->pipe_slabs;
+    if (S < 2 || pc->sf_set || !pc->save_operators || (!pc->pipe_force && pc->sum_n2 * 8 < ((i64)64 << 20))) return 0;
+    if (pc->lists.npatch < S) return 0;
+    const PatchLists &L = pc->lists;
+    const i64 np = L.npatch, N = pc->nowned;
+    std::vector<i64> lo(S, N), hi(S, -1);
+    pc->pipe_ranges.assign(S, std::vector<std::pair<i64, i64>>(pc->classes.size()));
+    for (int s = 0; s < S; ++s) {
+        const i64 p0 = np * s / S, p1 = np * (s + 1) / S;
+        for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
+            const SizeClass &c = pc->classes[ci];
+            auto first = pc->sorted2orig.begin() + c.first, last = first + c.count;
+            const i64 q0 = std::lower_bound(first, last, p0) - pc->sorted2orig.begin();
+            const i64 q1 = std::lower_bound(first, last, p1) - pc->sorted2orig.begin();
+            pc->pipe_ranges[s][ci] = {q0, q1};
+        }
+        for (i64 p = p0; p < p1; ++p)
+            for (i64 k = L.gtolOff[p]; k < L.gtolOff[p + 1]; ++k) { lo[s] = std::min(lo[s], L.gtol[k]); hi[s] = std::max(hi[s], L.gtol[k]); }
+    }
+    pc->pipe_in.assign(S + 1, 0); pc->pipe_out.assign(S + 1, 0);
+    i64 run = 0;
+    for (int s = 0; s < S; ++s) { run = std::max(run, hi[s] + 1); pc->pipe_in[s + 1] = s == S - 1 ? N : run; }
+    i64 suf = N;
+    pc->pipe_out[S] = N;
+    for (int s = S - 1; s >= 1; --s) { suf = std::min(suf, lo[s]); pc->pipe_out[s] = suf; }
+    for (int s = 1; s <= S; ++s) pc->pipe_out[s] = std::max(pc->pipe_out[s], pc->pipe_out[s - 1]);
+    // Dirichlet list offsets per y piece (the list is uploaded in ascending order)
+    std::vector<i64> bc;
+    for (i64 d : pc->globalBc) if (d >= 0 && d < N) bc.push_back(d);
+    if (!std::is_sorted(bc.begin(), bc.end())) return 0;
+    pc->pipe_bc.assign(S + 1, 0);
+    for (int s = 0; s <= S; ++s) pc->pipe_bc[s] = std::lower_bound(bc.begin(), bc.end(), pc->pipe_out[s]) - bc.begin();
+    if (!pc->s_in) {
+        CUDA_OK(cudaStreamCreateWithFlags(&pc->s_in, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&pc->s_out, cudaStreamNonBlocking));
+    }
+    while ((int)pc->ev_in.size() < S + 1) {
+        cudaEvent_t a, b;
+        CUDA_OK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        pc->ev_in.push_back(a); pc->ev_k.push_back(b);
+    }
+    pc->pipe_ready = true;
+    return 0;
+}
+
+static int apply_host_pipelined(PC *pc, const double *x, double *y)
+{
+    const int S = pc->pipe_slabs;
+    double *dx = pc->d_xs, *dy = pc->d_ys;
+    const double scale = pc->symmetrise_sweep ? 2.0 : 1.0;
+    CUDA_OK(cudaMemsetAsync(dy, 0, (size_t)pc->nowned * sizeof(double), pc->stream));
+    CUDA_OK(cudaEventRecord(pc->ev_k[S], pc->stream));
+    CUDA_OK(cudaStreamWaitEvent(pc->s_in, pc->ev_k[S], 0));        // do not overwrite x while an earlier apply still reads it
+    for (int s = 0; s < S; ++s) {
+        const i64 a = pc->pipe_in[s], b = pc->pipe_in[s + 1];
+        if (b > a) CUDA_OK(cudaMemcpyAsync(dx + a, x + a, (size_t)(b - a) * sizeof(double), cudaMemcpyHostToDevice, pc->s_in));
+        CUDA_OK(cudaEventRecord(pc->ev_in[s], pc->s_in));
+    }
+    for (int s = 0; s < S; ++s) {
+        CUDA_OK(cudaStreamWaitEvent(pc->stream, pc->ev_in[s], 0));
+        for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
+            const SizeClass &c = pc->classes[ci];
+            const i64 q0 = pc->pipe_ranges[s][ci].first, q1 = pc->pipe_ranges[s][ci].second;
+            if (q1 > q0) CHK(launch_apply_class(pc, c, q0, q1, pc->d_blocks + c.moff + (q0 - c.first) * c.stride, dx, dy, scale));
+        }
+        const i64 a = pc->pipe_out[s], b = pc->pipe_out[s + 1];
+        const i64 nb = pc->pipe_bc[s + 1] - pc->pipe_bc[s];
+        if (nb > 0) { ssc_bc_kernel<<<grid_for(nb, 256), 256, 0, pc->stream>>>(pc->d_bc + pc->pipe_bc[s], nb, dx, dy); pc->launches++; }
+        if (pc->partition_of_unity && b > a) { ssc_scale_kernel<<<grid_for(b - a, 256), 256, 0, pc->stream>>>(b - a, pc->d_w + a, dy + a); pc->launches++; }
+        CUDA_OK(cudaEventRecord(pc->ev_k[s], pc->stream));
+        CUDA_OK(cudaStreamWaitEvent(pc->s_out, pc->ev_k[s], 0));
+        if (b > a) CUDA_OK(cudaMemcpyAsync(y + a, dy + a, (size_t)(b - a) * sizeof(double), cudaMemcpyDeviceToHost, pc->s_out));
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(pc->s_out));
+    CUDA_OK(cudaStreamSynchronize(pc->stream));
+    return 0;
+}
+
 extern "C" int SSCPatchApply(SSCPatchPC pc, const double *x, double *y, int memspace)
 {
     if (!pc || !x || !y) return ssc_set_error(SSC_ERR_ARG_NULL, "null argument");
     CHK(set_device(pc));
     if (memspace == SSC_MEM_DEVICE) return apply_device(pc, x, y);
+    if (!pc->setup_done) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "SSCPatchSetUp() has not been called");
     if (!pc->d_xs) { CHK(dev_alloc(&pc->d_xs, pc->nowned)); CHK(dev_alloc(&pc->d_ys, pc->nowned)); }
+    if (pc->pipe_ready && pc->partition_of_unity && !pc->d_w) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "partition of unity was switched on after the first setup");
+    if (pc->pipe_ready) return apply_host_pipelined(pc, x, y);
     CUDA_OK(cudaMemcpyAsync(pc->d_xs, x, (size_t)pc->nowned * sizeof(double), cudaMemcpyHostToDevice, pc->stream));
     CHK(apply_device(pc, pc->d_xs, pc->d_ys));
     CUDA_OK(cudaMemcpyAsync(y, pc->d_ys, (size_t)pc->nowned * sizeof(double), cudaMemcpyDeviceToHost, pc->stream));

@@ -216,3 +216,25 @@ def test_singular_block_is_reported():
     with pytest.raises(SSCError) as e:
         pc.setUp()
     assert e.value.ierr == 71 and pc.size("failed_patches") == 1
+
+
+@pytest.mark.parametrize("pou", [0, 1])
+@pytest.mark.parametrize("slabs", [-2, -5])
+def test_pipelined_host_apply(slabs, pou):
+    """Host-space applies overlap H2D(x) / patch kernels / D2H(y) slab by slab (forced on for this small case)."""
+    from ssc_b200 import PinnedArray
+    form, bcs, disc, A = _problem(plex.TensorPlex((5, 4, 4)), 3, "scalar")
+    o = make_oracle(disc, A, partition_of_unity=pou)
+    pc = make_gpu(form, bcs, ssc_host_pipeline=slabs, partition_of_unity=pou)
+    pc.setUp()
+    xh, yh = PinnedArray(pc, disc.total_dofs), PinnedArray(pc, disc.total_dofs)
+    for seed in (20260101, 20260102, 20260103):
+        xh.array[:] = rhs_vector(disc.total_dofs, seed)
+        yh.array[:] = np.nan
+        pc.apply(xh.array, yh.array)
+        assert relerr(yh.array, o.apply(xh.array)) < TOL
+    # pageable memory works too
+    x = rhs_vector(disc.total_dofs)
+    y = np.zeros_like(x)
+    pc.apply(x, y)
+    assert relerr(y, o.apply(x)) < TOL
