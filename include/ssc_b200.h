@@ -148,6 +148,22 @@ int SSCEventRecord(SSCPatchPC pc, void *ev);
 int SSCEventElapsed(SSCPatchPC pc, void *start, void *stop, double *ms);  /* synchronises on stop */
 int SSCEventDestroy(SSCPatchPC pc, void *ev);
 
+/* ---- low-order (P1) coarse correction, SURVEY.md 8(f) N1: class P1PC of ssc/lo.py:105-198 ------------------ */
+/* y = R^T A1^{-1} R x with Dirichlet values carried over.  The host assembles R (ssc/lo.py:83-102) and the coarse
+ * operator A1 (ssc/lo.py:142-144); the device does the two sparse products and the coarse solve (dense LU: coarse
+ * spaces up to 3000 dofs in this build).  Option names: lo_ksp_type (preonly), lo_pc_type (lu | cholesky), lo_mat_type. */
+typedef struct SSCLowOrderPC_s *SSCLowOrderPC;
+int SSCLowOrderCreate(int device, SSCLowOrderPC *lo);                       /* P1PC.__init__            ssc/lo.py:107-110 */
+int SSCLowOrderDestroy(SSCLowOrderPC *lo);
+int SSCLowOrderSetOption(SSCLowOrderPC lo, const char *name, const char *value);   /* lo.setFromOptions ssc/lo.py:164-167 */
+int SSCLowOrderSetRestriction(SSCLowOrderPC lo, SSCInt ncoarse, SSCInt nfine, const SSCInt *rowptr,
+                              const int32_t *colidx, const double *vals);   /* restriction_matrix       ssc/lo.py:83-102 */
+int SSCLowOrderSetOperator(SSCLowOrderPC lo, SSCInt n, const SSCInt *rowptr, const int32_t *colidx,
+                           const double *vals);                             /* lo_op                    ssc/lo.py:142-144 */
+int SSCLowOrderSetBcs(SSCLowOrderPC lo, SSCInt nbc, const SSCInt *bcIndices);      /* bc_indices        ssc/lo.py:175-183 */
+int SSCLowOrderSetUp(SSCLowOrderPC lo);                                     /* initialize / update      ssc/lo.py:112-186 */
+int SSCLowOrderApply(SSCLowOrderPC lo, const double *x, double *y, int memspace);  /* apply             ssc/lo.py:187-198 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,12 +7,17 @@
  * ssc_b200/ may load it.
  *
  * Parity status: the reference cannot be compiled here (it needs PETSc private
- * headers, ssc/libssc.c:1-4) and its tests hold no golden vectors; the only
- * reference-held known answers for this path are (i) "vertex-star patches at
- * degree 1 are point Jacobi" (tests/test_jacobi_equivalent.py:85) and (ii) the
- * CG iteration counts of tests/test_p_independence.py:17-24.  This oracle is
- * pinned against (i) in tests/test_oracle_known_answers.py; PCApply *values* for degree >= 2 are
- * "parity unpinned" by the reference's own tests.
+ * headers, ssc/libssc.c:1-4) and its tests hold no golden vectors.  The known
+ * answers the reference's own tests hold for this path are both reproduced:
+ *  (i) "vertex-star patches at degree 1 are point Jacobi", scalar / vector /
+ *      tensor / mixed on its three meshes (tests/test_jacobi_equivalent.py:85)
+ *      -> tests/test_oracle_known_answers.py;
+ * (ii) the twelve CG iteration counts of ssc.SSC for degrees 1..4
+ *      (tests/test_p_independence.py:17-24: [5,5,5,5], [10,12,12,12], [4,21,22,22])
+ *      -> tests/test_p_independence.py, with this oracle as the patch PC.
+ * (ii) pins PCApply for degrees 2-4 through integer outcomes, not through
+ * vectors: no reference-produced PCApply vector exists to compare with, and the
+ * order inside gtol remains defined by this oracle.
  *
  * What is restated, with the lines it follows:
  *   transitive closure / star      DMPlexGetTransitiveClosure call sites :344 :348 :1460 (PETSc, external)

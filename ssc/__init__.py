@@ -1,2 +1,3 @@
-"""Drop-in name: ``-pc_python_type ssc.PatchPC`` resolves here (cf. ssc/__init__.py:2 of the reference)."""
+"""Drop-in names: ``-pc_python_type ssc.PatchPC`` / ``ssc.SSC`` resolve here (cf. ssc/__init__.py:1-2 of the reference)."""
+from ssc_b200.ssc_pc import SSC      # noqa: F401
 from ssc_b200.patch import PatchPC   # noqa: F401

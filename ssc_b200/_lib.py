@@ -70,6 +70,14 @@ _sigs = {
     "SSCEventRecord": [_H, C.c_void_p],
     "SSCEventElapsed": [_H, C.c_void_p, C.c_void_p, f64p],
     "SSCEventDestroy": [_H, C.c_void_p],
+    "SSCLowOrderCreate": [C.c_int, C.POINTER(_H)],
+    "SSCLowOrderDestroy": [C.POINTER(_H)],
+    "SSCLowOrderSetOption": [_H, C.c_char_p, C.c_char_p],
+    "SSCLowOrderSetRestriction": [_H, C.c_int64, C.c_int64, i64p, i32p, f64p],
+    "SSCLowOrderSetOperator": [_H, C.c_int64, i64p, i32p, f64p],
+    "SSCLowOrderSetBcs": [_H, C.c_int64, i64p],
+    "SSCLowOrderSetUp": [_H],
+    "SSCLowOrderApply": [_H, C.c_void_p, C.c_void_p, C.c_int],
 }
 EXPORTS = sorted(_sigs) + ["SSCGetLastError"]
 for _name, _args in _sigs.items():

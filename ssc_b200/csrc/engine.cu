@@ -1165,3 +1165,154 @@ extern "C" int SSCEventElapsed(SSCPatchPC pc, void *start, void *stop, double *m
     return 0;
 }
 extern "C" int SSCEventDestroy(SSCPatchPC pc, void *ev) { CHK(set_device(pc)); CUDA_OK(cudaEventDestroy((cudaEvent_t)ev)); return 0; }
+
+// ---------------------------------------------------------------------------------------------
+// Low-order (P1) coarse correction: y = R^T A1^-1 R x, Dirichlet values passed through (ssc/lo.py:105-198).
+// SURVEY.md 8(f) N1.  The coarse solve (-lo_pc_type lu) reuses the patch engine: the coarse space is one patch
+// holding every coarse dof, so "extract, invert, multiply" are the same kernels.  Dense, therefore bounded in size.
+// ---------------------------------------------------------------------------------------------
+struct DeviceCSR { i64 nrows = 0, ncols = 0, nnz = 0; i64 *rowptr = nullptr; int *colidx = nullptr; double *vals = nullptr; };
+struct SSCLowOrderPC_s {
+    int device = 0;
+    PC *coarse = nullptr;          // single-patch PC on the coarse operator
+    DeviceCSR R, RT;
+    i64 nfine = 0, ncoarse = 0, nbc = 0;
+    int *d_bc = nullptr;
+    double *d_w = nullptr, *d_v = nullptr, *d_xs = nullptr, *d_ys = nullptr;
+    std::vector<i64> a_rowptr; std::vector<int32_t> a_colidx; std::vector<double> a_vals;
+    bool have_R = false, have_A = false, setup = false;
+};
+typedef SSCLowOrderPC_s LO;
+
+static void free_csr(DeviceCSR &m) { dev_free(m.rowptr); dev_free(m.colidx); dev_free(m.vals); }
+static int upload_csr_matrix(LO *lo, DeviceCSR &m, i64 nrows, i64 ncols, const i64 *rowptr, const int32_t *colidx, const double *vals)
+{
+    free_csr(m);
+    m.nrows = nrows; m.ncols = ncols; m.nnz = rowptr[nrows];
+    CHK(dev_alloc(&m.rowptr, nrows + 1)); CHK(dev_alloc(&m.colidx, m.nnz)); CHK(dev_alloc(&m.vals, m.nnz));
+    CUDA_OK(cudaMemcpy(m.rowptr, rowptr, (size_t)(nrows + 1) * sizeof(i64), cudaMemcpyHostToDevice));
+    if (m.nnz) {
+        CUDA_OK(cudaMemcpy(m.colidx, colidx, (size_t)m.nnz * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(m.vals, vals, (size_t)m.nnz * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    (void)lo;
+    return 0;
+}
+
+extern "C" int SSCLowOrderCreate(int device, SSCLowOrderPC *out)
+{
+    LO *lo = new LO();
+    lo->device = device;
+    int ierr = SSCPatchCreate(device, &lo->coarse);
+    if (ierr) { delete lo; return ierr; }
+    *out = lo;
+    return 0;
+}
+extern "C" int SSCLowOrderDestroy(SSCLowOrderPC *plo)
+{
+    if (!plo || !*plo) return 0;
+    LO *lo = *plo;
+    cudaSetDevice(lo->device);
+    free_csr(lo->R); free_csr(lo->RT);
+    dev_free(lo->d_bc); dev_free(lo->d_w); dev_free(lo->d_v); dev_free(lo->d_xs); dev_free(lo->d_ys);
+    SSCPatchDestroy(&lo->coarse);
+    delete lo;
+    *plo = nullptr;
+    return 0;
+}
+extern "C" int SSCLowOrderSetOption(SSCLowOrderPC lo, const char *name_, const char *value)
+{
+    std::string name(name_ ? name_ : ""), v(value ? value : "");
+    if (name == "lo_ksp_type") { if (v != "preonly") return ssc_set_error(SSC_ERR_SUP, "lo_ksp_type '%s' is not supported (preonly)", v.c_str()); return 0; }
+    if (name == "lo_pc_type") {
+        if (v == "lu") return SSCPatchSetOption(lo->coarse, "sub_pc_type", "lu");
+        if (v == "cholesky") return SSCPatchSetOption(lo->coarse, "sub_pc_type", "cholesky");
+        return ssc_set_error(SSC_ERR_SUP, "lo_pc_type '%s' is not supported (lu, cholesky)", v.c_str());
+    }
+    if (name == "lo_mat_type") return 0;
+    return ssc_set_error(SSC_ERR_USER, "unknown option '%s'", name.c_str());
+}
+// restriction matrix of ssc/lo.py:83-102: ncoarse x nfine, rows/columns of Dirichlet nodes already dropped
+extern "C" int SSCLowOrderSetRestriction(SSCLowOrderPC lo, SSCInt ncoarse, SSCInt nfine, const SSCInt *rowptr, const int32_t *colidx, const double *vals)
+{
+    CUDA_OK(cudaSetDevice(lo->device));
+    CHK(upload_csr_matrix(lo, lo->R, ncoarse, nfine, rowptr, colidx, vals));
+    // transpose on the host (set-up only)
+    const i64 nnz = rowptr[ncoarse];
+    std::vector<i64> tp((size_t)nfine + 1, 0);
+    for (i64 k = 0; k < nnz; ++k) tp[colidx[k] + 1]++;
+    for (i64 j = 0; j < nfine; ++j) tp[j + 1] += tp[j];
+    std::vector<int32_t> tc((size_t)nnz);
+    std::vector<double> tv((size_t)nnz);
+    std::vector<i64> fill(tp.begin(), tp.end() - 1);
+    for (i64 i = 0; i < ncoarse; ++i)
+        for (i64 k = rowptr[i]; k < rowptr[i + 1]; ++k) { const i64 d = fill[colidx[k]]++; tc[d] = (int32_t)i; tv[d] = vals[k]; }
+    CHK(upload_csr_matrix(lo, lo->RT, nfine, ncoarse, tp.data(), tc.data(), tv.data()));
+    lo->nfine = nfine; lo->ncoarse = ncoarse; lo->have_R = true;
+    dev_free(lo->d_w); dev_free(lo->d_v); dev_free(lo->d_xs); dev_free(lo->d_ys);
+    CHK(dev_alloc(&lo->d_w, ncoarse)); CHK(dev_alloc(&lo->d_v, ncoarse)); CHK(dev_alloc(&lo->d_xs, nfine)); CHK(dev_alloc(&lo->d_ys, nfine));
+    return 0;
+}
+// coarse operator of ssc/lo.py:142-144 (rows of Dirichlet nodes = identity); values are copied, re-settable before every SetUp
+extern "C" int SSCLowOrderSetOperator(SSCLowOrderPC lo, SSCInt n, const SSCInt *rowptr, const int32_t *colidx, const double *vals)
+{
+    lo->a_rowptr.assign(rowptr, rowptr + n + 1);
+    lo->a_colidx.assign(colidx, colidx + rowptr[n]);
+    lo->a_vals.assign(vals, vals + rowptr[n]);
+    lo->have_A = true;
+    if (lo->ncoarse && lo->ncoarse != n) return ssc_set_error(SSC_ERR_ARG_INCOMP, "coarse operator has %lld rows, restriction has %lld", (long long)n, (long long)lo->ncoarse);
+    return 0;
+}
+// owned Dirichlet dofs of the fine space (ssc/lo.py:175-183)
+extern "C" int SSCLowOrderSetBcs(SSCLowOrderPC lo, SSCInt nbc, const SSCInt *bc)
+{
+    CUDA_OK(cudaSetDevice(lo->device));
+    std::vector<int> b32((size_t)nbc);
+    for (i64 i = 0; i < nbc; ++i) b32[(size_t)i] = (int)bc[i];
+    dev_free(lo->d_bc);
+    CHK(dev_alloc(&lo->d_bc, nbc));
+    if (nbc) CUDA_OK(cudaMemcpy(lo->d_bc, b32.data(), (size_t)nbc * sizeof(int), cudaMemcpyHostToDevice));
+    lo->nbc = nbc;
+    return 0;
+}
+// P1PC.initialize / update (ssc/lo.py:112-186): factorise the coarse operator
+extern "C" int SSCLowOrderSetUp(SSCLowOrderPC lo)
+{
+    if (!lo->have_R || !lo->have_A) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "set the restriction and the coarse operator before SetUp");
+    const i64 n = lo->ncoarse;
+    if (n > 3000) return ssc_set_error(SSC_ERR_SUP, "coarse space with %lld dofs: the dense coarse LU of this build is limited to 3000", (long long)n);
+    if (!lo->setup) {
+        std::vector<i64> off = {0, n}, gtol((size_t)n);
+        for (i64 i = 0; i < n; ++i) gtol[(size_t)i] = i;
+        CHK(SSCPatchSetPatches(lo->coarse, 1, off.data(), gtol.data(), n, n, 0, nullptr));
+    }
+    CHK(SSCPatchSetOperatorCSR(lo->coarse, n, lo->a_rowptr.data(), lo->a_colidx.data(), lo->a_vals.data(), SSC_MEM_HOST));
+    CHK(SSCPatchSetUp(lo->coarse));
+    lo->setup = true;
+    return 0;
+}
+// P1PC.apply (ssc/lo.py:187-198)
+extern "C" int SSCLowOrderApply(SSCLowOrderPC lo, const double *x, double *y, int memspace)
+{
+    if (!lo->setup) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "SSCLowOrderSetUp() has not been called");
+    CUDA_OK(cudaSetDevice(lo->device));
+    cudaStream_t st = lo->coarse->stream;
+    const double *dx = x;
+    double *dy = y;
+    if (memspace == SSC_MEM_HOST) {
+        CUDA_OK(cudaMemcpyAsync(lo->d_xs, x, (size_t)lo->nfine * sizeof(double), cudaMemcpyHostToDevice, st));
+        dx = lo->d_xs; dy = lo->d_ys;
+    }
+    const int bd = 256;
+    ssc_spmv_kernel<<<(unsigned)((lo->ncoarse * 32 + bd - 1) / bd), bd, 0, st>>>(lo->R.nrows, (const ll *)lo->R.rowptr, lo->R.colidx, lo->R.vals, dx, lo->d_w);
+    CHK(SSCPatchApply(lo->coarse, lo->d_w, lo->d_v, SSC_MEM_DEVICE));
+    ssc_spmv_kernel<<<(unsigned)((lo->nfine * 32 + bd - 1) / bd), bd, 0, st>>>(lo->RT.nrows, (const ll *)lo->RT.rowptr, lo->RT.colidx, lo->RT.vals, lo->d_v, dy);
+    if (lo->nbc) ssc_bc_kernel<<<grid_for(lo->nbc, 256), 256, 0, st>>>(lo->d_bc, lo->nbc, dx, dy);
+    lo->coarse->launches += 3;
+    CUDA_OK(cudaGetLastError());
+    if (memspace == SSC_MEM_HOST) {
+        CUDA_OK(cudaMemcpyAsync(y, lo->d_ys, (size_t)lo->nfine * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}

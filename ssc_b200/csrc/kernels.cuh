@@ -485,3 +485,17 @@ __global__ void ssc_fill_kernel(ll n, double *__restrict__ a, double v)
 {
     for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) a[i] = v;
 }
+
+// y = A x for a CSR matrix, one warp per row (restriction / prolongation of the low-order PC, ssc/lo.py:187-198)
+__global__ void ssc_spmv_kernel(ll nrows, const ll *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals,
+                                const double *__restrict__ x, double *__restrict__ y)
+{
+    const ll warp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= nrows) return;
+    double s = 0.0;
+    for (ll k = rowptr[warp] + lane; k < rowptr[warp + 1]; k += 32) s = fma(vals[k], __ldg(x + colidx[k]), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) y[warp] = s;
+}

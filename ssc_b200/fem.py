@@ -524,4 +524,30 @@ def poisson_problem(mesh, degree, kind="scalar"):
         disc = discretisation_from_form(form, bcs_)
         return apply_bcs(A, disc.ghost_bc_nodes)
     form = Form(spaces, assemble)
+    form.low_order = lambda: poisson_problem(mesh, 1, kind)          # the same form on the degree-1 space (ssc/lo.py:122-131)
+    form.load_vector = lambda: load_vector(spaces)
     return form, bcs
+
+
+def load_vector(spaces):
+    """inner(Constant(1), v)*dx for every component (the right-hand side of the reference's tests)."""
+    out = []
+    for V in spaces:
+        m = V.mesh
+        if m.cell_type == "simplex":
+            lam, w = simplex_quadrature(m.dim, V.degree + 1)
+            val, _ = V.tabulate_simplex(lam)
+            _, _, detJ = _simplex_geometry(m)
+            loc = val @ w
+            b = np.zeros(V.node_count)
+            np.add.at(b, V.cell_node_list.ravel(), (detJ[:, None] * loc[None, :]).ravel())
+        else:
+            _, Mh = reference_1d(V.degree)
+            loc = None
+            for a in range(m.dim):
+                f = Mh.sum(axis=1) * (m.lengths[a] / m.n[a])
+                loc = f if loc is None else np.kron(loc, f)
+            b = np.zeros(V.node_count)
+            np.add.at(b, V.cell_node_list.ravel(), np.broadcast_to(loc, V.cell_node_list.shape).ravel())
+        out.append(np.repeat(b, V.bs))
+    return np.concatenate(out)
