@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--apply-variant", type=int, default=None, help="ssc_apply_variant (kernel selection; default = library default)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo exchange: NVLink peer memory (default) or NCCL send/recv")
     ap.add_argument("--host-pipeline", type=int, default=None, help="ssc_host_pipeline (slabs of the overlapped host-space apply)")
     return ap.parse_args()
 
@@ -114,6 +115,7 @@ def build_problem(args, rank, nranks):
 
 def operator_csr(V, disc):
     from ssc_b200 import synth
+    synth.set_threads(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))   # torchrun pins OMP_NUM_THREADS=1
     return synth.tensor_poisson_csr(V, disc.ghost_bc_nodes)
 
 
@@ -184,12 +186,14 @@ def workload_config(args, nranks):
     c, p = args.cells, args.degree
     return {"workload": "3D Q%d Poisson, %dx%dx%d hex cells%s, vertex-star patches, additive, stored inverse (sub_pc_type lu)"
                         % (p, c, c, c * nranks, " (z-slabs of %d^3 per GPU)" % c if nranks > 1 else ""),
-            "cells_per_gpu": c ** 3, "degree": p, "parallelism": "patches by mesh slab x%d" % nranks,
+            "cells_per_gpu": c ** 3, "degree": p, "parallelism": "patches by mesh slab x%d" % nranks, "exchange": getattr(args, "exchange_used", None),
             "l2": "inputs larger than L2 (patch blocks %.1f GB per GPU), no flush" % (8 * ((2 * p - 1) ** 3) ** 2 * (c - 1) ** 3 / 1e9)}
 
 
 def main():
     args = parse()
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     nranks = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,6 +215,7 @@ def main():
     info["t_assemble"] = time.time() - t0
 
     pc = PC(device=local_rank)
+    exchange = None
     setup_patch_pc(pc, disc, None)
     pc._compute_op = None
     pc.setOperatorCSR(*csr)
@@ -219,12 +224,26 @@ def main():
     if args.host_pipeline is not None:
         pc.setOption("ssc_host_pipeline", args.host_pipeline)
     if nranks > 1:
-        uid = [get_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        pc.commInit(nranks, rank, uid[0])
         sf = partition.star_forest(slab.global_ids, slab.nowned, rank, nranks,
                                    lambda obj: _allgather(dist, obj, nranks))
         pc.setStarForest(slab.nowned, *sf)
+        exchange = args.exchange
+        if exchange == "p2p":
+            try:
+                partition.connect_peers(pc, sf, rank, lambda obj: _allgather(dist, obj, nranks))
+                ok = 1
+            except Exception as exc:                      # CUDA IPC not permitted in this container: say so and use NCCL
+                ok = 0
+                sys.stderr.write("rank %d: peer exchange unavailable (%s), using NCCL\n" % (rank, exc))
+            if min(_allgather(dist, ok, nranks)) == 0:
+                exchange = "nccl"
+                if ok:
+                    raise RuntimeError("peer exchange connected on this rank but not on all ranks")
+        if exchange == "nccl":
+            uid = [get_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            pc.commInit(nranks, rank, uid[0])
+    args.exchange_used = exchange if nranks > 1 else None
     t0 = time.time()
     pc.setUp()
     pc.synchronize()

@@ -94,6 +94,16 @@ int SSCPatchSetStarForest(SSCPatchPC pc, SSCInt nowned, SSCInt nself, const SSCI
 int SSCCommGetUniqueId(char uniqueId[128]);
 int SSCPatchCommInit(SSCPatchPC pc, int nranks, int rank, const char uniqueId[128]);
 
+/* NVLink peer exchange, an alternative to the NCCL path for ranks on one NVSwitch box.  Export gives 192 bytes (three
+ * CUDA IPC handles: local x vector, local y vector, barrier flags) to be handed to every neighbour.  Connect takes the
+ * neighbours' exports in the order of the star forest's neigh[], this rank's position in each neighbour's neigh[]
+ * (slotAtNeigh), and for every entry of sendRoot / recvLeaf the matching index on the neighbour (its ghost slot /
+ * its owned index).  After Connect the halo fill is direct peer stores and the overlap sum is issued by the patch
+ * kernel itself as fp64 reductions into the owners' vectors; SSCPatchCommInit is then not needed. */
+int SSCPatchPeerExport(SSCPatchPC pc, char *handles192);
+int SSCPatchPeerConnect(SSCPatchPC pc, const char *neighHandles, const int *slotAtNeigh, const SSCInt *remoteLeaf,
+                        const SSCInt *remoteRoot);
+
 /* ---- operator: replaces PCPatchSetComputeOperator ssc/libssc.c:293-308 (declared ssc/libssc.h:8) ------ */
 /* The reference re-assembles every patch matrix through a callback (:1150).  Here the patch blocks are cut out
  * of the assembled local operator in CSR form: rows for every local dof that lies in a patch, columns in local

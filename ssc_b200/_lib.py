@@ -44,6 +44,8 @@ _sigs = {
     "SSCPatchSetStarForest": [_H, C.c_int64, C.c_int64, i64p, i64p, C.c_int64, i32p, i64p, i64p, i64p, i64p],
     "SSCCommGetUniqueId": [C.c_char_p],
     "SSCPatchCommInit": [_H, C.c_int, C.c_int, C.c_char_p],
+    "SSCPatchPeerExport": [_H, C.c_char_p],
+    "SSCPatchPeerConnect": [_H, C.c_char_p, i32p, i64p, i64p],
     "SSCPatchSetOperatorCSR": [_H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
     "SSCPatchSetUp": [_H],
     "SSCPatchApply": [_H, C.c_void_p, C.c_void_p, C.c_int],

@@ -123,6 +123,16 @@ struct SSCPatchPC_s {
     std::vector<int> neigh;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // NVLink peer exchange (CUDA IPC)
+    bool p2p = false;
+    PeerScatter h_ps;
+    PeerScatter *d_ps = nullptr;
+    PeerPush h_push;
+    PeerFlags h_flags;
+    int *d_ghostPeer = nullptr, *d_ghostRemote = nullptr, *d_sendPeer = nullptr, *d_remoteLeaf = nullptr;
+    unsigned long long *d_flags = nullptr, epoch = 0;
+    int *d_timeout = nullptr;
+    std::vector<void *> ipc_opened;
     // operator (borrowed)
     i64 csr_nrows = 0;
     const i64 *csr_rowptr = nullptr;
@@ -244,7 +254,8 @@ static void free_device_state(PC *pc)
 {
     if (pc->device < 0) return;
     dev_free(pc->d_gtol); dev_free(pc->d_blocks); dev_free(pc->d_blocks0); dev_free(pc->d_fail); dev_free(pc->d_bc);
-    dev_free(pc->d_w); dev_free(pc->d_mult); dev_free(pc->d_xl); dev_free(pc->d_yl); dev_free(pc->d_xs); dev_free(pc->d_ys);
+    dev_free(pc->d_w); dev_free(pc->d_mult); dev_free(pc->d_xs); dev_free(pc->d_ys);
+    if (!pc->p2p) { dev_free(pc->d_xl); dev_free(pc->d_yl); }
     dev_free(pc->d_selfLeaf); dev_free(pc->d_selfRoot); dev_free(pc->d_sendRoot); dev_free(pc->d_recvLeaf);
     dev_free(pc->d_sendbuf); dev_free(pc->d_recvbuf);
     if (pc->csr_owned) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); }
@@ -275,6 +286,10 @@ extern "C" int SSCPatchDestroy(SSCPatchPC *ppc)
     cudaStreamSynchronize(pc->stream);
     free_device_state(pc);
     if (pc->d_flush) cudaFree(pc->d_flush);
+    for (void *q : pc->ipc_opened) cudaIpcCloseMemHandle(q);
+    pc->p2p = false;
+    dev_free(pc->d_xl); dev_free(pc->d_yl); dev_free(pc->d_flags); dev_free(pc->d_timeout); dev_free(pc->d_ps);
+    dev_free(pc->d_ghostPeer); dev_free(pc->d_ghostRemote); dev_free(pc->d_sendPeer); dev_free(pc->d_remoteLeaf);
     if (pc->s_in) { cudaStreamDestroy(pc->s_in); cudaStreamDestroy(pc->s_out); }
     for (auto &ev : pc->ev_in) cudaEventDestroy(ev);
     for (auto &ev : pc->ev_k) cudaEventDestroy(ev);
@@ -611,9 +626,9 @@ static int build_device_lists(PC *pc)
         CHK(upload_i32(pc, pc->recvLeaf, &pc->d_recvLeaf));
         CHK(dev_alloc(&pc->d_sendbuf, (i64)std::max(pc->sendRoot.size(), pc->recvLeaf.size())));
         CHK(dev_alloc(&pc->d_recvbuf, (i64)std::max(pc->sendRoot.size(), pc->recvLeaf.size())));
-        CHK(dev_alloc(&pc->d_xl, pc->nlocal));
-        CHK(dev_alloc(&pc->d_yl, pc->nlocal));
-        if (!pc->neigh.empty() && !pc->comm) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "the star forest names neighbour ranks but SSCPatchCommInit() has not been called");
+        if (!pc->d_xl) CHK(dev_alloc(&pc->d_xl, pc->nlocal));
+        if (!pc->d_yl) CHK(dev_alloc(&pc->d_yl, pc->nlocal));
+        if (!pc->neigh.empty() && !pc->comm && !pc->p2p) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "the star forest names neighbour ranks but SSCPatchCommInit() has not been called");
     } else if (pc->nowned != pc->nlocal) {
         return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "nowned (%lld) != nlocal (%lld) but no star forest was set", (long long)pc->nowned, (long long)pc->nlocal);
     }
@@ -657,6 +672,118 @@ static int sf_reduce(PC *pc, const double *yl, double *y)
     }
     NCCL_OK(g_nccl.GroupEnd());
     if (ns) { ssc_scatter_kernel<<<grid_for(ns, 256), 256, 0, pc->stream>>>(ns, pc->d_sendRoot, pc->d_sendbuf, y, 1); pc->launches++; }
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// NVLink peer exchange: the neighbours' local vectors are mapped with CUDA IPC; the halo fill becomes direct stores,
+// the overlap sum becomes fp64 reductions issued by the patch kernel itself, and two neighbour barriers per apply
+// replace the NCCL send/recv pairs.
+// ---------------------------------------------------------------------------------------------
+static int peer_barrier(PC *pc)
+{
+    if (pc->neigh.empty()) return 0;
+    pc->epoch++;
+    ssc_peer_barrier_kernel<<<1, 32, 0, pc->stream>>>((int)pc->neigh.size(), pc->h_flags, pc->d_flags, pc->epoch, pc->d_timeout);
+    pc->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+static int peer_check(PC *pc)
+{
+    if (!pc->p2p) return 0;
+    int t = 0;
+    CUDA_OK(cudaMemcpy(&t, pc->d_timeout, sizeof(int), cudaMemcpyDeviceToHost));
+    if (t) return ssc_set_error(SSC_ERR_LIB, "a neighbour rank did not reach the peer barrier within the time limit");
+    return 0;
+}
+__global__ void ssc_peer_pushadd_kernel(ll nghost, int nowned, const double *__restrict__ yl, PeerScatter ps)
+{
+    for (ll s = (ll)blockIdx.x * blockDim.x + threadIdx.x; s < nghost; s += (ll)gridDim.x * blockDim.x)
+        atomicAdd(ps.yl[ps.ghostPeer[s]] + ps.ghostRemote[s], yl[nowned + s]);
+}
+
+extern "C" int SSCPatchPeerExport(SSCPatchPC pc, char *handles)
+{
+    CHK(set_device(pc));
+    if (!pc->sf_set) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "set the star forest before exporting peer handles");
+    if (!pc->d_xl) CHK(dev_alloc(&pc->d_xl, pc->nlocal));
+    if (!pc->d_yl) CHK(dev_alloc(&pc->d_yl, pc->nlocal));
+    if (!pc->d_flags) { CHK(dev_alloc(&pc->d_flags, 16)); CUDA_OK(cudaMemset(pc->d_flags, 0, 16 * sizeof(unsigned long long))); }
+    if (!pc->d_timeout) { CHK(dev_alloc(&pc->d_timeout, 1)); CUDA_OK(cudaMemset(pc->d_timeout, 0, sizeof(int))); }
+    cudaIpcMemHandle_t h[3];
+    CUDA_OK(cudaIpcGetMemHandle(&h[0], pc->d_xl));
+    CUDA_OK(cudaIpcGetMemHandle(&h[1], pc->d_yl));
+    CUDA_OK(cudaIpcGetMemHandle(&h[2], pc->d_flags));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handles, h, 192);
+    return 0;
+}
+
+extern "C" int SSCPatchPeerConnect(SSCPatchPC pc, const char *neighHandles, const int *slotAtNeigh, const SSCInt *remoteLeaf, const SSCInt *remoteRoot)
+{
+    CHK(set_device(pc));
+    const size_t nn = pc->neigh.size();
+    if (nn > 16) return ssc_set_error(SSC_ERR_SUP, "at most 16 neighbour ranks are supported by the peer exchange");
+    if (!pc->d_flags) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "call SSCPatchPeerExport first");
+    for (size_t i = 0; i < pc->selfLeaf.size(); ++i)
+        if (pc->selfLeaf[i] != (i64)i || pc->selfRoot[i] != (i64)i) return ssc_set_error(SSC_ERR_SUP, "the peer exchange needs owned dofs numbered first and identically in the local and owned vectors");
+    if ((i64)pc->selfLeaf.size() != pc->nowned) return ssc_set_error(SSC_ERR_SUP, "the peer exchange needs every owned dof in the local vector");
+    const i64 nghost = pc->nlocal - pc->nowned;
+    std::vector<int> ghostPeer((size_t)std::max<i64>(nghost, 1), -1), ghostRemote((size_t)std::max<i64>(nghost, 1), 0);
+    std::vector<int> sendPeer(std::max<size_t>(pc->sendRoot.size(), 1), 0), rleaf(std::max<size_t>(pc->sendRoot.size(), 1), 0);
+    for (size_t k = 0; k < nn; ++k) {
+        cudaIpcMemHandle_t h[3];
+        memcpy(h, neighHandles + 192 * k, 192);
+        void *p[3] = {nullptr, nullptr, nullptr};
+        for (int j = 0; j < 3; ++j) {
+            cudaError_t err = cudaIpcOpenMemHandle(&p[j], h[j], cudaIpcMemLazyEnablePeerAccess);
+            if (err != cudaSuccess) { cudaGetLastError(); return ssc_set_error(SSC_ERR_GPU, "cudaIpcOpenMemHandle failed for neighbour rank %d: %s", pc->neigh[k], cudaGetErrorString(err)); }
+            pc->ipc_opened.push_back(p[j]);
+        }
+        pc->h_push.xl[k] = (double *)p[0];
+        pc->h_ps.yl[k] = (double *)p[1];
+        pc->h_flags.flags[k] = (unsigned long long *)p[2];
+        pc->h_flags.slot[k] = slotAtNeigh[k];
+        for (i64 i = pc->recvOff[k]; i < pc->recvOff[k + 1]; ++i) {
+            const i64 s = pc->recvLeaf[i] - pc->nowned;
+            if (s < 0 || s >= nghost) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "receive slot is not a ghost slot");
+            ghostPeer[(size_t)s] = (int)k; ghostRemote[(size_t)s] = (int)remoteRoot[i];
+        }
+        for (i64 i = pc->sendOff[k]; i < pc->sendOff[k + 1]; ++i) { sendPeer[(size_t)i] = (int)k; rleaf[(size_t)i] = (int)remoteLeaf[i]; }
+    }
+    for (i64 s = 0; s < nghost; ++s) if (ghostPeer[(size_t)s] < 0) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "ghost slot %lld has no owner among the neighbours", (long long)s);
+    auto up = [&](const std::vector<int> &v, int **d) -> int {
+        CHK(dev_alloc(d, (i64)v.size()));
+        CUDA_OK(cudaMemcpy(*d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    CHK(up(ghostPeer, &pc->d_ghostPeer)); CHK(up(ghostRemote, &pc->d_ghostRemote));
+    CHK(up(sendPeer, &pc->d_sendPeer)); CHK(up(rleaf, &pc->d_remoteLeaf));
+    pc->h_ps.ghostPeer = pc->d_ghostPeer; pc->h_ps.ghostRemote = pc->d_ghostRemote; pc->h_ps.nowned = (int)pc->nowned;
+    CHK(dev_alloc(&pc->d_ps, 1));
+    CUDA_OK(cudaMemcpy(pc->d_ps, &pc->h_ps, sizeof(PeerScatter), cudaMemcpyHostToDevice));
+    pc->p2p = true;
+    return 0;
+}
+
+// halo fill through peer stores + barrier
+static int peer_bcast(PC *pc, const double *x, double *xl)
+{
+    CUDA_OK(cudaMemcpyAsync(xl, x, (size_t)pc->nowned * sizeof(double), cudaMemcpyDeviceToDevice, pc->stream));
+    const i64 ns = (i64)pc->sendRoot.size();
+    if (ns) { ssc_peer_push_kernel<<<grid_for(ns, 256), 256, 0, pc->stream>>>(ns, pc->d_sendRoot, pc->d_sendPeer, pc->d_remoteLeaf, x, pc->h_push); pc->launches++; }
+    return peer_barrier(pc);
+}
+// overlap sum for a local vector that was filled WITHOUT the fused scatter (set-up time only: dof multiplicities)
+static int peer_reduce(PC *pc, double *yl, double *y)
+{
+    CHK(peer_barrier(pc));
+    const i64 ng = pc->nlocal - pc->nowned;
+    if (ng) { ssc_peer_pushadd_kernel<<<grid_for(ng, 256), 256, 0, pc->stream>>>(ng, (int)pc->nowned, yl, pc->h_ps); pc->launches++; }
+    CHK(peer_barrier(pc));
+    CUDA_OK(cudaMemcpyAsync(y, yl, (size_t)pc->nowned * sizeof(double), cudaMemcpyDeviceToDevice, pc->stream));
     return 0;
 }
 
@@ -756,7 +883,8 @@ static int compute_weights(PC *pc)
     double *ml = pc->sf_set ? pc->d_yl : pc->d_w;
     CUDA_OK(cudaMemsetAsync(ml, 0, (size_t)pc->nlocal * sizeof(double), pc->stream));
     if (pc->sum_n) { ssc_count_kernel<<<grid_for(pc->sum_n, 256), 256, 0, pc->stream>>>(pc->d_gtol, pc->sum_n, ml); pc->launches++; }
-    if (pc->sf_set) CHK(sf_reduce(pc, ml, pc->d_w));
+    if (pc->sf_set && pc->p2p) CHK(peer_reduce(pc, ml, pc->d_w));
+    else if (pc->sf_set) CHK(sf_reduce(pc, ml, pc->d_w));
     ssc_reciprocal_kernel<<<grid_for(pc->nowned, 256), 256, 0, pc->stream>>>(pc->nowned, pc->d_w);
     pc->launches++;
     CUDA_OK(cudaGetLastError());
@@ -811,7 +939,7 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
 #define LAUNCH_APPLY(K)                                                                                                  \
     do {                                                                                                                 \
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        K<<<(unsigned)grid, threads, smem, pc->stream>>>(blocks, c.stride, c.ld, gt, c.n, cnt, c.tp, c.ppb, xl, yl, scale, mult); \
+        K<<<(unsigned)grid, threads, smem, pc->stream>>>(blocks, c.stride, c.ld, gt, c.n, cnt, c.tp, c.ppb, xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr); \
     } while (0)
     if (pc->apply_variant == 2 && threads <= 256) LAUNCH_APPLY((ssc_apply_pipe_kernel<2, 8>));
     else if (pc->apply_variant == 1 && threads <= 256) LAUNCH_APPLY((ssc_apply_pipe_kernel<1, 8>));
@@ -828,11 +956,17 @@ static int apply_device(PC *pc, const double *x, double *y)
     const bool identity = !pc->sf_set;
     const double *xl = x;
     double *yl = y;
-    if (!identity) {                                        // ssc/libssc.c:1321-1326
-        CHK(sf_bcast(pc, x, pc->d_xl));
+    if (!identity && pc->p2p) {
         xl = pc->d_xl; yl = pc->d_yl;
+        CUDA_OK(cudaMemsetAsync(yl, 0, (size_t)pc->nlocal * sizeof(double), pc->stream));   // before the barrier inside peer_bcast:
+        CHK(peer_bcast(pc, x, pc->d_xl));                                                   // neighbours add into yl after it
+    } else {
+        if (!identity) {                                    // ssc/libssc.c:1321-1326
+            CHK(sf_bcast(pc, x, pc->d_xl));
+            xl = pc->d_xl; yl = pc->d_yl;
+        }
+        CUDA_OK(cudaMemsetAsync(yl, 0, (size_t)pc->nlocal * sizeof(double), pc->stream));   // :1334
     }
-    CUDA_OK(cudaMemsetAsync(yl, 0, (size_t)pc->nlocal * sizeof(double), pc->stream));   // :1334
     const double scale = pc->symmetrise_sweep ? 2.0 : 1.0;   // the second sweep re-adds the same corrections, :1336-1343
     cudaEvent_t k0 = nullptr, k1 = nullptr;
     if (pc->ktimer) {
@@ -862,7 +996,10 @@ static int apply_device(PC *pc, const double *x, double *y)
         }
     }
     if (pc->ktimer) CUDA_OK(cudaEventRecord(k1, pc->stream));
-    if (!identity) CHK(sf_reduce(pc, yl, y));                // :1396-1401
+    if (!identity && pc->p2p) {                             // ghost contributions already sit in their owners' vectors
+        CHK(peer_barrier(pc));
+        CUDA_OK(cudaMemcpyAsync(y, yl, (size_t)pc->nowned * sizeof(double), cudaMemcpyDeviceToDevice, pc->stream));
+    } else if (!identity) CHK(sf_reduce(pc, yl, y));         // :1396-1401
     if (pc->nbc) { ssc_bc_kernel<<<grid_for(pc->nbc, 256), 256, 0, pc->stream>>>(pc->d_bc, pc->nbc, x, y); pc->launches++; }   // :1404-1413
     if (pc->partition_of_unity) {                            // :1418-1421
         if (!pc->d_w) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "partition of unity was switched on after the first setup");
@@ -985,7 +1122,7 @@ extern "C" int SSCPatchSynchronize(SSCPatchPC pc)
 {
     CHK(set_device(pc));
     CUDA_OK(cudaStreamSynchronize(pc->stream));
-    return 0;
+    return peer_check(pc);
 }
 
 extern "C" int SSCPatchView(SSCPatchPC pc, char *buf, SSCInt len)

@@ -15,6 +15,25 @@ typedef long long ll;
 
 __device__ __forceinline__ unsigned hash_dof(int key) { return (unsigned)key * 2654435761u; }
 
+// Peer-memory scatter (multi-GPU, NVLink P2P): a patch dof >= nowned is a ghost whose owner lives on another GPU of
+// the box; its correction is added straight into the owner's local vector through a mapped peer pointer, so the
+// overlap sum of ssc/libssc.c:1399-1400 travels over NVLink while the patch kernel is still streaming blocks.
+struct PeerScatter {
+    double *yl[16];          // local y vector of every neighbour (cudaIpcOpenMemHandle)
+    const int *ghostPeer;    // ghost slot -> neighbour number
+    const int *ghostRemote;  // ghost slot -> index in that neighbour's vector
+    int nowned;
+};
+__device__ __forceinline__ void scatter_add(double *__restrict__ y, int gi, double v, const PeerScatter *__restrict__ ps)
+{
+    if (ps != nullptr && gi >= ps->nowned) {
+        const int s = gi - ps->nowned;
+        atomicAdd(ps->yl[ps->ghostPeer[s]] + ps->ghostRemote[s], v);
+    } else {
+        atomicAdd(y + gi, v);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1 extract: B_p[i][j] = A[gtol_p[i], gtol_p[j]]   (replaces MatZeroEntries + callback assembly,
 // ssc/libssc.c:1286-1291, :1120-1156).  One CTA per patch; a shared-memory hash maps global column -> patch
@@ -343,7 +362,8 @@ ssc_invert_reg_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 ssc_apply_kernel(const double *__restrict__ S, ll stride, int ld, const int *__restrict__ gtol, int n, ll count, int tp, int ppb,
-                 const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult)
+                 const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
+                 const PeerScatter *__restrict__ ps)
 {
     extern __shared__ __align__(16) double xs_all[];
     const int lp = threadIdx.x / tp, t = threadIdx.x - lp * tp;
@@ -369,7 +389,7 @@ ssc_apply_kernel(const double *__restrict__ S, ll stride, int ld, const int *__r
             a0 = fma(m4, xs[j + 4], a0); a1 = fma(m5, xs[j + 5], a1); a2 = fma(m6, xs[j + 6], a2); a3 = fma(m7, xs[j + 7], a3);
         }
         for (; j < n; ++j) a0 = fma(__ldcs(M + (ll)j * ld), xs[j], a0);
-        atomicAdd(y + g[i], ((a0 + a1) + (a2 + a3)) * sc);
+        scatter_add(y, g[i], ((a0 + a1) + (a2 + a3)) * sc, ps);
     }
 }
 
@@ -386,7 +406,8 @@ __device__ __forceinline__ void fma_vec(double2 m, double xv, double &a0, double
 template <int kVec, int kU>
 __global__ void __launch_bounds__(256)
 ssc_apply_pipe_kernel(const double *__restrict__ S, ll stride, int ld, const int *__restrict__ gtol, int n, ll count, int tp, int ppb,
-                      const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult)
+                      const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
+                      const PeerScatter *__restrict__ ps)
 {
     typedef typename VecT<kVec>::T T;
     extern __shared__ __align__(16) double xs_all[];
@@ -434,8 +455,8 @@ ssc_apply_pipe_kernel(const double *__restrict__ S, ll stride, int ld, const int
             }
         }
         for (int j = ngroups * kU; j < n; ++j) fma_vec(__ldcs(M + (ll)j * ldv), xs[j], a0, a1);
-        atomicAdd(y + g[i], (a0 + b0) * sc);
-        if (kVec == 2 && i + 1 < n) atomicAdd(y + g[i + 1], (a1 + b1) * sc);
+        scatter_add(y, g[i], (a0 + b0) * sc, ps);
+        if (kVec == 2 && i + 1 < n) scatter_add(y, g[i + 1], (a1 + b1) * sc, ps);
     }
 }
 
@@ -498,4 +519,33 @@ __global__ void ssc_spmv_kernel(ll nrows, const ll *__restrict__ rowptr, const i
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if (lane == 0) y[warp] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NVLink peer exchange (one process per GPU, buffers mapped with CUDA IPC)
+// ---------------------------------------------------------------------------------------------
+struct PeerPush { double *xl[16]; };
+// halo fill (SFBcast, ssc/libssc.c:1323-1324) as direct stores into the neighbours' ghost slots
+__global__ void ssc_peer_push_kernel(ll n, const int *__restrict__ sendRoot, const int *__restrict__ sendPeer, const int *__restrict__ remoteLeaf,
+                                     const double *__restrict__ x, PeerPush peers)
+{
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x)
+        peers.xl[sendPeer[i]][remoteLeaf[i]] = x[sendRoot[i]];
+}
+struct PeerFlags { unsigned long long *flags[16]; int slot[16]; };
+// Neighbour barrier: thread k tells neighbour k "everything this rank enqueued before epoch e is done" and waits for
+// the same word from it.  Each rank runs on its own GPU; a bounded spin turns a lost peer into an error flag, not a hang.
+__global__ void ssc_peer_barrier_kernel(int nneigh, PeerFlags peers, volatile unsigned long long *mine, unsigned long long epoch, int *timeout)
+{
+    const int k = threadIdx.x;
+    if (k >= nneigh) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flags[k] + peers.slot[k]), "l"(epoch) : "memory");
+    const long long t0 = clock64();
+    unsigned long long v;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + k) : "memory");
+        if (clock64() - t0 > 8000000000LL) { *timeout = 1; break; }      // ~4 s
+    } while (v < epoch);
+    __threadfence_system();
 }

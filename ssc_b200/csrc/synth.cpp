@@ -83,3 +83,12 @@ extern "C" int ssc_synth_tensor_fill(int d, const i64 *N, int p, const double *c
     }
     return 0;
 }
+
+extern "C" void ssc_synth_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

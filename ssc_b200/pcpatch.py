@@ -140,6 +140,9 @@ class PC(object):
                                    ip(arrs[2]), ip(arrs[3]), ghost.ctypes.data_as(C.c_void_p)))
         self.plex = plex
 
+    def getDM(self):
+        return self.plex
+
     def setAttr(self, k, v):
         self.attrs[k] = v
 
@@ -221,6 +224,16 @@ class PC(object):
         ng = np.ascontiguousarray(neigh, dtype=np.int32)
         CHKERR(lib.SSCPatchSetStarForest(self.handle, C.c_int64(nowned), C.c_int64(a[0].size), ip(a[0]), ip(a[1]), C.c_int64(ng.size),
                                          ng.ctypes.data_as(_lib.i32p), ip(a[2]), ip(a[3]), ip(a[4]), ip(a[5])))
+
+    def peerExport(self):
+        buf = C.create_string_buffer(192)
+        CHKERR(lib.SSCPatchPeerExport(self.handle, buf))
+        return buf.raw
+
+    def peerConnect(self, neigh_handles, slot_at_neigh, remote_leaf, remote_root):
+        slots = np.ascontiguousarray(slot_at_neigh, dtype=np.int32)
+        rl, rr = as_i64(remote_leaf), as_i64(remote_root)
+        CHKERR(lib.SSCPatchPeerConnect(self.handle, b"".join(neigh_handles), slots.ctypes.data_as(_lib.i32p), ip(rl), ip(rr)))
 
     def commInit(self, nranks, rank, unique_id):
         CHKERR(lib.SSCPatchCommInit(self.handle, int(nranks), int(rank), unique_id))

@@ -21,6 +21,10 @@ def _load():
     return _lib
 
 
+def set_threads(n):
+    _load().ssc_synth_set_threads(C.c_int(int(n)))
+
+
 def tensor_poisson_csr(V, bc_nodes=None):
     """(indptr int64, indices int32, data float64) of the Q_p stiffness matrix on the tensor space V, in V's node
     numbering, with the rows and columns of ``bc_nodes`` replaced by the identity."""

@@ -21,6 +21,7 @@ def main():
     c = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     p = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     pou = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    p2p = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     rank, nranks, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     dist.init_process_group("gloo", rank=rank, world_size=nranks)
 
@@ -35,16 +36,21 @@ def main():
     pc.setOperatorCSR(*synth.tensor_poisson_csr(slab.space, slab.discretisation.ghost_bc_nodes))
     if pou:
         pc.setOption("pc_patch_partition_of_unity", True)
-    uid = [get_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    pc.commInit(nranks, rank, uid[0])
-    pc.setStarForest(slab.nowned, *partition.star_forest(slab.global_ids, slab.nowned, rank, nranks, allgather))
+    sf = partition.star_forest(slab.global_ids, slab.nowned, rank, nranks, allgather)
+    pc.setStarForest(slab.nowned, *sf)
+    if p2p:
+        partition.connect_peers(pc, sf, rank, allgather)
+    else:
+        uid = [get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        pc.commInit(nranks, rank, uid[0])
     pc.setUp()
     xlat = np.random.default_rng(11).uniform(-1, 1, int(np.prod(slab.global_shape)))
     x = np.ascontiguousarray(xlat[slab.global_ids[:slab.nowned]])
     y = np.zeros_like(x)
-    for _ in range(2):
+    for _ in range(3):
         pc.apply(x, y)
+    pc.synchronize()
     parts = allgather((slab.global_ids[:slab.nowned], y))
     ok = True
     if rank == 0:
@@ -63,7 +69,7 @@ def main():
             ygpu[gid] = yy
         err = np.linalg.norm(ygpu - yref) / np.linalg.norm(yref)
         ok = bool(err < 1e-12)
-        print("mgpu_check ranks=%d cells=%d^2x%d p=%d pou=%d relerr=%.3e %s" % (nranks, c, c * nranks, p, pou, err, "OK" if ok else "FAIL"))
+        print("mgpu_check ranks=%d cells=%d^2x%d p=%d pou=%d exchange=%s relerr=%.3e %s" % (nranks, c, c * nranks, p, pou, "p2p" if p2p else "nccl", err, "OK" if ok else "FAIL"))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
