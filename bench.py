@@ -216,6 +216,7 @@ def main():
 
     pc = PC(device=local_rank)
     exchange = None
+    pc.setOption("ssc_builder_threads", max(1, min(32, (os.cpu_count() or 1) // nranks)))
     setup_patch_pc(pc, disc, None)
     pc._compute_op = None
     pc.setOperatorCSR(*csr)
@@ -248,6 +249,9 @@ def main():
     pc.setUp()
     pc.synchronize()
     info["t_setup_wall"] = time.time() - t0
+    if nranks > 1:
+        pc._csr_keep = None          # the CSR was only borrowed until SetUp returned; N=1 keeps it for the CPU baseline
+        csr = None
     setup = {"create_patches_ms": pc.eventTime("PCPATCHCreate"), "extract_ms": pc.eventTime("PCPATCHComputeOp"),
              "factor_ms": pc.eventTime("PCPATCHSolve"), "setup_wall_s": info["t_setup_wall"],
              "assemble_wall_s": info["t_assemble"], "mesh_wall_s": info["t_mesh"]}
