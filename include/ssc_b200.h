@@ -47,7 +47,8 @@ int SSCPatchDestroy(SSCPatchPC *pc);                      /* PCDestroy_PATCH  ss
 /* ---- options: PCSetFromOptions_PATCH ssc/libssc.c:1551-1620 ------------------------------- */
 /* name is the option without the prefix and leading dash, e.g. "pc_patch_save_operators", "sub_pc_type";
  * value is its string form ("true", "1", "lu", ...).  Unknown names and unsupported values return an error
- * (no silent fallback); "pc_patch_multiplicative true" errors exactly as ssc/libssc.c:1570-1572 does. */
+ * (no silent fallback).  "pc_patch_multiplicative true": the reference raises an error (mode removed, ssc/libssc.c:1570-1572);
+ * this build runs a coloured multiplicative sweep instead (BASELINE.json north_star). */
 int SSCPatchSetOption(SSCPatchPC pc, const char *name, const char *value);
 int SSCPatchSetSaveOperators(SSCPatchPC pc, int flg);     /* PCPatchSetSaveOperators     ssc/libssc.c:84-91   */
 int SSCPatchSetPartitionOfUnity(SSCPatchPC pc, int flg);  /* PCPatchSetPartitionOfUnity  ssc/libssc.c:93-100  */
@@ -135,6 +136,8 @@ int SSCPatchGetCells(SSCPatchPC pc, SSCInt *cellOffsets, SSCInt *cells);
 int SSCPatchGetDofs(SSCPatchPC pc, SSCInt *dofs);         /* only if option "ssc_keep_dofs_table" is on */
 /* dense operator (which = 0) or stored inverse (which = 1) of patch p, row-major n x n, copied to host */
 int SSCPatchGetPatchMatrix(SSCPatchPC pc, SSCInt p, int which, double *out);
+/* colour of every patch (-1 for empty ones) after SetUp with -pc_patch_multiplicative (N4: no reference counterpart) */
+int SSCPatchGetColours(SSCPatchPC pc, SSCInt *colours);
 /* dof weights of ssc/libssc.c:1254-1284 (nowned values, host) */
 int SSCPatchGetDofWeights(SSCPatchPC pc, double *w);
 /* device time in ms of the last completed stage, named as the reference's log events (ssc/libssc.c:19-24):

@@ -208,5 +208,16 @@ class OraclePatchPC(object):
         return y
 
 
+def _mult(self, x, order):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros_like(x)
+    order = _i64(order)
+    self._chk(self.L.oracle_apply_multiplicative(self.h, C.c_int64(x.size), _dp(x), _dp(y), C.c_int64(order.size), _ip(order)))
+    return y
+
+
+OraclePatchPC.applyMultiplicative = _mult
+
+
 def max_threads():
     return lib().oracle_max_threads()

@@ -632,3 +632,27 @@ int oracle_max_threads(void) {
     return 1;
 #endif
 }
+
+/* Sequential multiplicative Schwarz over the patches in the given order (N4; the reference has no such code path any
+ * more, ssc/libssc.c:1568-1572, so this defines the semantics the GPU's coloured sweep is checked against):
+ *   y = 0;  for p in order:  r_p = (x - A y)[gtol_p];  y[gtol_p] += B_p^{-1} r_p;   then Dirichlet pass-through. */
+int oracle_apply_multiplicative(OraclePC *pc, i64 n, const double *x, double *y, i64 norder, const i64 *order) {
+    if (!pc->lu) { snprintf(pc->err, 256, "operators not set up"); return 73; }
+    i64 maxn = 0; for (i64 i = 0; i < pc->npatch; i++) if (pc->gtolDof[i] > maxn) maxn = pc->gtolDof[i];
+    double *px = malloc((maxn + 1) * sizeof(double)), *py = malloc((maxn + 1) * sizeof(double));
+    memset(y, 0, n * sizeof(double));
+    for (i64 o = 0; o < norder; o++) {
+        i64 i = order[o], len = pc->gtolDof[i]; const i64 *g = pc->gtol + pc->gtolOff[i];
+        if (len <= 0) continue;
+        for (i64 l = 0; l < len; l++) {
+            double s = 0.0;
+            for (i64 k = pc->rowptr[g[l]]; k < pc->rowptr[g[l] + 1]; k++) s += pc->vals[k] * y[pc->colidx ? pc->colidx[k] : (i64)pc->colidx32[k]];
+            px[l] = x[g[l]] - s;
+        }
+        lu_solve(pc->lu[i], pc->piv[i], len, px, py);
+        for (i64 l = 0; l < len; l++) y[g[l]] += py[l];
+    }
+    for (i64 i = 0; i < pc->numGlobalBcs; i++) { i64 idx = pc->globalBcNodes[i]; if (idx < n) y[idx] = x[idx]; }
+    free(px); free(py);
+    return 0;
+}

@@ -59,6 +59,7 @@ _sigs = {
     "SSCPatchGetDofs": [_H, i64p],
     "SSCPatchGetPatchMatrix": [_H, C.c_int64, C.c_int, f64p],
     "SSCPatchGetDofWeights": [_H, f64p],
+    "SSCPatchGetColours": [_H, i64p],
     "SSCPatchGetEventTime": [_H, C.c_char_p, f64p],
     "SSCPatchKernelTimerReset": [_H, C.c_int],
     "SSCPatchKernelTimerRead": [_H, f64p, i64p],

@@ -144,6 +144,10 @@ struct SSCPatchPC_s {
     bool device_ready = false, setup_done = false;
     std::vector<SizeClass> classes;
     std::vector<i64> sorted2orig, orig2sorted;
+    std::vector<i64> colour;                                        // per original patch (multiplicative mode)
+    i64 ncolours = 0;
+    std::vector<std::vector<std::pair<i64, i64>>> colour_ranges;    // [colour][class] -> sorted positions
+    double *d_r = nullptr;
     int *d_gtol = nullptr;
     double *d_blocks = nullptr, *d_blocks0 = nullptr;
     i64 block_elems = 0, sum_n = 0, sum_n2 = 0, max_n = 0;
@@ -253,7 +257,7 @@ extern "C" int SSCPatchCreate(int device, SSCPatchPC *out)
 static void free_device_state(PC *pc)
 {
     if (pc->device < 0) return;
-    dev_free(pc->d_gtol); dev_free(pc->d_blocks); dev_free(pc->d_blocks0); dev_free(pc->d_fail); dev_free(pc->d_bc);
+    dev_free(pc->d_r); dev_free(pc->d_gtol); dev_free(pc->d_blocks); dev_free(pc->d_blocks0); dev_free(pc->d_fail); dev_free(pc->d_bc);
     dev_free(pc->d_w); dev_free(pc->d_mult); dev_free(pc->d_xs); dev_free(pc->d_ys);
     if (!pc->p2p) { dev_free(pc->d_xl); dev_free(pc->d_yl); }
     dev_free(pc->d_selfLeaf); dev_free(pc->d_selfRoot); dev_free(pc->d_sendRoot); dev_free(pc->d_recvLeaf);
@@ -335,11 +339,12 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "pc_patch_save_operators") return parse_bool(v, &pc->save_operators);
     if (name == "pc_patch_partition_of_unity") return parse_bool(v, &pc->partition_of_unity);
     if (name == "pc_patch_multiplicative") {
-        CHK(parse_bool(v, &pc->multiplicative));
-        if (pc->multiplicative) {   // ssc/libssc.c:1570-1572
-            pc->multiplicative = false;
-            return ssc_set_error(SSC_ERR_USER, "We've removed multiplicative to do BC condensation (for now)");
-        }
+        // The reference removed this mode ("We've removed multiplicative to do BC condensation (for now)",
+        // ssc/libssc.c:1568-1572).  north_star asks for it colour by colour; see DESIGN.md section 8 (N4).
+        bool flg = false;
+        CHK(parse_bool(v, &flg));
+        if (flg != pc->multiplicative && pc->device_ready) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "pc_patch_multiplicative must be chosen before the first SetUp");
+        pc->multiplicative = flg;
         return 0;
     }
     if (name == "pc_patch_construction_dim") {
@@ -570,6 +575,39 @@ static int build_device_lists(PC *pc)
     std::vector<i64> order;
     order.reserve(np);
     for (i64 p = 0; p < np; ++p) if (L.gtolOff[p + 1] - L.gtolOff[p] > 0) order.push_back(p);   // ssc/libssc.c:1355-1358
+    if (pc->multiplicative) {
+        // Greedy colouring of the patch conflict graph: two patches conflict when they share a cell, i.e. when the
+        // operator can couple their dofs.  Patches of one colour then commute and are applied together.
+        if (pc->direct_patches || L.cells.empty()) return ssc_set_error(SSC_ERR_SUP, "multiplicative sweeps need patches built from the mesh topology (cells per patch)");
+        if (pc->sf_set) return ssc_set_error(SSC_ERR_SUP, "multiplicative sweeps across ranks are not supported in this build");
+        if (pc->partition_of_unity) return ssc_set_error(SSC_ERR_ARG_INCOMP, "partition of unity weighting applies to the additive method only");
+        i64 maxcell = -1;
+        for (i64 c : L.cells) maxcell = std::max(maxcell, c);
+        std::vector<i64> coff((size_t)maxcell + 2, 0);
+        for (i64 c : L.cells) coff[(size_t)c + 1]++;
+        for (size_t c = 0; c + 1 < coff.size(); ++c) coff[c + 1] += coff[c];
+        std::vector<i64> cpatch((size_t)L.cells.size()), fill(coff.begin(), coff.end() - 1);
+        for (i64 p = 0; p < np; ++p) for (i64 k = L.cellOff[p]; k < L.cellOff[p + 1]; ++k) cpatch[(size_t)fill[(size_t)L.cells[k]]++] = p;
+        pc->colour.assign((size_t)np, -1);
+        std::vector<i64> mark;
+        pc->ncolours = 0;
+        for (i64 p = 0; p < np; ++p) {
+            if (L.gtolOff[p + 1] == L.gtolOff[p]) continue;
+            mark.assign((size_t)pc->ncolours + 1, 0);
+            for (i64 k = L.cellOff[p]; k < L.cellOff[p + 1]; ++k) {
+                const i64 c = L.cells[k];
+                for (i64 m = coff[(size_t)c]; m < coff[(size_t)c + 1]; ++m) { const i64 q = cpatch[(size_t)m]; if (q != p && pc->colour[(size_t)q] >= 0) mark[(size_t)pc->colour[(size_t)q]] = 1; }
+            }
+            i64 col = 0;
+            while (col < pc->ncolours && mark[(size_t)col]) ++col;
+            pc->colour[(size_t)p] = col;
+            pc->ncolours = std::max(pc->ncolours, col + 1);
+        }
+        std::stable_sort(order.begin(), order.end(), [&](i64 a, i64 b) {
+            const i64 na = L.gtolOff[a + 1] - L.gtolOff[a], nb = L.gtolOff[b + 1] - L.gtolOff[b];
+            return na != nb ? na < nb : pc->colour[(size_t)a] < pc->colour[(size_t)b];
+        });
+    } else
     std::stable_sort(order.begin(), order.end(), [&](i64 a, i64 b) { return L.gtolOff[a + 1] - L.gtolOff[a] < L.gtolOff[b + 1] - L.gtolOff[b]; });
     pc->sorted2orig = order;
     pc->orig2sorted.assign(np, -1);
@@ -593,6 +631,21 @@ static int build_device_lists(PC *pc)
         pc->sum_n += n; pc->sum_n2 += n * n; pc->max_n = std::max(pc->max_n, n);
     }
     pc->block_elems = moff;
+    if (pc->multiplicative) {
+        pc->colour_ranges.assign((size_t)pc->ncolours, std::vector<std::pair<i64, i64>>(pc->classes.size(), {0, 0}));
+        for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
+            const SizeClass &c = pc->classes[ci];
+            i64 q = c.first;
+            while (q < c.first + c.count) {
+                const i64 col = pc->colour[(size_t)order[(size_t)q]];
+                i64 q1 = q;
+                while (q1 < c.first + c.count && pc->colour[(size_t)order[(size_t)q1]] == col) ++q1;
+                pc->colour_ranges[(size_t)col][ci] = {q, q1};
+                q = q1;
+            }
+        }
+        CHK(dev_alloc(&pc->d_r, pc->nlocal));
+    }
     if (pc->nlocal > 2147483647LL) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "local vector too long for 32-bit device indices");
     // dof lists in sorted order, int32
     std::vector<int> g32((size_t)pc->sum_n);
@@ -913,7 +966,7 @@ extern "C" int SSCPatchSetUp(SSCPatchPC pc)
         pc->failed = 0;
         i64 firstbad = -1;
         for (size_t q = 0; q < fail.size(); ++q) if (fail[q]) { if (firstbad < 0) firstbad = pc->sorted2orig[q]; pc->failed++; }
-        if (pc->csr_owned) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); pc->csr_owned = false; }
+        if (pc->csr_owned && !pc->multiplicative) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); pc->csr_owned = false; }
         if (pc->failed) return ssc_set_error(SSC_ERR_MAT_LU_ZRPVT, "%lld patch operators could not be factorised (first: patch %lld)%s", (long long)pc->failed,
                                              (long long)firstbad, pc->sub_pc == SSC_SUB_CHOLESKY ? "; sub_pc_type cholesky needs SPD blocks" : "");
     } else {
@@ -950,9 +1003,44 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
     return 0;
 }
 
+// Coloured multiplicative Schwarz (no reference code path: ssc/libssc.c:1568-1572 removed it).
+//   y = 0;  for each colour c:  r = x - A y;  y += sum_{p in c} R_p^T B_p^-1 R_p r
+// Patches of one colour share no cell, so their corrections commute and one launch per size class applies them all;
+// with symmetrise_sweep the colours are then visited in reverse order.
+static int apply_multiplicative(PC *pc, const double *x, double *y)
+{
+    if (!pc->save_operators) return ssc_set_error(SSC_ERR_SUP, "multiplicative sweeps need saved patch operators");
+    if (!pc->d_rowptr) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "the operator is not resident on the device");
+    CUDA_OK(cudaMemsetAsync(y, 0, (size_t)pc->nowned * sizeof(double), pc->stream));
+    const int nsweep = pc->symmetrise_sweep ? 2 : 1;
+    bool first = true;
+    for (int sweep = 0; sweep < nsweep; ++sweep) {
+        for (i64 cc = 0; cc < pc->ncolours; ++cc) {
+            const i64 col = sweep == 0 ? cc : pc->ncolours - 1 - cc;
+            const double *r = x;
+            if (!first) {
+                const int bd = 256;
+                ssc_residual_kernel<<<(unsigned)((pc->nlocal * 32 + bd - 1) / bd), bd, 0, pc->stream>>>(pc->nlocal, (const ll *)pc->d_rowptr, pc->d_colidx, pc->d_vals, x, y, pc->d_r);
+                pc->launches++;
+                r = pc->d_r;
+            }
+            first = false;
+            for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
+                const SizeClass &c = pc->classes[ci];
+                const i64 q0 = pc->colour_ranges[(size_t)col][ci].first, q1 = pc->colour_ranges[(size_t)col][ci].second;
+                if (q1 > q0) CHK(launch_apply_class(pc, c, q0, q1, pc->d_blocks + c.moff + (q0 - c.first) * c.stride, r, y, 1.0));
+            }
+        }
+    }
+    if (pc->nbc) { ssc_bc_kernel<<<grid_for(pc->nbc, 256), 256, 0, pc->stream>>>(pc->d_bc, pc->nbc, x, y); pc->launches++; }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 static int apply_device(PC *pc, const double *x, double *y)
 {
     if (!pc->setup_done) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "SSCPatchSetUp() has not been called");
+    if (pc->multiplicative) return apply_multiplicative(pc, x, y);
     const bool identity = !pc->sf_set;
     const double *xl = x;
     double *yl = y;
@@ -1018,7 +1106,7 @@ static int build_host_pipeline(PC *pc)
 {
     pc->pipe_ready = false;
     const int S = pc->pipe_slabs;
-    if (S < 2 || pc->sf_set || !pc->save_operators || (!pc->pipe_force && pc->sum_n2 * 8 < ((i64)64 << 20))) return 0;
+    if (S < 2 || pc->sf_set || pc->multiplicative || !pc->save_operators || (!pc->pipe_force && pc->sum_n2 * 8 < ((i64)64 << 20))) return 0;
     if (pc->lists.npatch < S) return 0;
     const PatchLists &L = pc->lists;
     const i64 np = L.npatch, N = pc->nowned;
@@ -1132,6 +1220,7 @@ extern "C" int SSCPatchView(SSCPatchPC pc, char *buf, SSCInt len)
     char line[256];
     snprintf(line, sizeof line, "  Subspace Correction preconditioner with %lld patches\n", (long long)pc->lists.npatch); s += line;
     s += pc->multiplicative ? "  Schwarz type: multiplicative\n" : "  Schwarz type: additive\n";
+    if (pc->multiplicative && pc->setup_done) { snprintf(line, sizeof line, "  %lld colours of mutually independent patches\n", (long long)pc->ncolours); s += line; }
     s += pc->partition_of_unity ? "  Weighting by partition of unity\n" : "  Not weighting by partition of unity\n";
     s += pc->symmetrise_sweep ? "  Symmetrising sweep (start->end, then end->start)\n" : "  Not symmetrising sweep\n";
     s += !pc->save_operators ? "  Not saving patch operators (rebuilt every PCApply)\n" : "  Saving patch operators (rebuilt every PCSetUp)\n";
@@ -1167,6 +1256,7 @@ extern "C" int SSCPatchGetSize(SSCPatchPC pc, const char *what, SSCInt *value)
     else if (w == "num_gtol") *value = (i64)pc->lists.gtol.size();
     else if (w == "num_dofs") *value = (i64)pc->lists.dofs.size();
     else if (w == "num_classes") *value = (i64)pc->classes.size();
+    else if (w == "num_colours") *value = pc->ncolours;
     else if (w == "block_bytes") *value = pc->block_elems * 8;
     else if (w == "bytes_apply") *value = 8 * pc->sum_n2 + (4 + 8 + 8) * pc->sum_n + 16 * pc->nowned;
     else if (w == "bytes_extract") { if (pc->csr_set && pc->csr_space == SSC_MEM_HOST) nnz = pc->csr_rowptr[pc->csr_nrows]; *value = 12 * nnz + 8 * (pc->nlocal + 1) + 4 * pc->sum_n + 8 * pc->sum_n2; }
@@ -1231,6 +1321,13 @@ extern "C" int SSCPatchGetPatchMatrix(SSCPatchPC pc, SSCInt p, int which, double
         }
     }
     return ssc_set_error(SSC_ERR_LIB, "patch %lld not found in any size class", (long long)p);
+}
+
+extern "C" int SSCPatchGetColours(SSCPatchPC pc, SSCInt *colours)
+{
+    if (!pc->multiplicative || pc->colour.empty()) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "colours exist after SetUp in multiplicative mode");
+    std::copy(pc->colour.begin(), pc->colour.end(), colours);
+    return 0;
 }
 
 extern "C" int SSCPatchGetDofWeights(SSCPatchPC pc, double *w)

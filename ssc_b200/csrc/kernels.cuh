@@ -549,3 +549,17 @@ __global__ void ssc_peer_barrier_kernel(int nneigh, PeerFlags peers, volatile un
     } while (v < epoch);
     __threadfence_system();
 }
+
+// r = x - A y, one warp per row (residual between the colours of a multiplicative sweep)
+__global__ void ssc_residual_kernel(ll nrows, const ll *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals,
+                                    const double *__restrict__ x, const double *__restrict__ y, double *__restrict__ r)
+{
+    const ll warp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= nrows) return;
+    double s = 0.0;
+    for (ll k = rowptr[warp] + lane; k < rowptr[warp + 1]; k += 32) s = fma(vals[k], y[colidx[k]], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) r[warp] = x[warp] - s;
+}

