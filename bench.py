@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--apply-variant", type=int, default=None, help="ssc_apply_variant (kernel selection; default = library default)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo exchange: NVLink peer memory (default) or NCCL send/recv")
+    ap.add_argument("--factor-panel", type=int, default=None)
+    ap.add_argument("--factor-ctas", type=int, default=None)
     ap.add_argument("--host-pipeline", type=int, default=None, help="ssc_host_pipeline (slabs of the overlapped host-space apply)")
     return ap.parse_args()
 
@@ -222,6 +224,10 @@ def main():
     pc.setOperatorCSR(*csr)
     if args.apply_variant is not None:
         pc.setOption("ssc_apply_variant", args.apply_variant)
+    if args.factor_ctas is not None:
+        pc.setOption("ssc_factor_ctas", args.factor_ctas)
+    if args.factor_panel is not None:
+        pc.setOption("ssc_factor_panel", args.factor_panel)
     if args.host_pipeline is not None:
         pc.setOption("ssc_host_pipeline", args.host_pipeline)
     if nranks > 1:

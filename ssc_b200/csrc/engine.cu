@@ -105,6 +105,8 @@ struct SSCPatchPC_s {
     bool save_operators = true, partition_of_unity = false, multiplicative = false, print_patches = false;
     bool symmetrise_sweep = false, keep_operators = false, dim_set = false, codim_set = false;
     int sub_pc = SSC_SUB_LU;
+    int factor_ctas = 0;          // concurrent CTAs of the blocked factor kernel (0 = fill the SMs)
+    int factor_panel = 16;        // panel width of the blocked factor kernel (16 or 32)
     int factor_variant = 1;       // 1: register-resident Gauss-Jordan for n <= 128, 0: shared-memory kernel
     int apply_variant = 1;        // 0: simple loop, 1: pipelined LDG.64, 2: pipelined LDG.128 (even row stride)
     std::string sub_mat_type, sub_ksp_type = "preonly";
@@ -389,6 +391,8 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_keep_patch_operators") return parse_bool(v, &pc->keep_operators);
     if (name == "ssc_builder_threads") { pc->bopt.nthreads = atoi(v); return 0; }
     if (name == "ssc_factor_variant") { pc->factor_variant = atoi(v); return 0; }
+    if (name == "ssc_factor_panel") { pc->factor_panel = atoi(v); return 0; }
+    if (name == "ssc_factor_ctas") { pc->factor_ctas = atoi(v); return 0; }
     if (name == "ssc_host_pipeline") { const int s = atoi(v); pc->pipe_force = s < 0; pc->pipe_slabs = s < 0 ? -s : s; pc->pipe_ready = false; return 0; }   // negative: use it whatever the problem size
     if (name == "ssc_apply_variant") {
         const int a = atoi(v);
@@ -904,7 +908,27 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
         if (smem_f > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_invert_kernel<P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
         ssc_invert_kernel<P, S><<<grid_f, bdf, smem_f, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail);             \
     } while (0)
-    if (n <= 128 && pc->factor_variant == 1) {
+    if (n > 128 && pc->factor_variant == 1) {
+        // blocked Gauss-Jordan with DMMA updates, block resident in L2
+        const int npad = (n + 7) & ~7, WP = ((npad + 15) & ~15) + 4;
+        auto smem_for = [&](int nb) { return ((size_t)npad * (nb + 1) + (size_t)nb * WP + nb + 32) * sizeof(double) + (size_t)(34 + 2 * n + 2) * sizeof(int); };
+        const int nb = (pc->factor_panel == 32 && smem_for(32) <= 220 * 1024) ? 32 : 16;
+        const size_t smem_b = smem_for(nb);
+        if (smem_b > 220 * 1024) return ssc_set_error(SSC_ERR_SUP, "patch with %d dofs is too large for the blocked factor kernel", n);
+        const int per_sm = smem_b <= 110 * 1024 ? 2 : 1;
+        const int grid_b = (int)std::min<i64>(cnt, pc->factor_ctas > 0 ? (i64)pc->factor_ctas : (i64)pc->sm_count * per_sm);
+#define LAUNCH_BLK(P, NBV)                                                                                                     \
+    do {                                                                                                                       \
+        CUDA_OK(cudaFuncSetAttribute(ssc_invert_blocked_kernel<P, NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b)); \
+        ssc_invert_blocked_kernel<P, NBV><<<grid_b, 512, smem_b, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail);            \
+    } while (0)
+        if (pivot && nb == 32) LAUNCH_BLK(true, 32);
+        else if (pivot) LAUNCH_BLK(true, 16);
+        else if (nb == 32) LAUNCH_BLK(false, 32);
+        else LAUNCH_BLK(false, 16);
+#undef LAUNCH_BLK
+    }
+    else if (n <= 128 && pc->factor_variant == 1) {
         // register-resident tiles: (n/8) x (n/4) threads
         const int TC = (n + 3) / 4, TR = (n + 7) / 8;
         const int threads = (TR * TC + 31) / 32 * 32;
