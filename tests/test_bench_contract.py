@@ -1,0 +1,32 @@
+"""bench.py's reference arm runs on CPU and prints one JSON line with the contract's keys."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cells", "6", "--cpu-sample", "64",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "dofs/s" and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
+
+
+def test_product_arm_fails_loudly_without_gpu():
+    import ssc_b200
+    if ssc_b200.device_count() > 0:
+        return
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--cells", "4", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0 and "no CPU fallback" in out.stderr
