@@ -169,8 +169,6 @@ def run_reference(args, rank, nranks):
         base = cpu_baseline(V, disc, csr, args) if base is None or i >= args.warmup else base
         if i >= args.warmup:
             vals.append(base["value"])
-        if i == 0:
-            args.cpu_sample = min(args.cpu_sample, 8192)
         if len(vals) >= 3:           # bounded: a step here is seconds of CPU work
             break
     v = float(np.median(vals)) if vals else base["value"]
