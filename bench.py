@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--apply-variant", type=int, default=None, help="ssc_apply_variant (kernel selection; default = library default)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo exchange: NVLink peer memory (default) or NCCL send/recv")
     ap.add_argument("--factor-panel", type=int, default=None)
+    ap.add_argument("--deterministic", action="store_true", help="ssc_deterministic: slot-and-sum instead of fp64 atomics")
     ap.add_argument("--factor-ctas", type=int, default=None)
     ap.add_argument("--host-pipeline", type=int, default=None, help="ssc_host_pipeline (slabs of the overlapped host-space apply)")
     return ap.parse_args()
@@ -222,6 +223,8 @@ def main():
     pc.setOperatorCSR(*csr)
     if args.apply_variant is not None:
         pc.setOption("ssc_apply_variant", args.apply_variant)
+    if args.deterministic:
+        pc.setOption("ssc_deterministic", True)
     if args.factor_ctas is not None:
         pc.setOption("ssc_factor_ctas", args.factor_ctas)
     if args.factor_panel is not None:

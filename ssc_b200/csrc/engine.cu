@@ -150,6 +150,10 @@ struct SSCPatchPC_s {
     i64 ncolours = 0;
     std::vector<std::vector<std::pair<i64, i64>>> colour_ranges;    // [colour][class] -> sorted positions
     double *d_r = nullptr;
+    bool deterministic = false;      // slot-and-sum instead of atomics
+    double *d_ypatch = nullptr;
+    i64 *d_slotoff = nullptr;
+    int *d_slots = nullptr;
     int *d_gtol = nullptr;
     double *d_blocks = nullptr, *d_blocks0 = nullptr;
     i64 block_elems = 0, sum_n = 0, sum_n2 = 0, max_n = 0;
@@ -259,6 +263,7 @@ extern "C" int SSCPatchCreate(int device, SSCPatchPC *out)
 static void free_device_state(PC *pc)
 {
     if (pc->device < 0) return;
+    dev_free(pc->d_ypatch); dev_free(pc->d_slotoff); dev_free(pc->d_slots);
     dev_free(pc->d_r); dev_free(pc->d_gtol); dev_free(pc->d_blocks); dev_free(pc->d_blocks0); dev_free(pc->d_fail); dev_free(pc->d_bc);
     dev_free(pc->d_w); dev_free(pc->d_mult); dev_free(pc->d_xs); dev_free(pc->d_ys);
     if (!pc->p2p) { dev_free(pc->d_xl); dev_free(pc->d_yl); }
@@ -391,6 +396,13 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_keep_patch_operators") return parse_bool(v, &pc->keep_operators);
     if (name == "ssc_builder_threads") { pc->bopt.nthreads = atoi(v); return 0; }
     if (name == "ssc_factor_variant") { pc->factor_variant = atoi(v); return 0; }
+    if (name == "ssc_deterministic") {
+        bool f = false;
+        CHK(parse_bool(v, &f));
+        if (f != pc->deterministic && pc->device_ready) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "ssc_deterministic must be chosen before the first SetUp");
+        pc->deterministic = f;
+        return 0;
+    }
     if (name == "ssc_factor_panel") { pc->factor_panel = atoi(v); return 0; }
     if (name == "ssc_factor_ctas") { pc->factor_ctas = atoi(v); return 0; }
     if (name == "ssc_host_pipeline") { const int s = atoi(v); pc->pipe_force = s < 0; pc->pipe_slabs = s < 0 ? -s : s; pc->pipe_ready = false; return 0; }   // negative: use it whatever the problem size
@@ -662,6 +674,19 @@ static int build_device_lists(PC *pc)
     if (pc->sum_n) CUDA_OK(cudaMemcpyAsync(pc->d_gtol, g32.data(), (size_t)pc->sum_n * sizeof(int), cudaMemcpyHostToDevice, pc->stream));
     CUDA_OK(cudaStreamSynchronize(pc->stream));
     CHK(dev_alloc(&pc->d_fail, (i64)order.size()));
+    if (pc->deterministic) {
+        if (pc->sf_set) return ssc_set_error(SSC_ERR_SUP, "ssc_deterministic is a single-rank mode in this build");
+        if (pc->sum_n > 2147483647LL) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "too many patch dofs for 32-bit slot numbers");
+        std::vector<i64> soff((size_t)pc->nlocal + 1, 0);
+        for (i64 s = 0; s < pc->sum_n; ++s) soff[(size_t)g32[(size_t)s] + 1]++;
+        for (i64 g = 0; g < pc->nlocal; ++g) soff[(size_t)g + 1] += soff[(size_t)g];
+        std::vector<int> slots((size_t)pc->sum_n);
+        std::vector<i64> fill(soff.begin(), soff.end() - 1);
+        for (i64 s = 0; s < pc->sum_n; ++s) slots[(size_t)fill[(size_t)g32[(size_t)s]]++] = (int)s;      // ascending slot order per dof
+        CHK(dev_alloc(&pc->d_slotoff, pc->nlocal + 1)); CHK(dev_alloc(&pc->d_slots, pc->sum_n)); CHK(dev_alloc(&pc->d_ypatch, pc->sum_n));
+        CUDA_OK(cudaMemcpy(pc->d_slotoff, soff.data(), soff.size() * sizeof(i64), cudaMemcpyHostToDevice));
+        if (pc->sum_n) CUDA_OK(cudaMemcpy(pc->d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     // Dirichlet pass-through list, ssc/libssc.c:1408-1413 (only idx < local size)
     std::vector<i64> bc;
     for (i64 d : pc->globalBc) if (d >= 0 && d < pc->nowned) bc.push_back(d);
@@ -1013,10 +1038,11 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
     const i64 grid = (cnt + c.ppb - 1) / c.ppb;
     const int *gt = pc->d_gtol + c.goff + (q0 - c.first) * c.n;
     const double *mult = pc->d_mult ? pc->d_mult + q0 : nullptr;
+    double *ypatch = (pc->deterministic && !pc->multiplicative) ? pc->d_ypatch + c.goff + (q0 - c.first) * c.n : nullptr;
 #define LAUNCH_APPLY(K)                                                                                                  \
     do {                                                                                                                 \
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        K<<<(unsigned)grid, threads, smem, pc->stream>>>(blocks, c.stride, c.ld, gt, c.n, cnt, c.tp, c.ppb, xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr); \
+        K<<<(unsigned)grid, threads, smem, pc->stream>>>(blocks, c.stride, c.ld, gt, c.n, cnt, c.tp, c.ppb, xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch); \
     } while (0)
     if (pc->apply_variant == 2 && threads <= 256) LAUNCH_APPLY((ssc_apply_pipe_kernel<2, 8>));
     else if (pc->apply_variant == 1 && threads <= 256) LAUNCH_APPLY((ssc_apply_pipe_kernel<1, 8>));
@@ -1107,6 +1133,10 @@ static int apply_device(PC *pc, const double *x, double *y)
             }
         }
     }
+    if (pc->deterministic) {
+        ssc_slot_sum_kernel<<<grid_for(pc->nlocal, 256), 256, 0, pc->stream>>>(pc->nlocal, (const ll *)pc->d_slotoff, pc->d_slots, pc->d_ypatch, yl);
+        pc->launches++;
+    }
     if (pc->ktimer) CUDA_OK(cudaEventRecord(k1, pc->stream));
     if (!identity && pc->p2p) {                             // ghost contributions already sit in their owners' vectors
         CHK(peer_barrier(pc));
@@ -1130,7 +1160,7 @@ static int build_host_pipeline(PC *pc)
 {
     pc->pipe_ready = false;
     const int S = pc->pipe_slabs;
-    if (S < 2 || pc->sf_set || pc->multiplicative || !pc->save_operators || (!pc->pipe_force && pc->sum_n2 * 8 < ((i64)64 << 20))) return 0;
+    if (S < 2 || pc->sf_set || pc->multiplicative || pc->deterministic || !pc->save_operators || (!pc->pipe_force && pc->sum_n2 * 8 < ((i64)64 << 20))) return 0;
     if (pc->lists.npatch < S) return 0;
     const PatchLists &L = pc->lists;
     const i64 np = L.npatch, N = pc->nowned;

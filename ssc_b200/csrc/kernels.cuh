@@ -24,6 +24,14 @@ struct PeerScatter {
     const int *ghostRemote;  // ghost slot -> index in that neighbour's vector
     int nowned;
 };
+// Deterministic mode: instead of reducing into y, every patch dof stores its correction in its own slot of `ypatch`
+// (coalesced plain stores); ssc_slot_sum_kernel then adds the slots of each dof in a fixed order.
+__device__ __forceinline__ void scatter_add(double *__restrict__ y, int gi, double v, const PeerScatter *__restrict__ ps);
+__device__ __forceinline__ void emit(double *__restrict__ y, int gi, double v, const PeerScatter *__restrict__ ps, double *__restrict__ ypatch, ll slot)
+{
+    if (ypatch != nullptr) ypatch[slot] = v;
+    else scatter_add(y, gi, v, ps);
+}
 __device__ __forceinline__ void scatter_add(double *__restrict__ y, int gi, double v, const PeerScatter *__restrict__ ps)
 {
     if (ps != nullptr && gi >= ps->nowned) {
@@ -586,7 +594,7 @@ ssc_invert_blocked_kernel(double *__restrict__ blocks, int n, int ld, ll stride,
 __global__ void __launch_bounds__(1024)
 ssc_apply_kernel(const double *__restrict__ S, ll stride, int ld, const int *__restrict__ gtol, int n, ll count, int tp, int ppb,
                  const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
-                 const PeerScatter *__restrict__ ps)
+                 const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
 {
     extern __shared__ __align__(16) double xs_all[];
     const int lp = threadIdx.x / tp, t = threadIdx.x - lp * tp;
@@ -612,7 +620,7 @@ ssc_apply_kernel(const double *__restrict__ S, ll stride, int ld, const int *__r
             a0 = fma(m4, xs[j + 4], a0); a1 = fma(m5, xs[j + 5], a1); a2 = fma(m6, xs[j + 6], a2); a3 = fma(m7, xs[j + 7], a3);
         }
         for (; j < n; ++j) a0 = fma(__ldcs(M + (ll)j * ld), xs[j], a0);
-        scatter_add(y, g[i], ((a0 + a1) + (a2 + a3)) * sc, ps);
+        emit(y, g[i], ((a0 + a1) + (a2 + a3)) * sc, ps, ypatch, p * n + i);
     }
 }
 
@@ -630,7 +638,7 @@ template <int kVec, int kU>
 __global__ void __launch_bounds__(256)
 ssc_apply_pipe_kernel(const double *__restrict__ S, ll stride, int ld, const int *__restrict__ gtol, int n, ll count, int tp, int ppb,
                       const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
-                      const PeerScatter *__restrict__ ps)
+                      const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
 {
     typedef typename VecT<kVec>::T T;
     extern __shared__ __align__(16) double xs_all[];
@@ -678,8 +686,8 @@ ssc_apply_pipe_kernel(const double *__restrict__ S, ll stride, int ld, const int
             }
         }
         for (int j = ngroups * kU; j < n; ++j) fma_vec(__ldcs(M + (ll)j * ldv), xs[j], a0, a1);
-        scatter_add(y, g[i], (a0 + b0) * sc, ps);
-        if (kVec == 2 && i + 1 < n) scatter_add(y, g[i + 1], (a1 + b1) * sc, ps);
+        emit(y, g[i], (a0 + b0) * sc, ps, ypatch, p * n + i);
+        if (kVec == 2 && i + 1 < n) emit(y, g[i + 1], (a1 + b1) * sc, ps, ypatch, p * n + i + 1);
     }
 }
 
@@ -785,4 +793,14 @@ __global__ void ssc_residual_kernel(ll nrows, const ll *__restrict__ rowptr, con
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if (lane == 0) r[warp] = x[warp] - s;
+}
+
+// deterministic mode: y[g] = sum of the slots of dof g, in ascending slot order (no atomics)
+__global__ void ssc_slot_sum_kernel(ll n, const ll *__restrict__ off, const int *__restrict__ slots, const double *__restrict__ ypatch, double *__restrict__ y)
+{
+    for (ll g = (ll)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (ll)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (ll k = off[g]; k < off[g + 1]; ++k) s += ypatch[slots[k]];
+        y[g] = s;
+    }
 }

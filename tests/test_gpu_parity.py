@@ -281,3 +281,20 @@ def test_multiplicative_is_a_better_preconditioner():
         _, its[mult], _ = solve(pl.Mat(A), b, "gmres", lambda pc: pc.setFromOptions(), dm=pl.DM(fem.SNESContext(form, bcs)))
     pl.Options.clear()
     assert its[True] < its[False]
+
+
+def test_deterministic_mode_is_bitwise_reproducible():
+    """-ssc_deterministic: corrections go to per-patch slots and are summed per dof in a fixed order: no fp64 atomics,
+    bit-identical results run to run, same values as the atomic path to rounding."""
+    form, bcs, disc, A = _problem(plex.TensorPlex((5, 5, 4)), 3, "scalar")
+    o = make_oracle(disc, A, symmetrise_sweep=1)
+    pc = make_gpu(form, bcs, ssc_deterministic=True, symmetrise_sweep=1)
+    pc.setUp()
+    x = rhs_vector(disc.total_dofs)
+    ys = []
+    for _ in range(4):
+        y = np.full_like(x, np.nan)
+        pc.apply(x, y)
+        ys.append(y)
+    assert all(np.array_equal(ys[0], yy) for yy in ys[1:])
+    assert relerr(ys[0], o.apply(x)) < TOL
