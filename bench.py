@@ -259,7 +259,7 @@ def main():
     if nranks > 1:
         pc._csr_keep = None          # the CSR was only borrowed until SetUp returned; N=1 keeps it for the CPU baseline
         csr = None
-    setup = {"create_patches_ms": pc.eventTime("PCPATCHCreate"), "extract_ms": pc.eventTime("PCPATCHComputeOp"),
+    setup = {"note": "setup_wall_s = SSCPatchSetUp with the CSR in pageable host memory: patch construction on the host, H2D of dof lists and CSR, extract, factor", "create_patches_ms": pc.eventTime("PCPATCHCreate"), "extract_ms": pc.eventTime("PCPATCHComputeOp"),
              "factor_ms": pc.eventTime("PCPATCHSolve"), "setup_wall_s": info["t_setup_wall"],
              "assemble_wall_s": info["t_assemble"], "mesh_wall_s": info["t_mesh"]}
     nowned = pc.size("nowned")

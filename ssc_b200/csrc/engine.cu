@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 #include <dlfcn.h>
+#include <thread>
 
 // ---------------------------------------------------------------------------------------------
 // errors
@@ -172,6 +173,8 @@ struct SSCPatchPC_s {
     double *d_vals = nullptr;
     bool csr_owned = false;
     void *d_flush = nullptr;
+    void *stage[3] = {nullptr, nullptr, nullptr};      // pinned staging ring for large pageable uploads
+    cudaEvent_t stage_ev[3] = {nullptr, nullptr, nullptr};
     // pipelined host-space apply: H2D of x, patch kernels and D2H of y overlap slab by slab
     int pipe_slabs = 8;
     bool pipe_force = false;
@@ -297,6 +300,7 @@ extern "C" int SSCPatchDestroy(SSCPatchPC *ppc)
     cudaStreamSynchronize(pc->stream);
     free_device_state(pc);
     if (pc->d_flush) cudaFree(pc->d_flush);
+    for (int r = 0; r < 3; ++r) if (pc->stage[r]) { cudaFreeHost(pc->stage[r]); cudaEventDestroy(pc->stage_ev[r]); }
     for (void *q : pc->ipc_opened) cudaIpcCloseMemHandle(q);
     pc->p2p = false;
     dev_free(pc->d_xl); dev_free(pc->d_yl); dev_free(pc->d_flags); dev_free(pc->d_timeout); dev_free(pc->d_ps);
@@ -869,6 +873,44 @@ static int peer_reduce(PC *pc, double *yl, double *y)
     return 0;
 }
 
+// Host -> device copy of a large pageable array: worker threads copy slices into a small ring of pinned buffers while
+// the previous buffer is in flight over PCIe (a plain cudaMemcpy from pageable memory is bound by one host thread).
+static int staged_upload(PC *pc, void *dst, const void *src, size_t bytes)
+{
+    const size_t chunk = (size_t)128 << 20;
+    if (bytes < 2 * chunk) { CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, pc->stream)); return 0; }
+    const int R = 3;
+    if (!pc->stage[0]) {
+        for (int r = 0; r < R; ++r) {
+            cudaError_t err = cudaMallocHost(&pc->stage[r], chunk);
+            if (err != cudaSuccess) {       // no pinned memory to spare: fall back to the driver's own staging
+                cudaGetLastError();
+                for (int q = 0; q < r; ++q) { cudaFreeHost(pc->stage[q]); pc->stage[q] = nullptr; }
+                CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, pc->stream));
+                return 0;
+            }
+            CUDA_OK(cudaEventCreateWithFlags(&pc->stage_ev[r], cudaEventDisableTiming));
+        }
+    }
+    const int T = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    size_t off = 0;
+    for (int it = 0; off < bytes; ++it) {
+        const int r = it % R;
+        const size_t len = std::min(chunk, bytes - off);
+        if (it >= R) CUDA_OK(cudaEventSynchronize(pc->stage_ev[r]));
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t) {
+            const size_t a = len * t / T, b = len * (t + 1) / T;
+            th.emplace_back([=]() { memcpy((char *)pc->stage[r] + a, (const char *)src + off + a, b - a); });
+        }
+        for (auto &x : th) x.join();
+        CUDA_OK(cudaMemcpyAsync((char *)dst + off, pc->stage[r], len, cudaMemcpyHostToDevice, pc->stream));
+        CUDA_OK(cudaEventRecord(pc->stage_ev[r], pc->stream));
+        off += len;
+    }
+    return 0;
+}
+
 static int upload_csr(PC *pc)
 {
     if (!pc->csr_set) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "Must call SSCPatchSetOperatorCSR() to set the operator");   // cf. ssc/libssc.c:1131-1133
@@ -884,8 +926,8 @@ static int upload_csr(PC *pc)
     CHK(dev_alloc(&pc->d_vals, nnz));
     pc->csr_owned = true;
     CUDA_OK(cudaMemcpyAsync(pc->d_rowptr, pc->csr_rowptr, (size_t)(pc->csr_nrows + 1) * sizeof(i64), cudaMemcpyHostToDevice, pc->stream));
-    CUDA_OK(cudaMemcpyAsync(pc->d_colidx, pc->csr_colidx, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, pc->stream));
-    CUDA_OK(cudaMemcpyAsync(pc->d_vals, pc->csr_vals, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, pc->stream));
+    CHK(staged_upload(pc, pc->d_colidx, pc->csr_colidx, (size_t)nnz * sizeof(int)));
+    CHK(staged_upload(pc, pc->d_vals, pc->csr_vals, (size_t)nnz * sizeof(double)));
     return 0;
 }
 

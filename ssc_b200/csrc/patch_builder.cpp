@@ -18,18 +18,29 @@
 #include <algorithm>
 #include <thread>
 #include <atomic>
+#include <cstdlib>
 
 namespace {
 
+// the four per-dof marks share a cache line: a patch touches each of its ~n dofs in all four roles
+struct DofMark { int32_t owned, seen, local, idx; };
+
+// calloc, not vector::assign: a worker only ever touches the marks near its own range of patches, and untouched
+// zero pages are never faulted in
+template <class T> struct ZeroArray {
+    T *p = nullptr;
+    void init(i64 n) { std::free(p); p = static_cast<T *>(std::calloc((size_t)std::max<i64>(n, 1), sizeof(T))); }
+    ~ZeroArray() { std::free(p); }
+    T &operator[](i64 i) { return p[i]; }
+};
+
 struct Scratch {
-    std::vector<int32_t> ptOwned, ptStar, ptSeen;      // stamps over mesh points
-    std::vector<int32_t> dofOwned, dofSeen, dofLocal;   // stamps over local dofs
-    std::vector<int32_t> localIdx;
+    ZeroArray<int32_t> ptOwned, ptStar, ptSeen;        // stamps over mesh points
+    ZeroArray<DofMark> dof;                            // stamps over local dofs
     std::vector<i64> owned, star, seen, cells;
     void init(i64 pEnd, i64 nlocal) {
-        ptOwned.assign(pEnd, 0); ptStar.assign(pEnd, 0); ptSeen.assign(pEnd, 0);
-        dofOwned.assign(nlocal, 0); dofSeen.assign(nlocal, 0); dofLocal.assign(nlocal, 0);
-        localIdx.assign(nlocal, 0);
+        ptOwned.init(pEnd); ptStar.init(pEnd); ptSeen.init(pEnd);
+        dof.init(nlocal);
     }
 };
 
@@ -40,7 +51,7 @@ struct Chunk {
 };
 
 // grow `list` by everything reachable from list[from..] through `off/adj`, marking with `stamp`
-inline void bfs(const std::vector<i64> &off, const std::vector<i64> &adj, std::vector<int32_t> &mark,
+inline void bfs(const std::vector<i64> &off, const std::vector<i64> &adj, ZeroArray<int32_t> &mark,
                 int32_t stamp, std::vector<i64> &list, size_t from) {
     for (size_t head = from; head < list.size(); ++head) {
         i64 q = list[head];
@@ -51,7 +62,7 @@ inline void bfs(const std::vector<i64> &off, const std::vector<i64> &adj, std::v
     }
 }
 
-inline void push(std::vector<int32_t> &mark, int32_t stamp, std::vector<i64> &list, i64 p) {
+inline void push(ZeroArray<int32_t> &mark, int32_t stamp, std::vector<i64> &list, i64 p) {
     if (mark[p] != stamp) { mark[p] = stamp; list.push_back(p); }
 }
 
@@ -122,11 +133,11 @@ struct Builder {
         // owned / seen dofs: PCPatchGetPointDofs ssc/libssc.c:370-416; artificial BCs = seen \ owned (:420-440)
         for (i64 k = 0; k < disc.nsub; ++k) {
             if (k == opt.exclude_subspace) {
-                for_point_dofs(k, v, [&](i64 g) { s.dofOwned[g] = stamp; });
+                for_point_dofs(k, v, [&](i64 g) { s.dof[g].owned = stamp; });
             } else {
-                for (i64 p : s.owned) for_point_dofs(k, p, [&](i64 g) { s.dofOwned[g] = stamp; });
+                for (i64 p : s.owned) for_point_dofs(k, p, [&](i64 g) { s.dof[g].owned = stamp; });
             }
-            for (i64 p : s.seen) for_point_dofs(k, p, [&](i64 g) { s.dofSeen[g] = stamp; });
+            for (i64 p : s.seen) for_point_dofs(k, p, [&](i64 g) { s.dof[g].seen = stamp; });
         }
         // first-encounter numbering, ssc/libssc.c:731-778
         size_t g0 = out.gtol.size(), d0 = out.dofs.size();
@@ -143,9 +154,10 @@ struct Builder {
                         const i64 g = base + l;
                         if (g < 0 || g >= nlocal) { out.msg = "cell node map entry outside the local dof range"; return SSC_ERR_ARG_OUTOFRANGE; }
                         i64 loc;
-                        if (isGlobalBc[g] || (s.dofSeen[g] == stamp && s.dofOwned[g] != stamp)) loc = -1;
-                        else if (s.dofLocal[g] == stamp) loc = s.localIdx[g];
-                        else { s.dofLocal[g] = stamp; s.localIdx[g] = next; loc = next++; out.gtol.push_back(g); }
+                        DofMark &m = s.dof[g];
+                        if (isGlobalBc[g] || (m.seen == stamp && m.owned != stamp)) loc = -1;
+                        else if (m.local == stamp) loc = m.idx;
+                        else { m.local = stamp; m.idx = next; loc = next++; out.gtol.push_back(g); }
                         if (opt.keep_dofs && disc.nsub == 1) out.dofs.push_back(loc);
                     }
                 }
@@ -161,7 +173,7 @@ struct Builder {
                     const i64 *cnm = disc.cellNodeMap[k];
                     for (i64 j = 0; j < npc; ++j) for (i64 l = 0; l < bs; ++l) {
                         const i64 g = cnm[cell * npc + j] * bs + so + l;
-                        out.dofs.push_back(s.dofLocal[g] == stamp ? s.localIdx[g] : -1);
+                        out.dofs.push_back(s.dof[g].local == stamp ? s.dof[g].idx : -1);
                     }
                 }
             }
@@ -233,12 +245,23 @@ int ssc_build_patches(const HostPlex &plex, const Discretisation &disc, const Us
         ncells += (i64)c.cells.size(); ngtol += (i64)c.gtol.size(); ndofs += (i64)c.dofs.size();
     }
     out.cells.resize(ncells); out.gtol.resize(ngtol); out.dofs.resize(ndofs);
-    i64 a = 0, g = 0, d = 0;
-    for (auto &c : chunks) {
-        std::copy(c.cells.begin(), c.cells.end(), out.cells.begin() + a); a += (i64)c.cells.size();
-        std::copy(c.gtol.begin(), c.gtol.end(), out.gtol.begin() + g); g += (i64)c.gtol.size();
-        std::copy(c.dofs.begin(), c.dofs.end(), out.dofs.begin() + d); d += (i64)c.dofs.size();
+    // every chunk copies itself to its place (in parallel when there are several)
+    std::vector<i64> ca(chunks.size() + 1, 0), ga(chunks.size() + 1, 0), da(chunks.size() + 1, 0);
+    for (size_t t = 0; t < chunks.size(); ++t) {
+        ca[t + 1] = ca[t] + (i64)chunks[t].cells.size(); ga[t + 1] = ga[t] + (i64)chunks[t].gtol.size(); da[t + 1] = da[t] + (i64)chunks[t].dofs.size();
+    }
+    auto place = [&](int t) {
+        Chunk &c = chunks[t];
+        std::copy(c.cells.begin(), c.cells.end(), out.cells.begin() + ca[t]);
+        std::copy(c.gtol.begin(), c.gtol.end(), out.gtol.begin() + ga[t]);
+        std::copy(c.dofs.begin(), c.dofs.end(), out.dofs.begin() + da[t]);
         Chunk().cells.swap(c.cells); Chunk().gtol.swap(c.gtol); Chunk().dofs.swap(c.dofs);
+    };
+    if (T == 1) place(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t) th.emplace_back(place, t);
+        for (auto &x : th) x.join();
     }
     return 0;
 }
