@@ -95,6 +95,8 @@ struct SizeClass {
     i64 moff = 0;                 // offset of the class in d_blocks (doubles)
     i64 stride = 0;               // doubles per block
     int ld = 0;                   // row stride inside a block (doubles)
+    i64 poff = 0, pstride = 0;    // packed-symmetric storage: class offset and per-patch stride (doubles)
+    unsigned pbytes = 0;          // bytes of one packed triangle moved by the bulk copy
     int tp = 0, ppb = 0;          // apply launch shape
 };
 
@@ -152,6 +154,9 @@ struct SSCPatchPC_s {
     std::vector<std::vector<std::pair<i64, i64>>> colour_ranges;    // [colour][class] -> sorted positions
     double *d_r = nullptr;
     bool deterministic = false;      // slot-and-sum instead of atomics
+    bool symmetric = false;          // packed lower triangle of the (symmetric) inverse only
+    double *d_packed = nullptr;
+    i64 packed_elems = 0;
     double *d_ypatch = nullptr;
     i64 *d_slotoff = nullptr;
     int *d_slots = nullptr;
@@ -266,6 +271,7 @@ extern "C" int SSCPatchCreate(int device, SSCPatchPC *out)
 static void free_device_state(PC *pc)
 {
     if (pc->device < 0) return;
+    dev_free(pc->d_packed);
     dev_free(pc->d_ypatch); dev_free(pc->d_slotoff); dev_free(pc->d_slots);
     dev_free(pc->d_r); dev_free(pc->d_gtol); dev_free(pc->d_blocks); dev_free(pc->d_blocks0); dev_free(pc->d_fail); dev_free(pc->d_bc);
     dev_free(pc->d_w); dev_free(pc->d_mult); dev_free(pc->d_xs); dev_free(pc->d_ys);
@@ -400,6 +406,13 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_keep_patch_operators") return parse_bool(v, &pc->keep_operators);
     if (name == "ssc_builder_threads") { pc->bopt.nthreads = atoi(v); return 0; }
     if (name == "ssc_factor_variant") { pc->factor_variant = atoi(v); return 0; }
+    if (name == "ssc_symmetric_storage") {
+        bool f = false;
+        CHK(parse_bool(v, &f));
+        if (f != pc->symmetric && pc->device_ready) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "ssc_symmetric_storage must be chosen before the first SetUp");
+        pc->symmetric = f;
+        return 0;
+    }
     if (name == "ssc_deterministic") {
         bool f = false;
         CHK(parse_bool(v, &f));
@@ -643,6 +656,7 @@ static int build_device_lists(PC *pc)
             c.ld = pc->apply_variant == 2 ? (int)((n + 1) / 2 * 2) : (int)n;
             c.stride = (n * c.ld + 15) / 16 * 16;
             choose_launch_shape(c, pc->apply_variant);
+            { const i64 psz = n * (n + 1) / 2; c.pstride = (psz + 15) / 16 * 16; c.pbytes = (unsigned)(((psz + 1) / 2 * 2) * 8); }
             pc->classes.push_back(c);
         }
         SizeClass &c = pc->classes.back();
@@ -651,6 +665,13 @@ static int build_device_lists(PC *pc)
         pc->sum_n += n; pc->sum_n2 += n * n; pc->max_n = std::max(pc->max_n, n);
     }
     pc->block_elems = moff;
+    {
+        i64 po = 0;
+        for (SizeClass &c : pc->classes) { c.poff = po; po += c.count * c.pstride; }
+        pc->packed_elems = po;
+        if (pc->symmetric) for (const SizeClass &c : pc->classes)
+            if ((size_t)c.pbytes + (size_t)c.n * 8 > 225 * 1024) return ssc_set_error(SSC_ERR_SUP, "ssc_symmetric_storage holds a whole packed block in shared memory: patches up to 238 dofs (found %d)", c.n);
+    }
     if (pc->multiplicative) {
         pc->colour_ranges.assign((size_t)pc->ncolours, std::vector<std::pair<i64, i64>>(pc->classes.size(), {0, 0}));
         for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
@@ -1050,7 +1071,17 @@ extern "C" int SSCPatchSetUp(SSCPatchPC pc)
         if (pc->keep_operators && !pc->d_blocks0) CHK(dev_alloc(&pc->d_blocks0, pc->block_elems));
         for (const SizeClass &c : pc->classes)
             CHK(extract_and_invert(pc, c, c.first, c.first + c.count, pc->d_blocks + c.moff, pc->d_fail + c.first, true));
+        if (pc->symmetric) {
+            if (pc->sub_pc != SSC_SUB_CHOLESKY) return ssc_set_error(SSC_ERR_ARG_INCOMP, "ssc_symmetric_storage keeps half of a symmetric inverse: it needs SPD blocks, i.e. -sub_pc_type cholesky");
+            if (!pc->d_packed) CHK(dev_alloc(&pc->d_packed, pc->packed_elems));
+            for (const SizeClass &c : pc->classes) {
+                ssc_pack_sym_kernel<<<(unsigned)std::min<i64>(c.count, (i64)pc->sm_count * 32), 256, 0, pc->stream>>>(pc->d_blocks + c.moff, c.n, c.ld, c.stride, pc->d_packed + c.poff, c.pstride, c.count);
+                pc->launches++;
+            }
+            CUDA_OK(cudaGetLastError());
+        }
         CUDA_OK(cudaStreamSynchronize(pc->stream));
+        if (pc->symmetric) dev_free(pc->d_blocks);          // only the packed triangles stay resident
         // per-patch failure flags: the reference would surface KSP_DIVERGED_PCSETUP_FAILED (dead code ssc/libssc.c:1439-1442)
         std::vector<int> fail(pc->sorted2orig.size());
         if (!fail.empty()) CUDA_OK(cudaMemcpy(fail.data(), pc->d_fail, fail.size() * sizeof(int), cudaMemcpyDeviceToHost));
@@ -1061,6 +1092,7 @@ extern "C" int SSCPatchSetUp(SSCPatchPC pc)
         if (pc->failed) return ssc_set_error(SSC_ERR_MAT_LU_ZRPVT, "%lld patch operators could not be factorised (first: patch %lld)%s", (long long)pc->failed,
                                              (long long)firstbad, pc->sub_pc == SSC_SUB_CHOLESKY ? "; sub_pc_type cholesky needs SPD blocks" : "");
     } else {
+        if (pc->symmetric) return ssc_set_error(SSC_ERR_ARG_INCOMP, "ssc_symmetric_storage needs saved patch operators");
         CUDA_OK(cudaStreamSynchronize(pc->stream));
     }
     if (!pc->pipe_ready) CHK(build_host_pipeline(pc));
@@ -1071,16 +1103,27 @@ extern "C" int SSCPatchSetUp(SSCPatchPC pc)
 // ---------------------------------------------------------------------------------------------
 // apply
 // ---------------------------------------------------------------------------------------------
-static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const double *blocks, const double *xl, double *yl, double scale)
+static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const double *blocks_override, const double *xl, double *yl, double scale)
 {
     const i64 cnt = q1 - q0;
     if (cnt <= 0) return 0;
-    const int threads = std::max(32, (c.tp * c.ppb + 31) / 32 * 32);
-    const size_t smem = (size_t)c.ppb * c.n * sizeof(double);
-    const i64 grid = (cnt + c.ppb - 1) / c.ppb;
     const int *gt = pc->d_gtol + c.goff + (q0 - c.first) * c.n;
     const double *mult = pc->d_mult ? pc->d_mult + q0 : nullptr;
     double *ypatch = (pc->deterministic && !pc->multiplicative) ? pc->d_ypatch + c.goff + (q0 - c.first) * c.n : nullptr;
+    if (pc->symmetric && !blocks_override) {
+        const int threads = std::min(1024, (c.n + 31) / 32 * 32);
+        const size_t smem = (size_t)c.pbytes + (size_t)c.n * sizeof(double);
+        if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_apply_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ssc_apply_sym_kernel<<<(unsigned)cnt, threads, smem, pc->stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, gt, c.n, cnt,
+                                                                        xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch);
+        pc->launches++;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    const double *blocks = blocks_override ? blocks_override : pc->d_blocks + c.moff + (q0 - c.first) * c.stride;
+    const int threads = std::max(32, (c.tp * c.ppb + 31) / 32 * 32);
+    const size_t smem = (size_t)c.ppb * c.n * sizeof(double);
+    const i64 grid = (cnt + c.ppb - 1) / c.ppb;
 #define LAUNCH_APPLY(K)                                                                                                  \
     do {                                                                                                                 \
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
@@ -1120,7 +1163,7 @@ static int apply_multiplicative(PC *pc, const double *x, double *y)
             for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
                 const SizeClass &c = pc->classes[ci];
                 const i64 q0 = pc->colour_ranges[(size_t)col][ci].first, q1 = pc->colour_ranges[(size_t)col][ci].second;
-                if (q1 > q0) CHK(launch_apply_class(pc, c, q0, q1, pc->d_blocks + c.moff + (q0 - c.first) * c.stride, r, y, 1.0));
+                if (q1 > q0) CHK(launch_apply_class(pc, c, q0, q1, nullptr, r, y, 1.0));
             }
         }
     }
@@ -1159,7 +1202,7 @@ static int apply_device(PC *pc, const double *x, double *y)
         CUDA_OK(cudaEventRecord(k0, pc->stream));
     }
     if (pc->save_operators) {
-        for (const SizeClass &c : pc->classes) CHK(launch_apply_class(pc, c, c.first, c.first + c.count, pc->d_blocks + c.moff, xl, yl, scale));
+        for (const SizeClass &c : pc->classes) CHK(launch_apply_class(pc, c, c.first, c.first + c.count, nullptr, xl, yl, scale));
     } else {
         // -pc_patch_save_operators false: rebuild, factorise, use and drop every patch operator inside the apply
         // (ssc/libssc.c:1363-1382), in batches that fit a bounded scratch buffer
@@ -1264,7 +1307,7 @@ static int apply_host_pipelined(PC *pc, const double *x, double *y)
         for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
             const SizeClass &c = pc->classes[ci];
             const i64 q0 = pc->pipe_ranges[s][ci].first, q1 = pc->pipe_ranges[s][ci].second;
-            if (q1 > q0) CHK(launch_apply_class(pc, c, q0, q1, pc->d_blocks + c.moff + (q0 - c.first) * c.stride, dx, dy, scale));
+            if (q1 > q0) CHK(launch_apply_class(pc, c, q0, q1, nullptr, dx, dy, scale));
         }
         const i64 a = pc->pipe_out[s], b = pc->pipe_out[s + 1];
         const i64 nb = pc->pipe_bc[s + 1] - pc->pipe_bc[s];
@@ -1353,8 +1396,8 @@ extern "C" int SSCPatchGetSize(SSCPatchPC pc, const char *what, SSCInt *value)
     else if (w == "num_dofs") *value = (i64)pc->lists.dofs.size();
     else if (w == "num_classes") *value = (i64)pc->classes.size();
     else if (w == "num_colours") *value = pc->ncolours;
-    else if (w == "block_bytes") *value = pc->block_elems * 8;
-    else if (w == "bytes_apply") *value = 8 * pc->sum_n2 + (4 + 8 + 8) * pc->sum_n + 16 * pc->nowned;
+    else if (w == "block_bytes") *value = (pc->symmetric ? pc->packed_elems : pc->block_elems) * 8;
+    else if (w == "bytes_apply") *value = (pc->symmetric ? 4 * (pc->sum_n2 + pc->sum_n) : 8 * pc->sum_n2) + (4 + 8 + 8) * pc->sum_n + 16 * pc->nowned;   // SURVEY.md 8(d); packed: 4 sum n(n+1)
     else if (w == "bytes_extract") { if (pc->csr_set && pc->csr_space == SSC_MEM_HOST) nnz = pc->csr_rowptr[pc->csr_nrows]; *value = 12 * nnz + 8 * (pc->nlocal + 1) + 4 * pc->sum_n + 8 * pc->sum_n2; }
     else if (w == "flops_factor") { i64 f = 0; for (auto &c : pc->classes) f += 2 * c.count * (i64)c.n * c.n * c.n; *value = f; }
     else if (w == "failed_patches") *value = pc->failed;
@@ -1402,6 +1445,18 @@ extern "C" int SSCPatchGetPatchMatrix(SSCPatchPC pc, SSCInt p, int which, double
     if (p < 0 || p >= pc->lists.npatch) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "Asked for operator index is invalid");   // ssc/libssc.c:1069-1071
     const i64 q = pc->orig2sorted[p];
     if (q < 0) return 0;
+    if (which != 0 && pc->symmetric) {
+        for (const SizeClass &c : pc->classes) {
+            if (q >= c.first && q < c.first + c.count) {
+                const i64 n = c.n, psz = n * (n + 1) / 2;
+                std::vector<double> tmp((size_t)psz);
+                CUDA_OK(cudaStreamSynchronize(pc->stream));
+                CUDA_OK(cudaMemcpy(tmp.data(), pc->d_packed + c.poff + (q - c.first) * c.pstride, (size_t)psz * sizeof(double), cudaMemcpyDeviceToHost));
+                for (i64 j = 0; j < n; ++j) for (i64 i = j; i < n; ++i) out[i * n + j] = out[j * n + i] = tmp[(size_t)(j * n - j * (j - 1) / 2 + (i - j))];
+                return 0;
+            }
+        }
+    }
     const double *src = which == 0 ? pc->d_blocks0 : pc->d_blocks;
     if (!src) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "unfactored blocks are only kept with option ssc_keep_patch_operators");
     for (const SizeClass &c : pc->classes) {

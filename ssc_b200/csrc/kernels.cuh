@@ -804,3 +804,99 @@ __global__ void ssc_slot_sum_kernel(ll n, const ll *__restrict__ off, const int 
         y[g] = s;
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Packed-symmetric storage (-ssc_symmetric_storage, SPD blocks with -sub_pc_type cholesky): the inverse of an SPD
+// block is symmetric, so only its lower triangle is kept, column by column: L[colstart(j) + (i - j)] = S[i][j], i >= j,
+// colstart(j) = j n - j (j - 1) / 2.  Half the bytes of the general layout (own roofline line: SURVEY.md 8d).
+// The apply kernel brings the whole triangle of a patch into shared memory with ONE bulk asynchronous copy (TMA,
+// cp.async.bulk + mbarrier: SASS UBLKCP), several CTAs per SM keep ~190 KB in flight, and thread i then does
+//   y_i = sum_{j <= i} L[i][j] x_j  (row pass, conflict-free)  +  sum_{k > i} L[k][i] x_k  (column pass)
+// -- n multiply-adds per thread whatever i is.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__global__ void ssc_pack_sym_kernel(const double *__restrict__ blocks, int n, int ld, ll stride, double *__restrict__ packed, ll pstride, ll count)
+{
+    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
+        const double *S = blocks + p * stride;
+        double *L = packed + p * pstride;
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+            const int j = e / n, i = e - j * n;                          // S[j*ld + i] = inverse[i][j]; consecutive threads -> consecutive i
+            if (i >= j) L[(ll)j * n - (ll)j * (j - 1) / 2 + (i - j)] = 0.5 * (S[(ll)j * ld + i] + S[(ll)i * ld + j]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+ssc_apply_sym_kernel(const double *__restrict__ packed, ll pstride, unsigned copy_bytes, const int *__restrict__ gtol, int n, ll count,
+                     const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
+                     const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *L = reinterpret_cast<double *>(smem_raw);
+    double *xs = L + (copy_bytes >> 3);
+    __shared__ __align__(8) unsigned long long bar;
+    const ll p = blockIdx.x;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0) {
+        mbar_expect_tx(&bar, copy_bytes);
+        bulk_copy_g2s(L, packed + p * pstride, copy_bytes, &bar);
+    }
+    const int *g = gtol + p * n;
+    for (int i = t; i < n; i += blockDim.x) xs[i] = __ldg(x + g[i]);
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    const double sc = mult ? scale * mult[p] : scale;
+    for (int i = t; i < n; i += blockDim.x) {
+        double a0 = 0.0, a1 = 0.0;
+        // row pass: L[i][j], j <= i, sits at colstart(j) + (i - j)
+        int cs = i;                                   // colstart(j) + i - j for j = 0
+        int j = 0;
+        for (; j + 1 <= i; j += 2) {
+            const double l0 = L[cs];
+            const int cs1 = cs + (n - j) - 1;
+            const double l1 = L[cs1];
+            a0 = fma(l0, xs[j], a0);
+            a1 = fma(l1, xs[j + 1], a1);
+            cs = cs1 + (n - j - 1) - 1;
+        }
+        if (j <= i) a0 = fma(L[cs], xs[j], a0);
+        // column pass: L[k][i], k > i, sits at colstart(i) + (k - i)
+        const double *col = L + ((ll)i * n - (ll)i * (i - 1) / 2) - i;
+        int kk = i + 1;
+        for (; kk + 1 < n; kk += 2) { a0 = fma(col[kk], xs[kk], a0); a1 = fma(col[kk + 1], xs[kk + 1], a1); }
+        if (kk < n) a0 = fma(col[kk], xs[kk], a0);
+        emit(y, g[i], (a0 + a1) * sc, ps, ypatch, p * n + i);
+    }
+}

@@ -298,3 +298,40 @@ def test_deterministic_mode_is_bitwise_reproducible():
         ys.append(y)
     assert all(np.array_equal(ys[0], yy) for yy in ys[1:])
     assert relerr(ys[0], o.apply(x)) < TOL
+
+
+@pytest.mark.parametrize("case", [("hex", (4, 4, 4), 3, "scalar"), ("tri", None, 4, "vector"), ("tet", None, 2, "scalar"), ("hex", (2, 2, 2), 1, "mixed")])
+def test_packed_symmetric_storage(case):
+    """-ssc_symmetric_storage with -sub_pc_type cholesky: half the block bytes, bulk-copy (TMA) apply kernel, same answer."""
+    kind, shape, p, space = case
+    mesh = plex.TensorPlex(shape) if kind == "hex" else (plex.RectangleMesh(5, 4, 1, 1) if kind == "tri" else plex.BoxMesh(3, 3, 3))
+    form, bcs, disc, A = _problem(mesh, p, space)
+    o = make_oracle(disc, A, partition_of_unity=1)
+    pc = make_gpu(form, bcs, sub_pc_type="cholesky", ssc_symmetric_storage=True, partition_of_unity=1)
+    pc.setUp()
+    full = make_gpu(form, bcs)
+    full.setUp()
+    if pc.size("max_n") >= 100:                  # small blocks are dominated by the 128-byte alignment of each block
+        assert pc.size("block_bytes") < 0.55 * full.size("block_bytes")
+    for seed in (20260101, 20260102):
+        x = rhs_vector(disc.total_dofs, seed)
+        y = np.zeros_like(x)
+        pc.apply(x, y)
+        assert relerr(y, o.apply(x)) < TOL
+    i = int(np.argmax(np.diff(pc.getPatches()[0])))
+    Binv = pc.getPatchMatrix(i, inverse=True)
+    assert np.array_equal(Binv, Binv.T)
+    assert np.allclose(Binv, full.getPatchMatrix(i, inverse=True), rtol=1e-10, atol=1e-14)
+    pc.setUp()                                   # set-up again: blocks are re-extracted, re-factored, re-packed
+    y2 = np.zeros_like(x)
+    pc.apply(x, y2)
+    assert relerr(y2, o.apply(x)) < TOL
+
+
+def test_packed_symmetric_storage_needs_cholesky():
+    from ssc_b200 import SSCError
+    form, bcs, disc, A = _problem(plex.IntervalMesh(6), 2, "scalar")
+    pc = make_gpu(form, bcs, ssc_symmetric_storage=True)
+    with pytest.raises(SSCError) as e:
+        pc.setUp()
+    assert e.value.ierr == 75
