@@ -155,6 +155,7 @@ struct SSCPatchPC_s {
     double *d_r = nullptr;
     bool deterministic = false;      // slot-and-sum instead of atomics
     bool symmetric = false;          // packed lower triangle of the (symmetric) inverse only
+    bool sym_persistent = false;     // persistent ring-buffered form of the packed apply kernel (measured slower: profiles/README.md)
     double *d_packed = nullptr;
     i64 packed_elems = 0;
     double *d_ypatch = nullptr;
@@ -413,6 +414,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
         pc->symmetric = f;
         return 0;
     }
+    if (name == "ssc_symmetric_persistent") return parse_bool(v, &pc->sym_persistent);
     if (name == "ssc_deterministic") {
         bool f = false;
         CHK(parse_bool(v, &f));
@@ -1112,6 +1114,18 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
     double *ypatch = (pc->deterministic && !pc->multiplicative) ? pc->d_ypatch + c.goff + (q0 - c.first) * c.n : nullptr;
     if (pc->symmetric && !blocks_override) {
         const int threads = std::min(1024, (c.n + 31) / 32 * 32);
+        const i64 per_cta = cnt / std::max(1, pc->sm_count);
+        int stages = (int)std::min<size_t>(4, ((size_t)220 * 1024 - 3 * (size_t)c.n * 8) / std::max<size_t>(c.pbytes, 16));
+        if (pc->sym_persistent && stages >= 2 && per_cta >= 8) {
+            const size_t smem_p = (size_t)stages * c.pbytes + 3 * (size_t)c.n * sizeof(double);
+            const int threads_p = c.n <= 512 ? 2 * ((c.n + 31) / 32 * 32) : threads;
+            CUDA_OK(cudaFuncSetAttribute(ssc_apply_sym_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+            ssc_apply_sym_persistent_kernel<<<pc->sm_count, threads_p, smem_p, pc->stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, stages, gt,
+                                                                                        c.n, cnt, xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch);
+            pc->launches++;
+            CUDA_OK(cudaGetLastError());
+            return 0;
+        }
         const size_t smem = (size_t)c.pbytes + (size_t)c.n * sizeof(double);
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_apply_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ssc_apply_sym_kernel<<<(unsigned)cnt, threads, smem, pc->stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, gt, c.n, cnt,

@@ -841,6 +841,33 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// the two halves of y_i for the packed layout, four independent loads in flight each
+__device__ __forceinline__ double sym_row_pass(const double *__restrict__ L, const double *__restrict__ xs, int n, int i)
+{
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int cs = i, j = 0;                                   // L[i][j] sits at colstart(j) + (i - j); +(n - j - 1) per column
+    for (; j + 3 <= i; j += 4) {
+        const int c1 = cs + (n - j) - 1, c2 = c1 + (n - j) - 2, c3 = c2 + (n - j) - 3;
+        const double l0 = L[cs], l1 = L[c1], l2 = L[c2], l3 = L[c3];
+        a0 = fma(l0, xs[j], a0); a1 = fma(l1, xs[j + 1], a1); a2 = fma(l2, xs[j + 2], a2); a3 = fma(l3, xs[j + 3], a3);
+        cs = c3 + (n - j) - 4;
+    }
+    for (; j <= i; ++j) { a0 = fma(L[cs], xs[j], a0); cs += (n - j) - 1; }
+    return (a0 + a1) + (a2 + a3);
+}
+__device__ __forceinline__ double sym_col_pass(const double *__restrict__ L, const double *__restrict__ xs, int n, int i)
+{
+    const double *col = L + ((ll)i * n - (ll)i * (i - 1) / 2) - i;      // L[k][i] = col[k], k > i
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int kk = i + 1;
+    for (; kk + 3 < n; kk += 4) {
+        a0 = fma(col[kk], xs[kk], a0); a1 = fma(col[kk + 1], xs[kk + 1], a1);
+        a2 = fma(col[kk + 2], xs[kk + 2], a2); a3 = fma(col[kk + 3], xs[kk + 3], a3);
+    }
+    for (; kk < n; ++kk) a0 = fma(col[kk], xs[kk], a0);
+    return (a0 + a1) + (a2 + a3);
+}
+
 __global__ void ssc_pack_sym_kernel(const double *__restrict__ blocks, int n, int ld, ll stride, double *__restrict__ packed, ll pstride, ll count)
 {
     for (ll p = blockIdx.x; p < count; p += gridDim.x) {
@@ -878,25 +905,81 @@ ssc_apply_sym_kernel(const double *__restrict__ packed, ll pstride, unsigned cop
     __syncthreads();
     mbar_wait(&bar, 0);
     const double sc = mult ? scale * mult[p] : scale;
-    for (int i = t; i < n; i += blockDim.x) {
-        double a0 = 0.0, a1 = 0.0;
-        // row pass: L[i][j], j <= i, sits at colstart(j) + (i - j)
-        int cs = i;                                   // colstart(j) + i - j for j = 0
-        int j = 0;
-        for (; j + 1 <= i; j += 2) {
-            const double l0 = L[cs];
-            const int cs1 = cs + (n - j) - 1;
-            const double l1 = L[cs1];
-            a0 = fma(l0, xs[j], a0);
-            a1 = fma(l1, xs[j + 1], a1);
-            cs = cs1 + (n - j - 1) - 1;
+    for (int i = t; i < n; i += blockDim.x)
+        emit(y, g[i], (sym_row_pass(L, xs, n, i) + sym_col_pass(L, xs, n, i)) * sc, ps, ypatch, p * n + i);
+}
+
+// Persistent form of the packed-symmetric apply: one CTA per SM walks its share of the patches with a ring of kStages
+// shared-memory buffers.  Thread 0 keeps kStages - 1 bulk copies (one whole packed triangle each) in flight while the
+// CTA multiplies the patch that has landed; the residual entries of the next patch are gathered into registers before
+// the current patch is computed, so neither the gather nor the scatter latency stalls the stream.
+__global__ void __launch_bounds__(1024, 1)
+ssc_apply_sym_persistent_kernel(const double *__restrict__ packed, ll pstride, unsigned copy_bytes, int stages, const int *__restrict__ gtol, int n, ll count,
+                                const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
+                                const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar[8];
+    const size_t stage_doubles = copy_bytes >> 3;
+    double *ring = reinterpret_cast<double *>(smem_raw);
+    double *xsbuf = ring + stage_doubles * stages;            // 2 x n
+    double *ypart = xsbuf + 2 * n;                             // n
+    const int half = blockDim.x >> 1;
+    const bool split = half >= n;                              // two threads per row
+    const int t = threadIdx.x;
+    const ll first = blockIdx.x, step = gridDim.x;
+    const ll mine = first < count ? (count - first + step - 1) / step : 0;
+    if (t == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0) {
+        for (int s = 0; s < stages - 1 && s < mine; ++s) {
+            mbar_expect_tx(&bar[s], copy_bytes);
+            bulk_copy_g2s(ring + stage_doubles * s, packed + (first + s * step) * pstride, copy_bytes, &bar[s]);
         }
-        if (j <= i) a0 = fma(L[cs], xs[j], a0);
-        // column pass: L[k][i], k > i, sits at colstart(i) + (k - i)
-        const double *col = L + ((ll)i * n - (ll)i * (i - 1) / 2) - i;
-        int kk = i + 1;
-        for (; kk + 1 < n; kk += 2) { a0 = fma(col[kk], xs[kk], a0); a1 = fma(col[kk + 1], xs[kk + 1], a1); }
-        if (kk < n) a0 = fma(col[kk], xs[kk], a0);
-        emit(y, g[i], (a0 + a1) * sc, ps, ypatch, p * n + i);
+    }
+    // residual of the first patch
+    if (mine > 0) for (int i = t; i < n; i += blockDim.x) xsbuf[i] = __ldg(x + gtol[first * n + i]);
+    __syncthreads();
+    for (ll k = 0; k < mine; ++k) {
+        const ll p = first + k * step;
+        const int s = (int)(k % stages);
+        const unsigned parity = (unsigned)((k / stages) & 1);
+        // keep the ring full: the stage freed at the end of the previous iteration takes patch k + stages - 1
+        if (t == 0 && k + stages - 1 < mine) {
+            const int sn = (int)((k + stages - 1) % stages);
+            mbar_expect_tx(&bar[sn], copy_bytes);
+            bulk_copy_g2s(ring + stage_doubles * sn, packed + (p + (stages - 1) * step) * pstride, copy_bytes, &bar[sn]);
+        }
+        const double *xs = xsbuf + (k & 1) * n;
+        double *xn = xsbuf + ((k + 1) & 1) * n;
+        // gather for the next patch into a register (rows beyond blockDim are fetched after the compute, rare)
+        const int *gn = gtol + (p + step) * n;
+        double xnext = 0.0;
+        const bool have_next = k + 1 < mine;
+        if (have_next && t < n) xnext = __ldg(x + gn[t]);
+        const int *g = gtol + p * n;
+        const double *L = ring + stage_doubles * s;
+        mbar_wait(&bar[s], parity);
+        const double sc = mult ? scale * mult[p] : scale;
+        if (split) {
+            // first half of the CTA: row pass; second half: column pass, handed over through shared memory
+            const int i = t < half ? t : t - half;
+            double part = 0.0;
+            if (i < n) part = t < half ? sym_row_pass(L, xs, n, i) : sym_col_pass(L, xs, n, i);
+            if (t >= half && i < n) ypart[i] = part;
+            __syncthreads();
+            if (t < half && i < n) emit(y, g[i], (part + ypart[i]) * sc, ps, ypatch, p * n + i);
+        } else {
+            for (int i = t; i < n; i += blockDim.x)
+                emit(y, g[i], (sym_row_pass(L, xs, n, i) + sym_col_pass(L, xs, n, i)) * sc, ps, ypatch, p * n + i);
+        }
+        if (have_next) {
+            if (t < n) xn[t] = xnext;
+            for (int i = t + blockDim.x; i < n; i += blockDim.x) xn[i] = __ldg(x + gn[i]);
+        }
+        __syncthreads();          // stage s and xs are free again
     }
 }

@@ -335,3 +335,25 @@ def test_packed_symmetric_storage_needs_cholesky():
     with pytest.raises(SSCError) as e:
         pc.setUp()
     assert e.value.ierr == 75
+
+
+@pytest.mark.parametrize("persistent", [True, False])
+def test_packed_symmetric_persistent_ring(persistent):
+    """Enough patches of one size (> 8 per SM) to take the persistent ring-buffered form of the packed apply kernel."""
+    from ssc_b200 import synth
+    mesh = plex.TensorPlex((12, 12, 12))
+    V = fem.FunctionSpace(mesh, 2)
+    disc = fem.Discretisation([V])
+    import scipy.sparse as sp
+    r, c, v = synth.tensor_poisson_csr(V, disc.ghost_bc_nodes)
+    A = sp.csr_matrix((v, c, r), shape=(V.node_count,) * 2)
+    o = make_oracle(disc, A)
+    pc = make_gpu(disc, None, sub_pc_type="cholesky", ssc_symmetric_storage=True, ssc_symmetric_persistent=persistent)
+    pc._compute_op = None
+    pc.setOperatorCSR(r, c, v)
+    pc.setUp()
+    for seed in (1, 2, 3):
+        x = rhs_vector(disc.total_dofs, seed)
+        y = np.zeros_like(x)
+        pc.apply(x, y)
+        assert relerr(y, o.apply(x)) < TOL
