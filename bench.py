@@ -34,7 +34,7 @@ METRIC = "PCApply dofs/s (3D Q3 Poisson vertex-star patches, additive, fp64)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ssc_b200", choices=["ssc_b200", "reference"])
     ap.add_argument("--cells", type=int, default=64, help="hex cells per direction per GPU")
