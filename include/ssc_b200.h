@@ -130,6 +130,9 @@ int SSCPatchView(SSCPatchPC pc, char *buf, SSCInt len);
 int SSCPatchGetSize(SSCPatchPC pc, const char *what, SSCInt *value);
 /* run the host-side patch construction now (ssc/libssc.c:1219-1220); needs no device.  SetUp calls it if needed. */
 int SSCPatchBuildPatches(SSCPatchPC pc);
+/* -pc_patch_print_patches (ssc/libssc.c:674-730): owned / seen / global-BC / artificial-BC dofs of every patch, ascending;
+ * printed to stdout when the patches are built and available here as text (needed = length incl. the final 0) */
+int SSCPatchGetPrintout(SSCPatchPC pc, char *buf, SSCInt len, SSCInt *needed);
 /* copies of the host-side construction results (ssc/libssc.c:452-900); any pointer may be NULL */
 int SSCPatchGetPatches(SSCPatchPC pc, SSCInt *gtolOffsets, SSCInt *gtol);
 int SSCPatchGetCells(SSCPatchPC pc, SSCInt *cellOffsets, SSCInt *cells);

@@ -54,6 +54,7 @@ _sigs = {
     "SSCPatchView": [_H, C.c_char_p, C.c_int64],
     "SSCPatchGetSize": [_H, C.c_char_p, i64p],
     "SSCPatchBuildPatches": [_H],
+    "SSCPatchGetPrintout": [_H, C.c_char_p, C.c_int64, i64p],
     "SSCPatchGetPatches": [_H, i64p, i64p],
     "SSCPatchGetCells": [_H, i64p, i64p],
     "SSCPatchGetDofs": [_H, i64p],

@@ -38,6 +38,7 @@ struct BuildOptions {
     int construct_type = 0;                    // PC_PATCH_STAR
     i64 codim = -1, dim = -1, exclude_subspace = -1, vankadim = -1;
     bool keep_dofs = false;
+    bool print_patches = false;                // -pc_patch_print_patches, ssc/libssc.c:674-730
     int nthreads = 0;
 };
 
@@ -51,6 +52,7 @@ struct PatchLists {
     std::vector<i64> cellOff, cells;           // cellCounts / cells   (ssc/libssc.c:452-580, renumbered :887)
     std::vector<i64> gtolOff, gtol;            // gtolCounts / gtol    (ssc/libssc.c:779-837)
     std::vector<i64> dofs;                     // per-cell patch-local index table (:846-889), optional
+    std::string printout;                      // text of -pc_patch_print_patches
 };
 
 // Host-side restatement-free implementation of A1-A5 (see patch_builder.cpp)

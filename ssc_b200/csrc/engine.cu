@@ -389,7 +389,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
         return ssc_set_error(SSC_ERR_USER, "-pc_patch_vanka_space has been renamed to -pc_patch_exclude_subspace");
     if (name == "pc_patch_exclude_subspace") { pc->bopt.exclude_subspace = atoll(v); return 0; }
     if (name == "pc_patch_sub_mat_type") return SSCPatchSetSubMatType(pc, v);
-    if (name == "pc_patch_print_patches") return parse_bool(v, &pc->print_patches);
+    if (name == "pc_patch_print_patches") { CHK(parse_bool(v, &pc->print_patches)); pc->bopt.print_patches = pc->print_patches; pc->lists_valid = pc->lists_valid && !pc->print_patches; return 0; }
     if (name == "pc_patch_symmetrise_sweep") return parse_bool(v, &pc->symmetrise_sweep);
     if (name == "sub_ksp_type") {
         if (std::string(v) != "preonly") return ssc_set_error(SSC_ERR_SUP, "sub_ksp_type '%s' is not supported: patch problems are solved directly (preonly)", v);
@@ -595,14 +595,12 @@ static void choose_launch_shape(SizeClass &c, int variant)
     c.ppb = std::max(1, 192 / c.tp);
 }
 
+static int need_lists(PC *pc);
 // first-time part of PCSetUp_PATCH (ssc/libssc.c:1210-1250): dof lists -> size classes -> device arrays
 static int build_device_lists(PC *pc)
 {
     auto t0 = std::chrono::steady_clock::now();
-    if (!pc->lists_valid) {
-        CHK(ssc_build_patches(pc->plex, pc->disc, pc->user, pc->bopt, pc->lists));
-        pc->lists_valid = true;
-    }
+    CHK(need_lists(pc));
     pc->event_ms["PCPATCHCreate"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     const PatchLists &L = pc->lists;
     const i64 np = L.npatch;
@@ -1425,6 +1423,15 @@ static int need_lists(PC *pc)
     if (pc->lists_valid) return 0;
     CHK(ssc_build_patches(pc->plex, pc->disc, pc->user, pc->bopt, pc->lists));
     pc->lists_valid = true;
+    if (pc->print_patches) fputs(pc->lists.printout.c_str(), stdout);     // PetscSynchronizedPrintf of ssc/libssc.c:679-728
+    return 0;
+}
+// text of -pc_patch_print_patches (also written to stdout when the patches are built); returns the full length
+extern "C" int SSCPatchGetPrintout(SSCPatchPC pc, char *buf, SSCInt len, SSCInt *needed)
+{
+    CHK(need_lists(pc));
+    if (needed) *needed = (i64)pc->lists.printout.size() + 1;
+    if (buf && len > 0) { strncpy(buf, pc->lists.printout.c_str(), (size_t)len - 1); buf[len - 1] = 0; }
     return 0;
 }
 // host-only: build (if needed) the dof lists without touching the device

@@ -46,6 +46,7 @@ struct Scratch {
 
 struct Chunk {
     std::vector<i64> cellCount, gtolCount, cells, gtol, dofs;
+    std::string printout;
     int err = 0;
     std::string msg;
 };
@@ -138,6 +139,28 @@ struct Builder {
                 for (i64 p : s.owned) for_point_dofs(k, p, [&](i64 g) { s.dof[g].owned = stamp; });
             }
             for (i64 p : s.seen) for_point_dofs(k, p, [&](i64 g) { s.dof[g].seen = stamp; });
+        }
+        if (opt.print_patches) {
+            // ssc/libssc.c:674-730 (the reference prints in hash order; here every list ascends)
+            std::vector<i64> od, sd, gb, ab;
+            for (i64 k = 0; k < disc.nsub; ++k)
+                for (i64 p : s.seen) for_point_dofs(k, p, [&](i64 g) {
+                    sd.push_back(g);
+                    if (s.dof[g].owned == stamp) od.push_back(g);
+                    else ab.push_back(g);
+                    if (isGlobalBc[g]) gb.push_back(g);
+                });
+            for (i64 k = 0; k < disc.nsub; ++k)        // owned dofs on points outside the seen set (cannot happen for star patches)
+                for (i64 p : s.owned) if (s.ptSeen[p] != stamp2) for_point_dofs(k, p, [&](i64 g) { od.push_back(g); });
+            auto line = [&](const char *title, std::vector<i64> &v_) {
+                std::sort(v_.begin(), v_.end());
+                v_.erase(std::unique(v_.begin(), v_.end()), v_.end());
+                out.printout += "Patch " + std::to_string(v) + ": " + title + ":\n";
+                for (i64 g : v_) out.printout += std::to_string(g) + " ";
+                out.printout += "\n";
+            };
+            line("owned dofs", od); line("seen dofs", sd); line("global BCs", gb); line("artificial BCs", ab);
+            out.printout += "\n";
         }
         // first-encounter numbering, ssc/libssc.c:731-778
         size_t g0 = out.gtol.size(), d0 = out.dofs.size();
@@ -244,6 +267,8 @@ int ssc_build_patches(const HostPlex &plex, const Discretisation &disc, const Us
         }
         ncells += (i64)c.cells.size(); ngtol += (i64)c.gtol.size(); ndofs += (i64)c.dofs.size();
     }
+    out.printout.clear();
+    for (auto &c : chunks) out.printout += c.printout;
     out.cells.resize(ncells); out.gtol.resize(ngtol); out.dofs.resize(ndofs);
     // every chunk copies itself to its place (in parallel when there are several)
     std::vector<i64> ca(chunks.size() + 1, 0), ga(chunks.size() + 1, 0), da(chunks.size() + 1, 0);

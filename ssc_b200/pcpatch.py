@@ -297,6 +297,13 @@ class PC(object):
     def buildPatches(self):
         CHKERR(lib.SSCPatchBuildPatches(self.handle))
 
+    def getPrintout(self):
+        n = C.c_int64(0)
+        CHKERR(lib.SSCPatchGetPrintout(self.handle, None, C.c_int64(0), C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        CHKERR(lib.SSCPatchGetPrintout(self.handle, buf, n, None))
+        return buf.value.decode()
+
     def getPatches(self):
         self.buildPatches()
         off = np.zeros(self.size("npatch") + 1, dtype=np.int64)

@@ -93,3 +93,28 @@ def test_user_patches_through_the_python_hook():
     pc.setFromOptions()
     pl.Options.clear()
     assert all(np.array_equal(a, b) for a, b in zip(star.patches(), pc.getPatches()))
+
+
+def test_print_patches(capfd):
+    """-pc_patch_print_patches (ssc/libssc.c:674-730): owned = patch dofs + their Dirichlet dofs, artificial = seen \\ owned."""
+    mesh = plex.RectangleMesh(3, 3, 1, 1)
+    form, bcs = fem.poisson_problem(mesh, 2, "scalar")
+    disc = fem.discretisation_from_form(form, bcs)
+    pc = PC(device=-1)
+    setup_patch_pc(pc, form, bcs)
+    pc.setOption("pc_patch_print_patches", True)
+    off, gtol = pc.getPatches()
+    text = pc.getPrintout()
+    assert capfd.readouterr().out == text
+    vs, ve = mesh.depth_stratum(0)
+    blocks = [b for b in text.split("\n\n") if b.strip()]
+    assert len(blocks) == ve - vs
+    for i, b in enumerate(blocks):
+        lines = b.strip().split("\n")
+        assert lines[0] == "Patch %d: owned dofs:" % (vs + i) and lines[2].endswith("seen dofs:")
+        owned = set(map(int, lines[1].split()))
+        seen = set(map(int, lines[3].split()))
+        gbc = set(map(int, lines[5].split())) if lines[5].strip() else set()
+        art = set(map(int, lines[7].split())) if len(lines) > 7 and lines[7].strip() else set()
+        assert art == seen - owned and gbc == seen & set(disc.ghost_bc_nodes.tolist())
+        assert set(gtol[off[i]:off[i + 1]].tolist()) == owned - gbc
