@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--impl", default="ssc_b200", choices=["ssc_b200", "reference"])
     ap.add_argument("--cells", type=int, default=64, help="hex cells per direction per GPU")
     ap.add_argument("--degree", type=int, default=3)
+    ap.add_argument("--workload", default="poisson_hex", choices=["poisson_hex", "elasticity_tets"],
+                    help="poisson_hex = BASELINE.json configs[2] (default); elasticity_tets = configs[3]: vector P2 linear elasticity on a Freudenthal tet mesh (N=1 only)")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="patches in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -105,6 +107,13 @@ def build_problem(args, rank, nranks):
     from ssc_b200 import partition
     t0 = time.time()
     c, p = args.cells, args.degree
+    if args.workload == "elasticity_tets":
+        if nranks != 1:
+            raise SystemExit("elasticity_tets is a single-GPU workload")
+        mesh = plex.BoxMesh(c, c, c)
+        V = fem.FunctionSpace(mesh, 2, 3)
+        disc = fem.Discretisation([V])
+        return V, disc, None, {"t_mesh": time.time() - t0}
     if nranks == 1:
         mesh = plex.TensorPlex((c, c, c))
         V = fem.FunctionSpace(mesh, p)
@@ -119,6 +128,11 @@ def build_problem(args, rank, nranks):
 
 def operator_csr(V, disc):
     from ssc_b200 import synth
+    if V.mesh.cell_type == "simplex":
+        from ssc_b200 import fem
+        A, _ = fem.assemble_elasticity_simplex(V)
+        A = fem.apply_bcs(A, disc.ghost_bc_nodes)
+        return A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data
     synth.set_threads(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))   # torchrun pins OMP_NUM_THREADS=1
     return synth.tensor_poisson_csr(V, disc.ghost_bc_nodes)
 
@@ -186,6 +200,10 @@ def run_reference(args, rank, nranks):
 
 def workload_config(args, nranks):
     c, p = args.cells, args.degree
+    if args.workload == "elasticity_tets":
+        return {"workload": "3D linear elasticity, vector P2 on %dx%dx%d cubes split into tets, vertex-star patches (n = 45 interior), additive" % (c, c, c),
+                "cells_per_gpu": 6 * c ** 3, "degree": 2, "parallelism": "single GPU", "exchange": None,
+                "l2": "L2 flushed between timed steps" }
     return {"workload": "3D Q%d Poisson, %dx%dx%d hex cells%s, vertex-star patches, additive, stored inverse (sub_pc_type lu)"
                         % (p, c, c, c * nranks, " (z-slabs of %d^3 per GPU)" % c if nranks > 1 else ""),
             "cells_per_gpu": c ** 3, "degree": p, "parallelism": "patches by mesh slab x%d" % nranks, "exchange": getattr(args, "exchange_used", None),
@@ -294,10 +312,20 @@ def main():
     pc.kernelTimerReset(True)
     barrier()
     pc.eventRecord(e0)
-    for _ in range(args.steps):
-        pc.apply(dx, dy)
-    pc.eventRecord(e1)
-    ms = pc.eventElapsed(e0, e1)
+    flush = args.workload != "poisson_hex" or pc.size("block_bytes") < (1 << 30)     # small working sets: flush L2 between steps
+    if flush:
+        ms = 0.0
+        for _ in range(args.steps):
+            pc.flushL2()
+            pc.eventRecord(e0)
+            pc.apply(dx, dy)
+            pc.eventRecord(e1)
+            ms += pc.eventElapsed(e0, e1)
+    else:
+        for _ in range(args.steps):
+            pc.apply(dx, dy)
+        pc.eventRecord(e1)
+        ms = pc.eventElapsed(e0, e1)
     barrier()
     kms, kn = pc.kernelTimerRead()
     pc.kernelTimerReset(False)
@@ -342,12 +370,14 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "ssc_apply_kernel (all size classes of one apply)", "kernel_ms": kernel_ms,
                 "algorithmic_bytes": bytes_apply, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
-    out = {"metric": METRIC, "value": nglobal / (ms_step * 1e-3), "unit": "dofs/s", "n_gpus": nranks, "steps": args.steps,
+    out = {"metric": METRIC if args.workload == "poisson_hex" else "PCApply dofs/s (3D vector P2 elasticity on tets, vertex-star patches, additive, fp64)", "value": nglobal / (ms_step * 1e-3), "unit": "dofs/s", "n_gpus": nranks, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(args, nranks),
            "dofs": nglobal, "patches_per_gpu": pc.size("npatch"), "hbm_gbs_step": bytes_apply * nranks / (ms_step * 1e-3) / 1e9,
            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "setup": setup}
-    if nranks == 1 and not args.no_spd_packed:
+    if flush:
+        out["config"]["l2"] = "working set %.2f GB: L2 flushed (256 MB write) before every timed step, each step timed on its own" % (pc.size("block_bytes") / 1e9)
+    if nranks == 1 and not args.no_spd_packed and args.workload == "poisson_hex":
         try:
             out["spd_packed"] = spd_packed_line(args, disc, csr, dx, dy, peak)
         except Exception as exc:                     # an extra, never allowed to take the main line down
