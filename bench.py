@@ -137,7 +137,7 @@ def operator_csr(V, disc):
     return synth.tensor_poisson_csr(V, disc.ghost_bc_nodes)
 
 
-def cpu_baseline(V, disc, csr, args, nthreads=None):
+def cpu_baseline(V, disc, csr, args, nthreads=None, x=None, y_gpu=None):
     """The oracle's PCApply loop (gather, LU solve with precomputed factors, scatter-add) on a contiguous sample of the
     workload's patches, all host threads; scaled to the whole vector by sum(n^2) (the loop is bound by streaming factors)."""
     from oracle import oracle
@@ -156,8 +156,18 @@ def cpu_baseline(V, disc, csr, args, nthreads=None):
     o.setPatches(soff, gtol[off[lo]:off[lo + S]], disc.total_dofs)
     o.setOperatorCSRArrays(*csr)
     o.setUpOperators(nthreads=nthreads)
-    x = np.random.default_rng(20260101).uniform(-1, 1, disc.total_dofs)
-    o.applyLocal(x, nthreads=nthreads)         # warm-up
+    if x is None:
+        x = np.random.default_rng(20260101).uniform(-1, 1, disc.total_dofs)
+    yo = o.applyLocal(x, nthreads=nthreads)    # warm-up; also the parity sample below
+    parity = None
+    if y_gpu is not None:
+        # dofs all of whose patches are inside the sample: there the oracle's partial sum is the complete PCApply value
+        mult_all = np.bincount(gtol, minlength=disc.total_dofs)
+        part = np.bincount(gtol[off[lo]:off[lo + S]], minlength=disc.total_dofs)
+        sel = np.nonzero((part > 0) & (part == mult_all))[0]
+        if sel.size:
+            err = float(np.abs(y_gpu[sel] - yo[sel]).max() / np.abs(yo[sel]).max())
+            parity = {"dofs_checked": int(sel.size), "max_rel_err_vs_oracle": err, "ok": bool(err < 1e-12)}
     reps, t = 0, 0.0
     while t < 10.0 and reps < 20:
         t0 = time.perf_counter()
@@ -170,7 +180,7 @@ def cpu_baseline(V, disc, csr, args, nthreads=None):
     return {"value": disc.total_dofs / full, "unit": "dofs/s", "cores": int(nthreads), "kind": "port",
             "sample": "%d contiguous mid-mesh patches of %d (%.2f%% of sum n^2), %d applies, scaled by sum n^2; CPU restatement of libssc PCApply (oracle/ssc_oracle.c), factors precomputed"
                       % (S, np_all, 100 * frac, reps),
-            "ms_per_step_full_estimate": full * 1e3}
+            "ms_per_step_full_estimate": full * 1e3, "parity": parity}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -383,7 +393,11 @@ def main():
         except Exception as exc:                     # an extra, never allowed to take the main line down
             out["spd_packed"] = {"error": str(exc)}
     if nranks == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(V, disc, csr, args)
+        pc.apply(dx, dy)
+        pc.synchronize()
+        out["cpu_baseline"] = cpu_baseline(V, disc, csr, args, x=np.array(xh.array), y_gpu=dy.get())
+        if out["cpu_baseline"]["parity"] and not out["cpu_baseline"]["parity"]["ok"]:
+            raise SystemExit("PCApply differs from the CPU oracle on the sampled dofs: %r" % (out["cpu_baseline"]["parity"],))
     print(json.dumps(out))
 
 

@@ -141,6 +141,9 @@ int SSCPatchGetDofs(SSCPatchPC pc, SSCInt *dofs);         /* only if option "ssc
 int SSCPatchGetPatchMatrix(SSCPatchPC pc, SSCInt p, int which, double *out);
 /* colour of every patch (-1 for empty ones) after SetUp with -pc_patch_multiplicative (N4: no reference counterpart) */
 int SSCPatchGetColours(SSCPatchPC pc, SSCInt *colours);
+/* patches whose operator could not be factorised at the last SetUp (the reference would surface
+ * KSP_DIVERGED_PCSETUP_FAILED per sub-KSP, dead code at ssc/libssc.c:1437-1443) */
+int SSCPatchGetFailedPatches(SSCPatchPC pc, SSCInt *list, SSCInt maxn, SSCInt *nfailed);
 /* dof weights of ssc/libssc.c:1254-1284 (nowned values, host) */
 int SSCPatchGetDofWeights(SSCPatchPC pc, double *w);
 /* device time in ms of the last completed stage, named as the reference's log events (ssc/libssc.c:19-24):

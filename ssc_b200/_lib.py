@@ -60,6 +60,7 @@ _sigs = {
     "SSCPatchGetDofs": [_H, i64p],
     "SSCPatchGetPatchMatrix": [_H, C.c_int64, C.c_int, f64p],
     "SSCPatchGetDofWeights": [_H, f64p],
+    "SSCPatchGetFailedPatches": [_H, i64p, C.c_int64, i64p],
     "SSCPatchGetColours": [_H, i64p],
     "SSCPatchGetEventTime": [_H, C.c_char_p, f64p],
     "SSCPatchKernelTimerReset": [_H, C.c_int],

@@ -155,6 +155,7 @@ struct SSCPatchPC_s {
     double *d_r = nullptr;
     bool deterministic = false;      // slot-and-sum instead of atomics
     bool symmetric = false;          // packed lower triangle of the (symmetric) inverse only
+    bool sym_bulk = true;            // packed apply: TMA bulk copy (true, 3.24 ms at 64^3 Q3) or per-thread cp.async (false, 4.46 ms)
     bool sym_persistent = false;     // persistent ring-buffered form of the packed apply kernel (measured slower: profiles/README.md)
     double *d_packed = nullptr;
     i64 packed_elems = 0;
@@ -166,6 +167,7 @@ struct SSCPatchPC_s {
     i64 block_elems = 0, sum_n = 0, sum_n2 = 0, max_n = 0;
     int *d_fail = nullptr;
     i64 failed = 0;
+    std::vector<i64> failed_list;
     int *d_bc = nullptr;
     i64 nbc = 0;
     double *d_w = nullptr, *d_mult = nullptr;
@@ -181,6 +183,7 @@ struct SSCPatchPC_s {
     void *d_flush = nullptr;
     void *stage[3] = {nullptr, nullptr, nullptr};      // pinned staging ring for large pageable uploads
     cudaEvent_t stage_ev[3] = {nullptr, nullptr, nullptr};
+    bool stage_busy[3] = {false, false, false};
     // pipelined host-space apply: H2D of x, patch kernels and D2H of y overlap slab by slab
     int pipe_slabs = 8;
     bool pipe_force = false;
@@ -415,6 +418,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
         return 0;
     }
     if (name == "ssc_symmetric_persistent") return parse_bool(v, &pc->sym_persistent);
+    if (name == "ssc_symmetric_bulk_copy") return parse_bool(v, &pc->sym_bulk);
     if (name == "ssc_deterministic") {
         bool f = false;
         CHK(parse_bool(v, &f));
@@ -918,7 +922,7 @@ static int staged_upload(PC *pc, void *dst, const void *src, size_t bytes)
     for (int it = 0; off < bytes; ++it) {
         const int r = it % R;
         const size_t len = std::min(chunk, bytes - off);
-        if (it >= R) CUDA_OK(cudaEventSynchronize(pc->stage_ev[r]));
+        if (pc->stage_busy[r]) CUDA_OK(cudaEventSynchronize(pc->stage_ev[r]));   // also across calls: the previous array's tail may still be in flight
         std::vector<std::thread> th;
         for (int t = 0; t < T; ++t) {
             const size_t a = len * t / T, b = len * (t + 1) / T;
@@ -927,6 +931,7 @@ static int staged_upload(PC *pc, void *dst, const void *src, size_t bytes)
         for (auto &x : th) x.join();
         CUDA_OK(cudaMemcpyAsync((char *)dst + off, pc->stage[r], len, cudaMemcpyHostToDevice, pc->stream));
         CUDA_OK(cudaEventRecord(pc->stage_ev[r], pc->stream));
+        pc->stage_busy[r] = true;
         off += len;
     }
     return 0;
@@ -1087,7 +1092,8 @@ extern "C" int SSCPatchSetUp(SSCPatchPC pc)
         if (!fail.empty()) CUDA_OK(cudaMemcpy(fail.data(), pc->d_fail, fail.size() * sizeof(int), cudaMemcpyDeviceToHost));
         pc->failed = 0;
         i64 firstbad = -1;
-        for (size_t q = 0; q < fail.size(); ++q) if (fail[q]) { if (firstbad < 0) firstbad = pc->sorted2orig[q]; pc->failed++; }
+        pc->failed_list.clear();
+        for (size_t q = 0; q < fail.size(); ++q) if (fail[q]) { if (firstbad < 0) firstbad = pc->sorted2orig[q]; pc->failed++; pc->failed_list.push_back(pc->sorted2orig[q]); }
         if (pc->csr_owned && !pc->multiplicative) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); pc->csr_owned = false; }
         if (pc->failed) return ssc_set_error(SSC_ERR_MAT_LU_ZRPVT, "%lld patch operators could not be factorised (first: patch %lld)%s", (long long)pc->failed,
                                              (long long)firstbad, pc->sub_pc == SSC_SUB_CHOLESKY ? "; sub_pc_type cholesky needs SPD blocks" : "");
@@ -1113,10 +1119,12 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
     if (pc->symmetric && !blocks_override) {
         const int threads = std::min(1024, (c.n + 31) / 32 * 32);
         const i64 per_cta = cnt / std::max(1, pc->sm_count);
-        int stages = (int)std::min<size_t>(4, ((size_t)220 * 1024 - 3 * (size_t)c.n * 8) / std::max<size_t>(c.pbytes, 16));
+        int stages = (int)std::min<size_t>(4, ((size_t)220 * 1024 - 5 * (size_t)(c.n + 32) * 8) / std::max<size_t>(c.pbytes, 16));
         if (pc->sym_persistent && stages >= 2 && per_cta >= 8) {
-            const size_t smem_p = (size_t)stages * c.pbytes + 3 * (size_t)c.n * sizeof(double);
-            const int threads_p = c.n <= 512 ? 2 * ((c.n + 31) / 32 * 32) : threads;
+            const int rp = (c.n + 31) / 32 * 32;
+            const int Fp = std::max(1, std::min(4, 1024 / rp));
+            const int threads_p = rp * Fp;
+            const size_t smem_p = (size_t)stages * c.pbytes + (2 * (size_t)c.n + (size_t)(Fp - 1) * rp) * sizeof(double);
             CUDA_OK(cudaFuncSetAttribute(ssc_apply_sym_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
             ssc_apply_sym_persistent_kernel<<<pc->sm_count, threads_p, smem_p, pc->stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, stages, gt,
                                                                                         c.n, cnt, xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch);
@@ -1125,8 +1133,16 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
             return 0;
         }
         const size_t smem = (size_t)c.pbytes + (size_t)c.n * sizeof(double);
-        if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_apply_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ssc_apply_sym_kernel<<<(unsigned)cnt, threads, smem, pc->stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, gt, c.n, cnt,
+        if (pc->sym_bulk) {
+            if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_apply_sym_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ssc_apply_sym_kernel<true><<<(unsigned)cnt, threads, smem, pc->stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, gt, c.n, cnt,
+                                                                                  xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch);
+            pc->launches++;
+            CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+        if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_apply_sym_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ssc_apply_sym_kernel<false><<<(unsigned)cnt, threads, smem, pc->stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, gt, c.n, cnt,
                                                                         xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch);
         pc->launches++;
         CUDA_OK(cudaGetLastError());
@@ -1499,6 +1515,14 @@ extern "C" int SSCPatchGetColours(SSCPatchPC pc, SSCInt *colours)
 {
     if (!pc->multiplicative || pc->colour.empty()) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "colours exist after SetUp in multiplicative mode");
     std::copy(pc->colour.begin(), pc->colour.end(), colours);
+    return 0;
+}
+
+// original numbers of the patches whose operator could not be factorised at the last SetUp (at most maxn are written)
+extern "C" int SSCPatchGetFailedPatches(SSCPatchPC pc, SSCInt *list, SSCInt maxn, SSCInt *nfailed)
+{
+    if (nfailed) *nfailed = (i64)pc->failed_list.size();
+    for (i64 i = 0; i < maxn && i < (i64)pc->failed_list.size(); ++i) list[i] = pc->failed_list[(size_t)i];
     return 0;
 }
 

@@ -880,6 +880,9 @@ __global__ void ssc_pack_sym_kernel(const double *__restrict__ blocks, int n, in
     }
 }
 
+// kBulk = true: one TMA bulk copy per patch (UBLKCP + mbarrier), the default.  kBulk = false: every thread issues 16-byte
+// cp.async copies (LDGSTS) -- measured slower on B200 (4.46 ms against 3.24 ms at 64^3 Q3, profiles/README.md).
+template <bool kBulk>
 __global__ void __launch_bounds__(1024)
 ssc_apply_sym_kernel(const double *__restrict__ packed, ll pstride, unsigned copy_bytes, const int *__restrict__ gtol, int n, ll count,
                      const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
@@ -891,19 +894,28 @@ ssc_apply_sym_kernel(const double *__restrict__ packed, ll pstride, unsigned cop
     __shared__ __align__(8) unsigned long long bar;
     const ll p = blockIdx.x;
     const int t = threadIdx.x;
-    if (t == 0) {
-        mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (t == 0) {
-        mbar_expect_tx(&bar, copy_bytes);
-        bulk_copy_g2s(L, packed + p * pstride, copy_bytes, &bar);
+    if (kBulk) {
+        if (t == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (t == 0) {
+            mbar_expect_tx(&bar, copy_bytes);
+            bulk_copy_g2s(L, packed + p * pstride, copy_bytes, &bar);
+        }
+    } else {
+        const char *src = reinterpret_cast<const char *>(packed + p * pstride);
+        const unsigned dst = smem_u32(L);
+        for (unsigned off = 16u * t; off < copy_bytes; off += 16u * blockDim.x)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     const int *g = gtol + p * n;
     for (int i = t; i < n; i += blockDim.x) xs[i] = __ldg(x + g[i]);
+    if (!kBulk) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    mbar_wait(&bar, 0);
+    if (kBulk) mbar_wait(&bar, 0);
     const double sc = mult ? scale * mult[p] : scale;
     for (int i = t; i < n; i += blockDim.x)
         emit(y, g[i], (sym_row_pass(L, xs, n, i) + sym_col_pass(L, xs, n, i)) * sc, ps, ypatch, p * n + i);
@@ -923,9 +935,9 @@ ssc_apply_sym_persistent_kernel(const double *__restrict__ packed, ll pstride, u
     const size_t stage_doubles = copy_bytes >> 3;
     double *ring = reinterpret_cast<double *>(smem_raw);
     double *xsbuf = ring + stage_doubles * stages;            // 2 x n
-    double *ypart = xsbuf + 2 * n;                             // n
-    const int half = blockDim.x >> 1;
-    const bool split = half >= n;                              // two threads per row
+    double *ypart = xsbuf + 2 * n;                             // (F - 1) x rp partial sums
+    const int rp = (n + 31) & ~31;                             // row slots per part
+    const int F = max(1, (int)blockDim.x / rp);                // threads per row
     const int t = threadIdx.x;
     const ll first = blockIdx.x, step = gridDim.x;
     const ll mine = first < count ? (count - first + step - 1) / step : 0;
@@ -964,17 +976,30 @@ ssc_apply_sym_persistent_kernel(const double *__restrict__ packed, ll pstride, u
         const double *L = ring + stage_doubles * s;
         mbar_wait(&bar[s], parity);
         const double sc = mult ? scale * mult[p] : scale;
-        if (split) {
-            // first half of the CTA: row pass; second half: column pass, handed over through shared memory
-            const int i = t < half ? t : t - half;
-            double part = 0.0;
-            if (i < n) part = t < half ? sym_row_pass(L, xs, n, i) : sym_col_pass(L, xs, n, i);
-            if (t >= half && i < n) ypart[i] = part;
+        {
+            // F threads per row; thread (i, q) adds the terms m = q, q + F, ... of
+            //   y_i = sum_m L[colstart(min(i, m)) + |i - m|] x_m        (the symmetric product on the packed triangle)
+            const int i = t % rp, q = t / rp;
+            double a0 = 0.0, a1 = 0.0;
+            if (i < n && q < F) {
+                const int ci = i * n - ((i * (i - 1)) >> 1) - i;          // colstart(i) - i
+                int m = q;
+                for (; m + F < n; m += 2 * F) {
+                    const int m1 = m + F;
+                    const int i0 = m <= i ? m * n - ((m * (m - 1)) >> 1) + (i - m) : ci + m;
+                    const int i1 = m1 <= i ? m1 * n - ((m1 * (m1 - 1)) >> 1) + (i - m1) : ci + m1;
+                    a0 = fma(L[i0], xs[m], a0);
+                    a1 = fma(L[i1], xs[m1], a1);
+                }
+                if (m < n) { const int i0 = m <= i ? m * n - ((m * (m - 1)) >> 1) + (i - m) : ci + m; a0 = fma(L[i0], xs[m], a0); }
+                if (q > 0) ypart[(q - 1) * rp + i] = a0 + a1;
+            }
             __syncthreads();
-            if (t < half && i < n) emit(y, g[i], (part + ypart[i]) * sc, ps, ypatch, p * n + i);
-        } else {
-            for (int i = t; i < n; i += blockDim.x)
-                emit(y, g[i], (sym_row_pass(L, xs, n, i) + sym_col_pass(L, xs, n, i)) * sc, ps, ypatch, p * n + i);
+            if (i < n && q == 0) {
+                double s = a0 + a1;
+                for (int qq = 1; qq < F; ++qq) s += ypart[(qq - 1) * rp + i];
+                emit(y, g[i], s * sc, ps, ypatch, p * n + i);
+            }
         }
         if (have_next) {
             if (t < n) xn[t] = xnext;
