@@ -359,8 +359,31 @@ def main():
         e2e = {"value": nglobal / (ems * 1e-3), "unit": "dofs/s", "h2d_bytes_per_step": 8 * nowned, "d2h_bytes_per_step": 8 * nowned,
                "ms_per_step": ems, "api": "ssc_b200.PC.apply(x, y) on pinned host vectors (SSCPatchApply, SSC_MEM_HOST)"}
 
+    # size-independent property at full size (all N): the additive operator is symmetric for an SPD problem, so
+    # <M a, b> == <a, M b> over the whole (distributed) vector; a broken halo fill or overlap sum breaks it
+    rng2 = np.random.default_rng(777 + rank)
+    a_h, b_h = rng2.uniform(-1, 1, nowned), rng2.uniform(-1, 1, nowned)
+    da, db, dMa, dMb = (DeviceVec(pc, nowned) for _ in range(4))
+    da.set(a_h)
+    db.set(b_h)
+    pc.apply(da, dMa)
+    pc.apply(db, dMb)
+    pc.synchronize()
+    Ma, Mb = dMa.get(), dMb.get()
+    bc = disc.global_bc_nodes
+    free = np.ones(nowned, dtype=bool)
+    free[bc[bc < nowned]] = False                      # Dirichlet rows are passed through, not part of the symmetric operator
+    dots = np.array([float(Ma[free] @ b_h[free]), float(a_h[free] @ Mb[free])])
+    if dist is not None:
+        parts = _allgather(dist, dots, nranks)
+        dots = np.sum(parts, axis=0)
+    symmetry = {"<Ma,b>": float(dots[0]), "<a,Mb>": float(dots[1]), "rel_diff": float(abs(dots[0] - dots[1]) / max(abs(dots[0]), 1e-300))}
+    for v in (da, db, dMa, dMb):
+        v.free()
     if rank != 0:
         return
+    if symmetry["rel_diff"] > 1e-10:
+        raise SystemExit("symmetry check failed: %r" % (symmetry,))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -384,7 +407,7 @@ def main():
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(args, nranks),
            "dofs": nglobal, "patches_per_gpu": pc.size("npatch"), "hbm_gbs_step": bytes_apply * nranks / (ms_step * 1e-3) / 1e9,
-           "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "setup": setup}
+           "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "setup": setup, "symmetry_check": symmetry}
     if flush:
         out["config"]["l2"] = "working set %.2f GB: L2 flushed (256 MB write) before every timed step, each step timed on its own" % (pc.size("block_bytes") / 1e9)
     if nranks == 1 and not args.no_spd_packed and args.workload == "poisson_hex":
