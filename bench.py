@@ -286,7 +286,7 @@ def main():
     pc.synchronize()
     info["t_setup_wall"] = time.time() - t0
     if nranks > 1:
-        pc._csr_keep = None          # the CSR was only borrowed until SetUp returned; N=1 keeps it for the CPU baseline
+        pc.releaseOperator()         # the CSR was only borrowed until SetUp returned; N=1 keeps it for the CPU baseline
         csr = None
     setup = {"note": "setup_wall_s = SSCPatchSetUp with the CSR in pageable host memory: patch construction on the host, H2D of dof lists and CSR, extract, factor", "create_patches_ms": pc.eventTime("PCPATCHCreate"), "extract_ms": pc.eventTime("PCPATCHComputeOp"),
              "factor_ms": pc.eventTime("PCPATCHSolve"), "setup_wall_s": info["t_setup_wall"],

@@ -32,7 +32,24 @@ def build(force=False, verbose=False):
     if os.path.exists(ssrc) and (force or _stale(SYNTH, [ssrc])):
         subprocess.check_call(["/usr/bin/g++", "-O3", "-march=x86-64-v3", "-std=c++17", "-fopenmp", "-shared", "-fPIC",
                                "-o", SYNTH, ssrc])
+    build_cython(force)
     return LIB
+
+
+def build_cython(force=False):
+    """ssc_b200/PatchPC.pyx -> ssc_b200/PatchPC.<abi>.so, linked against libssc_b200.so through $ORIGIN."""
+    import sysconfig
+    import numpy
+    pyx = os.path.join(HERE, "PatchPC.pyx")
+    ext = os.path.join(HERE, "PatchPC" + sysconfig.get_config_var("EXT_SUFFIX"))
+    if not (force or _stale(ext, [pyx, os.path.join(HERE, "..", "include", "ssc_b200.h"), LIB])):
+        return ext
+    csrc = os.path.join(HERE, "csrc", "PatchPC_cython.c")
+    subprocess.check_call([sys.executable, "-m", "cython", "-3", pyx, "-o", csrc])
+    subprocess.check_call(["/usr/bin/gcc", "-O2", "-shared", "-fPIC", "-fno-strict-aliasing", "-DNPY_NO_DEPRECATED_API=NPY_1_7_API_VERSION",
+                           "-I", sysconfig.get_paths()["include"], "-I", numpy.get_include(), "-I", os.path.join(HERE, "..", "include"),
+                           csrc, "-o", ext, "-L", HERE, "-l:libssc_b200.so", "-Wl,-rpath,$ORIGIN"])
+    return ext
 
 
 if __name__ == "__main__":

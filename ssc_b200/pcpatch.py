@@ -12,6 +12,8 @@ import numpy as np
 
 from . import _lib
 from ._lib import CHKERR, MEM_DEVICE, MEM_HOST, as_i64, dp, i64p, ip, lib
+from . import PatchPC as cPatchPC      # the Cython shim (the package later rebinds this name to the python class,
+                                       # exactly like ssc/patch.py:12 + ssc/__init__.py:2 in the reference)
 
 # option names of PCSetFromOptions_PATCH (ssc/libssc.c:1551-1620) and of the per-patch KSP prefix "sub_" (:1240-1241)
 PATCH_OPTIONS = ("pc_patch_save_operators", "pc_patch_partition_of_unity", "pc_patch_multiplicative",
@@ -76,9 +78,8 @@ def _host_array(v):
 
 class PC(object):
     def __init__(self, device=0, comm=None):
-        self.handle = C.c_void_p()
-        CHKERR(lib.SSCPatchInitializePackage())
-        CHKERR(lib.SSCPatchCreate(int(device), C.byref(self.handle)))
+        self._core = cPatchPC.PC(int(device))          # owns the SSCPatchPC handle
+        self.handle = C.c_void_p(self._core.handle)    # same pointer, for the ctypes introspection calls
         self.device = device
         self.comm = comm
         self.prefix = ""
@@ -92,7 +93,7 @@ class PC(object):
     # ---- lifetime -------------------------------------------------------------------------
     def destroy(self):
         if self.handle:
-            lib.SSCPatchDestroy(C.byref(self.handle))
+            self._core.destroy()
             self.handle = C.c_void_p()
 
     def __del__(self):
@@ -136,8 +137,7 @@ class PC(object):
             plex = Plex.from_dmplex(plex)
         arrs = [as_i64(a) for a in (plex.cone_off, plex.cones, plex.depth_start, plex.depth_end)]
         ghost = np.ascontiguousarray(plex.ghost, dtype=np.uint8)
-        CHKERR(lib.SSCPatchSetPlex(self.handle, C.c_int64(plex.dim), C.c_int64(plex.pEnd), ip(arrs[0]), ip(arrs[1]),
-                                   ip(arrs[2]), ip(arrs[3]), ghost.ctypes.data_as(C.c_void_p)))
+        self._core.setPlex(plex.dim, arrs[0], arrs[1], arrs[2], arrs[3], ghost)
         self.plex = plex
 
     def getDM(self):
@@ -157,7 +157,7 @@ class PC(object):
     def setOption(self, name, value):
         if isinstance(value, bool):
             value = "true" if value else "false"
-        CHKERR(lib.SSCPatchSetOption(self.handle, name.encode(), str(value).encode()))
+        self._core.setOption(name, value)
 
     def setFromOptions(self):
         """PCSetFromOptions_PATCH (ssc/libssc.c:1551-1620): read every known name under this PC's prefix."""
@@ -179,23 +179,15 @@ class PC(object):
     # ---- ssc/PatchPC.pyx:110-170 -----------------------------------------------------------
     def setPatchCellNumbering(self, sec):
         dof, off = (as_i64(sec[0]), as_i64(sec[1])) if isinstance(sec, tuple) else _section_arrays(sec, self.plex.pEnd)
-        CHKERR(lib.SSCPatchSetCellNumbering(self.handle, ip(dof), ip(off)))
+        self._core.setPatchCellNumbering(dof, off)
 
     def setPatchDiscretisationInfo(self, dms, bs, cellNodeMaps, subspaceOffsets, ghostBcNodes, globalBcNodes):
         """``dms[i]`` is the (dof, offset) pair of the default section of subspace i (or a petsc4py DM)."""
         n = len(dms)
         secs = [(as_i64(d[0]), as_i64(d[1])) if isinstance(d, tuple) else _section_arrays(d.getDefaultSection(), self.plex.pEnd)
                 for d in dms]
-        cnm = [as_i64(m) for m in cellNodeMaps]
-        bs = as_i64(bs)
-        npc = as_i64([m.shape[1] for m in cnm])
-        off = as_i64(subspaceOffsets)
-        gb, glb = as_i64(ghostBcNodes), as_i64(globalBcNodes)
-        self._keep = cnm          # borrowed by the library for the PC's lifetime (ssc/libssc.c:268)
-        P = i64p * n
-        CHKERR(lib.SSCPatchSetDiscretisationInfo(
-            self.handle, C.c_int64(n), P(*[ip(s[0]) for s in secs]), P(*[ip(s[1]) for s in secs]), ip(bs), ip(npc),
-            P(*[ip(m) for m in cnm]), ip(off), C.c_int64(gb.size), ip(gb), C.c_int64(glb.size), ip(glb)))
+        cnm = [np.ascontiguousarray(m, dtype=np.int64) for m in cellNodeMaps]
+        self._core.setPatchDiscretisationInfo(secs, as_i64(bs), cnm, as_i64(subspaceOffsets), as_i64(ghostBcNodes), as_i64(globalBcNodes))
 
     def setPatchComputeOperator(self, operator, args=None, kargs=None):
         """The reference's callback assembles one patch matrix (ssc/PatchPC.pyx:158-163).  Here ``operator`` is
@@ -244,11 +236,15 @@ class PC(object):
             indices = np.ascontiguousarray(indices, dtype=np.int32)
             data = np.ascontiguousarray(data, dtype=np.float64)
             self._csr_keep = (indptr, indices, data)
-            n = indptr.size - 1
-            ptrs = [a.ctypes.data_as(C.c_void_p) for a in self._csr_keep]
-        else:
-            n, ptrs = indptr[0], [C.c_void_p(p) for p in (indptr[1], indices, data)]
+            self._core.setOperatorCSR(indptr, indices, data)
+            return
+        n, ptrs = indptr[0], [C.c_void_p(p) for p in (indptr[1], indices, data)]
         CHKERR(lib.SSCPatchSetOperatorCSR(self.handle, C.c_int64(n), ptrs[0], ptrs[1], ptrs[2], int(memspace)))
+
+    def releaseOperator(self):
+        """Drop the host CSR arrays kept alive for the library (they are only borrowed until setUp returns)."""
+        self._csr_keep = None
+        self._core.releaseOperator()
 
     # ---- setup / apply ---------------------------------------------------------------------
     def setUp(self):
@@ -259,24 +255,24 @@ class PC(object):
             self.setOperatorCSR(*csr)
         elif self._csr_keep is None and self.P is not None and hasattr(self.P, "getValuesCSR"):
             self.setOperatorCSR(*self.P.getValuesCSR())
-        CHKERR(lib.SSCPatchSetUp(self.handle))
+        self._core.setUp()
 
     def apply(self, x, y):
         if isinstance(x, DeviceVec):
-            CHKERR(lib.SSCPatchApply(self.handle, x.ptr, y.ptr, MEM_DEVICE))
+            self._core.applyDevice(x.ptr.value, y.ptr.value)
             return
         xa, ya = _host_array(x), _host_array(y)
         if not (xa.flags.c_contiguous and ya.flags.c_contiguous and xa.dtype == np.float64 and ya.dtype == np.float64):
             raise ValueError("x and y must be contiguous float64")
         if xa.size != self.size("nowned") or ya.size != xa.size:
             raise ValueError("vector length %d does not match the PC (%d)" % (xa.size, self.size("nowned")))
-        CHKERR(lib.SSCPatchApply(self.handle, xa.ctypes.data_as(C.c_void_p), ya.ctypes.data_as(C.c_void_p), MEM_HOST))
+        self._core.apply(xa, ya)
 
     def applyTranspose(self, x, y):
-        CHKERR(lib.SSCPatchApplyTranspose(self.handle, None, None, MEM_HOST))
+        self._core.applyTranspose()
 
     def synchronize(self):
-        CHKERR(lib.SSCPatchSynchronize(self.handle))
+        self._core.synchronize()
 
     def view(self, viewer=None):
         buf = C.create_string_buffer(4096)
