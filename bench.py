@@ -289,7 +289,8 @@ def main():
         pc.releaseOperator()         # the CSR was only borrowed until SetUp returned; N=1 keeps it for the CPU baseline
         csr = None
     setup = {"note": "setup_wall_s = SSCPatchSetUp with the CSR in pageable host memory: patch construction on the host, H2D of dof lists and CSR, extract, factor", "create_patches_ms": pc.eventTime("PCPATCHCreate"), "extract_ms": pc.eventTime("PCPATCHComputeOp"),
-             "factor_ms": pc.eventTime("PCPATCHSolve"), "setup_wall_s": info["t_setup_wall"],
+             "factor_ms": pc.eventTime("PCPATCHSolve"), "lists_ms": pc.eventTime("SSCSetupLists"), "upload_operator_ms": pc.eventTime("SSCSetupUploadOperator"),
+             "alloc_blocks_ms": pc.eventTime("SSCSetupAllocBlocks"), "setup_wall_s": info["t_setup_wall"],
              "assemble_wall_s": info["t_assemble"], "mesh_wall_s": info["t_mesh"]}
     nowned = pc.size("nowned")
     nglobal = nowned
@@ -401,7 +402,7 @@ def main():
     except (OSError, ValueError, KeyError):
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "ssc_apply_kernel (all size classes of one apply)", "kernel_ms": kernel_ms,
+                "traffic": traffic, "kernel": "ssc_apply_pipe_kernel<1,8> (the size-class launches of one apply; traffic = ncu capture of the n=125 launch)", "kernel_ms": kernel_ms,
                 "algorithmic_bytes": bytes_apply, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
     out = {"metric": METRIC if args.workload == "poisson_hex" else "PCApply dofs/s (3D vector P2 elasticity on tets, vertex-star patches, additive, fp64)", "value": nglobal / (ms_step * 1e-3), "unit": "dofs/s", "n_gpus": nranks, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

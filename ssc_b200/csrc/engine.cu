@@ -102,7 +102,7 @@ struct SizeClass {
 
 struct SSCPatchPC_s {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, up_stream = nullptr;
     int sm_count = 148;
     // options (defaults: PCCreate_PATCH ssc/libssc.c:1697-1711)
     bool save_operators = true, partition_of_unity = false, multiplicative = false, print_patches = false;
@@ -187,7 +187,7 @@ struct SSCPatchPC_s {
     // pipelined host-space apply: H2D of x, patch kernels and D2H of y overlap slab by slab
     int pipe_slabs = 8;
     bool pipe_force = false;
-    bool pipe_ready = false;
+    bool pipe_ready = false, pipe_tried = false;
     std::vector<std::vector<std::pair<i64, i64>>> pipe_ranges;   // [slab][class] -> sorted positions [q0, q1)
     std::vector<i64> pipe_in, pipe_out, pipe_bc;                 // x piece bounds, y piece bounds, bc list offsets per y piece
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -263,6 +263,7 @@ extern "C" int SSCPatchCreate(int device, SSCPatchPC *out)
     pc->device = device;
     CUDA_OK(cudaSetDevice(device));
     CUDA_OK(cudaStreamCreateWithFlags(&pc->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&pc->up_stream, cudaStreamNonBlocking));
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     pc->sm_count = prop.multiProcessorCount;
@@ -322,6 +323,7 @@ extern "C" int SSCPatchDestroy(SSCPatchPC *ppc)
     if (pc->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(pc->comm);
     cudaEventDestroy(pc->ev0); cudaEventDestroy(pc->ev1);
     cudaStreamDestroy(pc->stream);
+    cudaStreamDestroy(pc->up_stream);
     delete pc;
     *ppc = nullptr;
     return 0;
@@ -903,7 +905,7 @@ static int peer_reduce(PC *pc, double *yl, double *y)
 static int staged_upload(PC *pc, void *dst, const void *src, size_t bytes)
 {
     const size_t chunk = (size_t)128 << 20;
-    if (bytes < 2 * chunk) { CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, pc->stream)); return 0; }
+    if (bytes < 2 * chunk) { CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, pc->up_stream)); return 0; }
     const int R = 3;
     if (!pc->stage[0]) {
         for (int r = 0; r < R; ++r) {
@@ -911,7 +913,7 @@ static int staged_upload(PC *pc, void *dst, const void *src, size_t bytes)
             if (err != cudaSuccess) {       // no pinned memory to spare: fall back to the driver's own staging
                 cudaGetLastError();
                 for (int q = 0; q < r; ++q) { cudaFreeHost(pc->stage[q]); pc->stage[q] = nullptr; }
-                CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, pc->stream));
+                CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, pc->up_stream));
                 return 0;
             }
             CUDA_OK(cudaEventCreateWithFlags(&pc->stage_ev[r], cudaEventDisableTiming));
@@ -929,8 +931,8 @@ static int staged_upload(PC *pc, void *dst, const void *src, size_t bytes)
             th.emplace_back([=]() { memcpy((char *)pc->stage[r] + a, (const char *)src + off + a, b - a); });
         }
         for (auto &x : th) x.join();
-        CUDA_OK(cudaMemcpyAsync((char *)dst + off, pc->stage[r], len, cudaMemcpyHostToDevice, pc->stream));
-        CUDA_OK(cudaEventRecord(pc->stage_ev[r], pc->stream));
+        CUDA_OK(cudaMemcpyAsync((char *)dst + off, pc->stage[r], len, cudaMemcpyHostToDevice, pc->up_stream));
+        CUDA_OK(cudaEventRecord(pc->stage_ev[r], pc->up_stream));
         pc->stage_busy[r] = true;
         off += len;
     }
@@ -951,7 +953,7 @@ static int upload_csr(PC *pc)
     CHK(dev_alloc(&pc->d_colidx, nnz));
     CHK(dev_alloc(&pc->d_vals, nnz));
     pc->csr_owned = true;
-    CUDA_OK(cudaMemcpyAsync(pc->d_rowptr, pc->csr_rowptr, (size_t)(pc->csr_nrows + 1) * sizeof(i64), cudaMemcpyHostToDevice, pc->stream));
+    CUDA_OK(cudaMemcpyAsync(pc->d_rowptr, pc->csr_rowptr, (size_t)(pc->csr_nrows + 1) * sizeof(i64), cudaMemcpyHostToDevice, pc->up_stream));
     CHK(staged_upload(pc, pc->d_colidx, pc->csr_colidx, (size_t)nnz * sizeof(int)));
     CHK(staged_upload(pc, pc->d_vals, pc->csr_vals, (size_t)nnz * sizeof(double)));
     return 0;
@@ -1067,12 +1069,33 @@ extern "C" int SSCPatchSetUp(SSCPatchPC pc)
     CHK(set_device(pc));
     if (pc->sub_ksp_type != "preonly") return ssc_set_error(SSC_ERR_SUP, "only preonly patch solves are supported");
     const bool first = !pc->device_ready;
-    if (first) CHK(build_device_lists(pc));
+    auto tick = std::chrono::steady_clock::now();
+    auto lap = [&](const char *name) {
+        auto now = std::chrono::steady_clock::now();
+        pc->event_ms[name] = std::chrono::duration<double, std::milli>(now - tick).count();
+        tick = now;
+    };
+    // the operator travels to the device on its own stream while the host builds the patches
+    int up_rc = 0;
+    std::string up_msg;
+    std::thread uploader([&]() {
+        cudaSetDevice(pc->device);
+        up_rc = upload_csr(pc);
+        if (up_rc) up_msg = SSCGetLastError();
+    });
+    int list_rc = first ? build_device_lists(pc) : 0;
+    std::string list_msg = list_rc ? SSCGetLastError() : "";
+    lap("SSCSetupLists");                                               // patch construction + size classes + dof-list upload
+    uploader.join();
+    if (list_rc) return ssc_set_error(list_rc, "%s", list_msg.c_str());
+    if (up_rc) return ssc_set_error(up_rc, "%s", up_msg.c_str());
+    CUDA_OK(cudaStreamSynchronize(pc->up_stream));
+    lap("SSCSetupUploadOperator");                                      // what is left of the upload after the patches are built
     if (first && pc->partition_of_unity) CHK(compute_weights(pc));      // only on the first setup, ssc/libssc.c:1254
-    CHK(upload_csr(pc));
     pc->event_ms["PCPATCHComputeOp"] = 0; pc->event_ms["PCPATCHSolve"] = 0;
     if (pc->save_operators) {
         if (!pc->d_blocks) CHK(dev_alloc(&pc->d_blocks, pc->block_elems));
+        lap("SSCSetupAllocBlocks");
         if (pc->keep_operators && !pc->d_blocks0) CHK(dev_alloc(&pc->d_blocks0, pc->block_elems));
         for (const SizeClass &c : pc->classes)
             CHK(extract_and_invert(pc, c, c.first, c.first + c.count, pc->d_blocks + c.moff, pc->d_fail + c.first, true));
@@ -1101,7 +1124,7 @@ extern "C" int SSCPatchSetUp(SSCPatchPC pc)
         if (pc->symmetric) return ssc_set_error(SSC_ERR_ARG_INCOMP, "ssc_symmetric_storage needs saved patch operators");
         CUDA_OK(cudaStreamSynchronize(pc->stream));
     }
-    if (!pc->pipe_ready) CHK(build_host_pipeline(pc));
+    pc->pipe_tried = false;      // the slab schedule of host-space applies is built on first use
     pc->setup_done = true;
     return 0;
 }
@@ -1358,6 +1381,7 @@ extern "C" int SSCPatchApply(SSCPatchPC pc, const double *x, double *y, int mems
     if (memspace == SSC_MEM_DEVICE) return apply_device(pc, x, y);
     if (!pc->setup_done) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "SSCPatchSetUp() has not been called");
     if (!pc->d_xs) { CHK(dev_alloc(&pc->d_xs, pc->nowned)); CHK(dev_alloc(&pc->d_ys, pc->nowned)); }
+    if (!pc->pipe_ready && !pc->pipe_tried) { pc->pipe_tried = true; CHK(build_host_pipeline(pc)); }
     if (pc->pipe_ready && pc->partition_of_unity && !pc->d_w) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "partition of unity was switched on after the first setup");
     if (pc->pipe_ready) return apply_host_pipelined(pc, x, y);
     CUDA_OK(cudaMemcpyAsync(pc->d_xs, x, (size_t)pc->nowned * sizeof(double), cudaMemcpyHostToDevice, pc->stream));
