@@ -108,6 +108,7 @@ struct SSCPatchPC_s {
     bool save_operators = true, partition_of_unity = false, multiplicative = false, print_patches = false;
     bool symmetrise_sweep = false, keep_operators = false, dim_set = false, codim_set = false;
     int sub_pc = SSC_SUB_LU;
+    int factor_tile = 4;          // register tiles of the n <= 128 factor kernel: 4 (8x4, default) or 8 (8x8, measured slower)
     int factor_ctas = 0;          // concurrent CTAs of the blocked factor kernel (0 = fill the SMs)
     int factor_panel = 16;        // panel width of the blocked factor kernel (16 or 32)
     int factor_variant = 1;       // 1: register-resident Gauss-Jordan for n <= 128, 0: shared-memory kernel
@@ -430,6 +431,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     }
     if (name == "ssc_factor_panel") { pc->factor_panel = atoi(v); return 0; }
     if (name == "ssc_factor_ctas") { pc->factor_ctas = atoi(v); return 0; }
+    if (name == "ssc_factor_tile") { pc->factor_tile = atoi(v); return 0; }
     if (name == "ssc_host_pipeline") { const int s = atoi(v); pc->pipe_force = s < 0; pc->pipe_slabs = s < 0 ? -s : s; pc->pipe_ready = false; return 0; }   // negative: use it whatever the problem size
     if (name == "ssc_apply_variant") {
         const int a = atoi(v);
@@ -1022,6 +1024,13 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
         else if (nb == 32) LAUNCH_BLK(false, 32);
         else LAUNCH_BLK(false, 16);
 #undef LAUNCH_BLK
+    }
+    else if (n <= 128 && pc->factor_variant == 1 && pc->factor_tile == 8) {
+        // register-resident 8 x 8 tiles: (n/8)^2 threads; needs tid < n for the permutation arrays -> at least n threads
+        const int TC = (n + 7) / 8;
+        const int threads = std::max((TC * TC + 31) / 32 * 32, (n + 31) / 32 * 32);
+        if (pivot) ssc_invert_reg8_kernel<true><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC);
+        else ssc_invert_reg8_kernel<false><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC);
     }
     else if (n <= 128 && pc->factor_variant == 1) {
         // register-resident tiles: (n/8) x (n/4) threads

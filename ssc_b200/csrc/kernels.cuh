@@ -361,6 +361,132 @@ ssc_invert_reg_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll
     }
 }
 
+// Same algorithm with 8 x 8 tiles: (n/8)^2 threads, 64 FMAs per thread and step against 16 shared-memory loads and
+// half as many warps repeating the pivot search -- the 8 x 4 form above is issue-bound on exactly that overhead.
+template <bool kPivot>
+__global__ void __launch_bounds__(256, 1)
+ssc_invert_reg8_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll count, int *__restrict__ fail_flags, int TC)
+{
+    __shared__ __align__(16) double colv[2][128];
+    __shared__ __align__(16) double rowv[2][128];
+    __shared__ int perm[128], qinv[128];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tr = tid / TC, tc = tid - tr * TC;
+    const bool owner = tr < TC;                              // TC = ceil(n / 8) tiles in both directions
+    const int r0 = owner ? 8 * tr : 0, c0 = 8 * tc;
+    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
+        double *B = blocks + p * stride;
+        double a[8][8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int j = c0 + c;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = r0 + r;
+                a[r][c] = (owner && i < n && j < n) ? B[(ll)j * ldg + i] : 0.0;      // transposed load: A = B^T
+            }
+        }
+        unsigned usedmask = 0;
+        int fail = 0;
+        for (int k = 0; k < n; ++k) {
+            const int buf = k & 1;
+            if (owner && tc == (k >> 3)) {
+#define PUBLISH_COL(C)                                                                  \
+    _Pragma("unroll") for (int r = 0; r < 8; ++r) { colv[buf][r0 + r] = a[r][C]; a[r][C] = 0.0; }
+                switch (k & 7) {
+                case 0: PUBLISH_COL(0) break;
+                case 1: PUBLISH_COL(1) break;
+                case 2: PUBLISH_COL(2) break;
+                case 3: PUBLISH_COL(3) break;
+                case 4: PUBLISH_COL(4) break;
+                case 5: PUBLISH_COL(5) break;
+                case 6: PUBLISH_COL(6) break;
+                default: PUBLISH_COL(7) break;
+                }
+#undef PUBLISH_COL
+            }
+            __syncthreads();
+            int prow = k;
+            if (kPivot) {
+                double best = -1.0;
+                int bi = 1 << 30;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int i = lane + 32 * s;
+                    if (i < n && !((usedmask >> s) & 1u)) {
+                        const double v = fabs(colv[buf][i]);
+                        if (v > best) { best = v; bi = i; }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                }
+                prow = bi;
+                if (prow >= n) { fail = 1; break; }
+                if ((prow & 31) == lane) usedmask |= 1u << (prow >> 5);
+                if (tid == 0) perm[k] = prow;
+            }
+            const double d = colv[buf][prow];
+            if (!(fabs(d) > 0.0) || (!kPivot && !(d > 0.0))) { fail = 1; break; }     // uniform across the CTA
+            const double dinv = 1.0 / d;
+            if (owner && tr == (prow >> 3)) {
+#define PUBLISH_ROW(R)                                                                                          \
+    _Pragma("unroll") for (int c = 0; c < 8; ++c) { rowv[buf][c0 + c] = (c0 + c == k) ? dinv : a[R][c] * dinv; a[R][c] = 0.0; }
+                switch (prow & 7) {
+                case 0: PUBLISH_ROW(0) break;
+                case 1: PUBLISH_ROW(1) break;
+                case 2: PUBLISH_ROW(2) break;
+                case 3: PUBLISH_ROW(3) break;
+                case 4: PUBLISH_ROW(4) break;
+                case 5: PUBLISH_ROW(5) break;
+                case 6: PUBLISH_ROW(6) break;
+                default: PUBLISH_ROW(7) break;
+                }
+#undef PUBLISH_ROW
+            }
+            __syncthreads();
+            const double2 *cp = reinterpret_cast<const double2 *>(&colv[buf][r0]);
+            const double2 *rp2 = reinterpret_cast<const double2 *>(&rowv[buf][c0]);
+            double cv[8], rv[8];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) { const double2 t = cp[h]; cv[2 * h] = t.x; cv[2 * h + 1] = t.y; }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) { const double2 t = rp2[h]; rv[2 * h] = t.x; rv[2 * h + 1] = t.y; }
+            const int rp = prow - r0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const double m = (r == rp) ? 1.0 : -cv[r];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) a[r][c] = fma(m, rv[c], a[r][c]);
+            }
+        }
+        __syncthreads();
+        if (tid < n) { if (!kPivot) perm[tid] = tid; }
+        __syncthreads();
+        if (tid < n) qinv[perm[tid]] = tid;
+        __syncthreads();
+        if (tid == 0) fail_flags[p] = fail;
+        if (!fail && owner) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = r0 + r;
+                if (i < n) {
+                    const ll row = (ll)qinv[i] * ldg;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int j = c0 + c;
+                        if (j < n) B[row + perm[j]] = a[r][c];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Blocked Gauss-Jordan for n > 128: the block stays in global memory (L2), 16 columns at a time are brought into
 // shared memory and eliminated there (with partial pivoting, rows exchanged across the whole block), and the
 // transformation they define is applied to all other columns as one (n x 16) x (16 x n) product on the fp64 tensor

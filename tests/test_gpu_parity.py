@@ -159,7 +159,7 @@ def test_apply_kernel_variants(variant, shape, p, kind):
     assert np.array_equal(pc.getPatchMatrix(i), o.patchMatrix(i))
 
 
-@pytest.mark.parametrize("factor_variant", [0, 1])
+@pytest.mark.parametrize("factor_variant", [0, 1, 14])
 @pytest.mark.parametrize("n", [5, 33, 64, 100, 128, 150])
 def test_general_blocks_need_pivoting(n, factor_variant):
     """Non-symmetric operator with zero diagonal entries: -sub_pc_type lu must pivot.  Patches are arbitrary dof sets
@@ -189,7 +189,9 @@ def test_general_blocks_need_pivoting(n, factor_variant):
     o.setOperatorCSR(A)
     o.setUpOperators()
     pc = PC(device=0)
-    pc.setOption("ssc_factor_variant", factor_variant)
+    pc.setOption("ssc_factor_variant", min(factor_variant, 1))
+    if factor_variant == 14:
+        pc.setOption("ssc_factor_tile", 8)          # the 8 x 8 register-tile kernel
     pc.setPatches(off, gtol, N)
     pc.setOperatorCSR(A.indptr, A.indices, A.data)
     pc.setUp()
