@@ -96,11 +96,13 @@ int SSCCommGetUniqueId(char uniqueId[128]);
 int SSCPatchCommInit(SSCPatchPC pc, int nranks, int rank, const char uniqueId[128]);
 
 /* NVLink peer exchange, an alternative to the NCCL path for ranks on one NVSwitch box.  Export gives 192 bytes (three
- * CUDA IPC handles: local x vector, local y vector, barrier flags) to be handed to every neighbour.  Connect takes the
- * neighbours' exports in the order of the star forest's neigh[], this rank's position in each neighbour's neigh[]
- * (slotAtNeigh), and for every entry of sendRoot / recvLeaf the matching index on the neighbour (its ghost slot /
- * its owned index).  After Connect the halo fill is direct peer stores and the overlap sum is issued by the patch
- * kernel itself as fp64 reductions into the owners' vectors; SSCPatchCommInit is then not needed. */
+ * CUDA IPC handles: this rank's ghost-value array of x, its "incoming" array with one entry per owned dof, and its
+ * barrier flags) to be handed to every neighbour.  Connect takes the neighbours' exports in the order of the star
+ * forest's neigh[], this rank's position in each neighbour's neigh[] (slotAtNeigh), and for every entry of sendRoot /
+ * recvLeaf the matching index on the neighbour: its ghost slot number (local leaf index minus its owned count) /
+ * its owned index.  After Connect the halo fill is direct peer stores, the overlap sum is issued by the patch kernel
+ * itself as fp64 reductions into the owners' incoming arrays, and x / y are used in place (no local copies);
+ * SSCPatchCommInit is then not needed. */
 int SSCPatchPeerExport(SSCPatchPC pc, char *handles192);
 int SSCPatchPeerConnect(SSCPatchPC pc, const char *neighHandles, const int *slotAtNeigh, const SSCInt *remoteLeaf,
                         const SSCInt *remoteRoot);

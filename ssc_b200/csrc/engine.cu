@@ -135,7 +135,9 @@ struct SSCPatchPC_s {
     PeerScatter *d_ps = nullptr;
     PeerPush h_push;
     PeerFlags h_flags;
-    int *d_ghostPeer = nullptr, *d_ghostRemote = nullptr, *d_sendPeer = nullptr, *d_remoteLeaf = nullptr;
+    int *d_ghostPeer = nullptr, *d_ghostRemote = nullptr, *d_sendPeer = nullptr, *d_remoteLeaf = nullptr, *d_iface = nullptr;
+    i64 niface = 0;
+    double *d_xg = nullptr, *d_yin = nullptr;       // ghost values of x (filled by neighbours), incoming contributions to owned dofs
     unsigned long long *d_flags = nullptr, epoch = 0;
     int *d_timeout = nullptr;
     std::vector<void *> ipc_opened;
@@ -281,7 +283,7 @@ static void free_device_state(PC *pc)
     dev_free(pc->d_ypatch); dev_free(pc->d_slotoff); dev_free(pc->d_slots);
     dev_free(pc->d_r); dev_free(pc->d_gtol); dev_free(pc->d_blocks); dev_free(pc->d_blocks0); dev_free(pc->d_fail); dev_free(pc->d_bc);
     dev_free(pc->d_w); dev_free(pc->d_mult); dev_free(pc->d_xs); dev_free(pc->d_ys);
-    if (!pc->p2p) { dev_free(pc->d_xl); dev_free(pc->d_yl); }
+    dev_free(pc->d_xl); dev_free(pc->d_yl);
     dev_free(pc->d_selfLeaf); dev_free(pc->d_selfRoot); dev_free(pc->d_sendRoot); dev_free(pc->d_recvLeaf);
     dev_free(pc->d_sendbuf); dev_free(pc->d_recvbuf);
     if (pc->csr_owned) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); }
@@ -315,7 +317,7 @@ extern "C" int SSCPatchDestroy(SSCPatchPC *ppc)
     for (int r = 0; r < 3; ++r) if (pc->stage[r]) { cudaFreeHost(pc->stage[r]); cudaEventDestroy(pc->stage_ev[r]); }
     for (void *q : pc->ipc_opened) cudaIpcCloseMemHandle(q);
     pc->p2p = false;
-    dev_free(pc->d_xl); dev_free(pc->d_yl); dev_free(pc->d_flags); dev_free(pc->d_timeout); dev_free(pc->d_ps);
+    dev_free(pc->d_xg); dev_free(pc->d_yin); dev_free(pc->d_iface); dev_free(pc->d_flags); dev_free(pc->d_timeout); dev_free(pc->d_ps);
     dev_free(pc->d_ghostPeer); dev_free(pc->d_ghostRemote); dev_free(pc->d_sendPeer); dev_free(pc->d_remoteLeaf);
     if (pc->s_in) { cudaStreamDestroy(pc->s_in); cudaStreamDestroy(pc->s_out); }
     for (auto &ev : pc->ev_in) cudaEventDestroy(ev);
@@ -741,8 +743,8 @@ static int build_device_lists(PC *pc)
         CHK(upload_i32(pc, pc->recvLeaf, &pc->d_recvLeaf));
         CHK(dev_alloc(&pc->d_sendbuf, (i64)std::max(pc->sendRoot.size(), pc->recvLeaf.size())));
         CHK(dev_alloc(&pc->d_recvbuf, (i64)std::max(pc->sendRoot.size(), pc->recvLeaf.size())));
-        if (!pc->d_xl) CHK(dev_alloc(&pc->d_xl, pc->nlocal));
-        if (!pc->d_yl) CHK(dev_alloc(&pc->d_yl, pc->nlocal));
+        if (!pc->p2p && !pc->d_xl) CHK(dev_alloc(&pc->d_xl, pc->nlocal));
+        if (!pc->p2p && !pc->d_yl) CHK(dev_alloc(&pc->d_yl, pc->nlocal));
         if (!pc->neigh.empty() && !pc->comm && !pc->p2p) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "the star forest names neighbour ranks but SSCPatchCommInit() has not been called");
     } else if (pc->nowned != pc->nlocal) {
         return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "nowned (%lld) != nlocal (%lld) but no star forest was set", (long long)pc->nowned, (long long)pc->nlocal);
@@ -823,13 +825,14 @@ extern "C" int SSCPatchPeerExport(SSCPatchPC pc, char *handles)
 {
     CHK(set_device(pc));
     if (!pc->sf_set) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "set the star forest before exporting peer handles");
-    if (!pc->d_xl) CHK(dev_alloc(&pc->d_xl, pc->nlocal));
-    if (!pc->d_yl) CHK(dev_alloc(&pc->d_yl, pc->nlocal));
+    const i64 nghost = pc->nlocal - pc->nowned;
+    if (!pc->d_xg) { CHK(dev_alloc(&pc->d_xg, nghost)); CUDA_OK(cudaMemset(pc->d_xg, 0, (size_t)std::max<i64>(nghost, 1) * sizeof(double))); }
+    if (!pc->d_yin) { CHK(dev_alloc(&pc->d_yin, pc->nowned)); CUDA_OK(cudaMemset(pc->d_yin, 0, (size_t)std::max<i64>(pc->nowned, 1) * sizeof(double))); }
     if (!pc->d_flags) { CHK(dev_alloc(&pc->d_flags, 16)); CUDA_OK(cudaMemset(pc->d_flags, 0, 16 * sizeof(unsigned long long))); }
     if (!pc->d_timeout) { CHK(dev_alloc(&pc->d_timeout, 1)); CUDA_OK(cudaMemset(pc->d_timeout, 0, sizeof(int))); }
     cudaIpcMemHandle_t h[3];
-    CUDA_OK(cudaIpcGetMemHandle(&h[0], pc->d_xl));
-    CUDA_OK(cudaIpcGetMemHandle(&h[1], pc->d_yl));
+    CUDA_OK(cudaIpcGetMemHandle(&h[0], pc->d_xg));
+    CUDA_OK(cudaIpcGetMemHandle(&h[1], pc->d_yin));
     CUDA_OK(cudaIpcGetMemHandle(&h[2], pc->d_flags));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     memcpy(handles, h, 192);
@@ -866,7 +869,10 @@ extern "C" int SSCPatchPeerConnect(SSCPatchPC pc, const char *neighHandles, cons
             if (s < 0 || s >= nghost) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "receive slot is not a ghost slot");
             ghostPeer[(size_t)s] = (int)k; ghostRemote[(size_t)s] = (int)remoteRoot[i];
         }
-        for (i64 i = pc->sendOff[k]; i < pc->sendOff[k + 1]; ++i) { sendPeer[(size_t)i] = (int)k; rleaf[(size_t)i] = (int)remoteLeaf[i]; }
+        for (i64 i = pc->sendOff[k]; i < pc->sendOff[k + 1]; ++i) {
+            if (remoteLeaf[i] < 0) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "remoteLeaf must be the neighbour's ghost slot number (local index minus its owned count)");
+            sendPeer[(size_t)i] = (int)k; rleaf[(size_t)i] = (int)remoteLeaf[i];
+        }
     }
     for (i64 s = 0; s < nghost; ++s) if (ghostPeer[(size_t)s] < 0) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "ghost slot %lld has no owner among the neighbours", (long long)s);
     auto up = [&](const std::vector<int> &v, int **d) -> int {
@@ -877,29 +883,43 @@ extern "C" int SSCPatchPeerConnect(SSCPatchPC pc, const char *neighHandles, cons
     CHK(up(ghostPeer, &pc->d_ghostPeer)); CHK(up(ghostRemote, &pc->d_ghostRemote));
     CHK(up(sendPeer, &pc->d_sendPeer)); CHK(up(rleaf, &pc->d_remoteLeaf));
     pc->h_ps.ghostPeer = pc->d_ghostPeer; pc->h_ps.ghostRemote = pc->d_ghostRemote; pc->h_ps.nowned = (int)pc->nowned;
+    pc->h_ps.xg = pc->d_xg;
+    {
+        std::vector<i64> u(pc->sendRoot);
+        std::sort(u.begin(), u.end());
+        u.erase(std::unique(u.begin(), u.end()), u.end());
+        pc->niface = (i64)u.size();
+        CHK(upload_i32(pc, u, &pc->d_iface));
+    }
     CHK(dev_alloc(&pc->d_ps, 1));
     CUDA_OK(cudaMemcpy(pc->d_ps, &pc->h_ps, sizeof(PeerScatter), cudaMemcpyHostToDevice));
     pc->p2p = true;
     return 0;
 }
 
-// halo fill through peer stores + barrier
-static int peer_bcast(PC *pc, const double *x, double *xl)
+// halo fill through peer stores + barrier: neighbours' ghost arrays receive this rank's interface values
+static int peer_bcast(PC *pc, const double *x)
 {
-    CUDA_OK(cudaMemcpyAsync(xl, x, (size_t)pc->nowned * sizeof(double), cudaMemcpyDeviceToDevice, pc->stream));
     const i64 ns = (i64)pc->sendRoot.size();
     if (ns) { ssc_peer_push_kernel<<<grid_for(ns, 256), 256, 0, pc->stream>>>(ns, pc->d_sendRoot, pc->d_sendPeer, pc->d_remoteLeaf, x, pc->h_push); pc->launches++; }
     return peer_barrier(pc);
 }
-// overlap sum for a local vector that was filled WITHOUT the fused scatter (set-up time only: dof multiplicities)
-static int peer_reduce(PC *pc, double *yl, double *y)
+// after the patch kernels: wait for the neighbours, then fold their contributions to this rank's interface dofs into y
+static int peer_fold(PC *pc, double *y)
+{
+    CHK(peer_barrier(pc));
+    if (pc->niface) { ssc_peer_fold_kernel<<<grid_for(pc->niface, 256), 256, 0, pc->stream>>>(pc->niface, pc->d_iface, pc->d_yin, y); pc->launches++; }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+// overlap sum of a local (owned + ghost) vector that was filled WITHOUT the fused scatter (set-up only: dof multiplicities)
+static int peer_reduce(PC *pc, const double *yl, double *y)
 {
     CHK(peer_barrier(pc));
     const i64 ng = pc->nlocal - pc->nowned;
     if (ng) { ssc_peer_pushadd_kernel<<<grid_for(ng, 256), 256, 0, pc->stream>>>(ng, (int)pc->nowned, yl, pc->h_ps); pc->launches++; }
-    CHK(peer_barrier(pc));
     CUDA_OK(cudaMemcpyAsync(y, yl, (size_t)pc->nowned * sizeof(double), cudaMemcpyDeviceToDevice, pc->stream));
-    return 0;
+    return peer_fold(pc, y);
 }
 
 // Host -> device copy of a large pageable array: worker threads copy slices into a small ring of pinned buffers while
@@ -1061,7 +1081,9 @@ static int compute_weights(PC *pc)
     // ssc/libssc.c:1254-1284: scatter ones through every patch, reduce to owners, reciprocal
     dev_free(pc->d_w);
     CHK(dev_alloc(&pc->d_w, pc->nowned));
-    double *ml = pc->sf_set ? pc->d_yl : pc->d_w;
+    double *tmp_local = nullptr;
+    if (pc->sf_set && pc->p2p) CHK(dev_alloc(&tmp_local, pc->nlocal));
+    double *ml = pc->sf_set ? (pc->p2p ? tmp_local : pc->d_yl) : pc->d_w;
     CUDA_OK(cudaMemsetAsync(ml, 0, (size_t)pc->nlocal * sizeof(double), pc->stream));
     if (pc->sum_n) { ssc_count_kernel<<<grid_for(pc->sum_n, 256), 256, 0, pc->stream>>>(pc->d_gtol, pc->sum_n, ml); pc->launches++; }
     if (pc->sf_set && pc->p2p) CHK(peer_reduce(pc, ml, pc->d_w));
@@ -1069,6 +1091,7 @@ static int compute_weights(PC *pc)
     ssc_reciprocal_kernel<<<grid_for(pc->nowned, 256), 256, 0, pc->stream>>>(pc->nowned, pc->d_w);
     pc->launches++;
     CUDA_OK(cudaGetLastError());
+    if (tmp_local) { CUDA_OK(cudaStreamSynchronize(pc->stream)); cudaFree(tmp_local); }
     return 0;
 }
 
@@ -1240,9 +1263,10 @@ static int apply_device(PC *pc, const double *x, double *y)
     const double *xl = x;
     double *yl = y;
     if (!identity && pc->p2p) {
-        xl = pc->d_xl; yl = pc->d_yl;
-        CUDA_OK(cudaMemsetAsync(yl, 0, (size_t)pc->nlocal * sizeof(double), pc->stream));   // before the barrier inside peer_bcast:
-        CHK(peer_bcast(pc, x, pc->d_xl));                                                   // neighbours add into yl after it
+        // owned entries are read from x and added into y directly; ghosts live in d_xg (filled by the neighbours) and
+        // their corrections go straight to the owners' d_yin over NVLink (PeerScatter)
+        CUDA_OK(cudaMemsetAsync(y, 0, (size_t)pc->nowned * sizeof(double), pc->stream));
+        CHK(peer_bcast(pc, x));
     } else {
         if (!identity) {                                    // ssc/libssc.c:1321-1326
             CHK(sf_bcast(pc, x, pc->d_xl));
@@ -1283,10 +1307,8 @@ static int apply_device(PC *pc, const double *x, double *y)
         pc->launches++;
     }
     if (pc->ktimer) CUDA_OK(cudaEventRecord(k1, pc->stream));
-    if (!identity && pc->p2p) {                             // ghost contributions already sit in their owners' vectors
-        CHK(peer_barrier(pc));
-        CUDA_OK(cudaMemcpyAsync(y, yl, (size_t)pc->nowned * sizeof(double), cudaMemcpyDeviceToDevice, pc->stream));
-    } else if (!identity) CHK(sf_reduce(pc, yl, y));         // :1396-1401
+    if (!identity && pc->p2p) CHK(peer_fold(pc, y));         // neighbours' contributions to the interface dofs
+    else if (!identity) CHK(sf_reduce(pc, yl, y));           // :1396-1401
     if (pc->nbc) { ssc_bc_kernel<<<grid_for(pc->nbc, 256), 256, 0, pc->stream>>>(pc->d_bc, pc->nbc, x, y); pc->launches++; }   // :1404-1413
     if (pc->partition_of_unity) {                            // :1418-1421
         if (!pc->d_w) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "partition of unity was switched on after the first setup");

@@ -19,11 +19,18 @@ __device__ __forceinline__ unsigned hash_dof(int key) { return (unsigned)key * 2
 // the box; its correction is added straight into the owner's local vector through a mapped peer pointer, so the
 // overlap sum of ssc/libssc.c:1399-1400 travels over NVLink while the patch kernel is still streaming blocks.
 struct PeerScatter {
-    double *yl[16];          // local y vector of every neighbour (cudaIpcOpenMemHandle)
+    double *yl[16];          // "incoming" vector (one entry per owned dof) of every neighbour (cudaIpcOpenMemHandle)
     const int *ghostPeer;    // ghost slot -> neighbour number
-    const int *ghostRemote;  // ghost slot -> index in that neighbour's vector
+    const int *ghostRemote;  // ghost slot -> owned index on that neighbour
+    const double *xg;        // this rank's ghost values of x, written by the neighbours (halo fill)
     int nowned;
 };
+// residual entry of local dof gi: owned ones come from the caller's vector, ghosts from the array the neighbours filled
+__device__ __forceinline__ double gather_x(const double *__restrict__ x, int gi, const PeerScatter *__restrict__ ps)
+{
+    if (ps != nullptr && gi >= ps->nowned) return ps->xg[gi - ps->nowned];
+    return __ldg(x + gi);
+}
 // Deterministic mode: instead of reducing into y, every patch dof stores its correction in its own slot of `ypatch`
 // (coalesced plain stores); ssc_slot_sum_kernel then adds the slots of each dof in a fixed order.
 __device__ __forceinline__ void scatter_add(double *__restrict__ y, int gi, double v, const PeerScatter *__restrict__ ps);
@@ -728,7 +735,7 @@ ssc_apply_kernel(const double *__restrict__ S, ll stride, int ld, const int *__r
     const bool active = lp < ppb && p < count;
     double *xs = xs_all + (size_t)lp * n;
     const int *g = gtol + p * n;
-    if (active) for (int i = t; i < n; i += tp) xs[i] = __ldg(x + g[i]);
+    if (active) for (int i = t; i < n; i += tp) xs[i] = gather_x(x, g[i], ps);
     __syncthreads();
     if (!active) return;
     const double sc = mult ? scale * mult[p] : scale;
@@ -773,7 +780,7 @@ ssc_apply_pipe_kernel(const double *__restrict__ S, ll stride, int ld, const int
     const bool active = lp < ppb && p < count;
     double *xs = xs_all + (size_t)lp * n;
     const int *g = gtol + p * n;
-    if (active) for (int i = t; i < n; i += tp) xs[i] = __ldg(x + g[i]);
+    if (active) for (int i = t; i < n; i += tp) xs[i] = gather_x(x, g[i], ps);
     __syncthreads();
     if (!active) return;
     const double sc = mult ? scale * mult[p] : scale;
@@ -1038,7 +1045,7 @@ ssc_apply_sym_kernel(const double *__restrict__ packed, ll pstride, unsigned cop
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     const int *g = gtol + p * n;
-    for (int i = t; i < n; i += blockDim.x) xs[i] = __ldg(x + g[i]);
+    for (int i = t; i < n; i += blockDim.x) xs[i] = gather_x(x, g[i], ps);
     if (!kBulk) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (kBulk) mbar_wait(&bar, 0);
@@ -1079,7 +1086,7 @@ ssc_apply_sym_persistent_kernel(const double *__restrict__ packed, ll pstride, u
         }
     }
     // residual of the first patch
-    if (mine > 0) for (int i = t; i < n; i += blockDim.x) xsbuf[i] = __ldg(x + gtol[first * n + i]);
+    if (mine > 0) for (int i = t; i < n; i += blockDim.x) xsbuf[i] = gather_x(x, gtol[first * n + i], ps);
     __syncthreads();
     for (ll k = 0; k < mine; ++k) {
         const ll p = first + k * step;
@@ -1097,7 +1104,7 @@ ssc_apply_sym_persistent_kernel(const double *__restrict__ packed, ll pstride, u
         const int *gn = gtol + (p + step) * n;
         double xnext = 0.0;
         const bool have_next = k + 1 < mine;
-        if (have_next && t < n) xnext = __ldg(x + gn[t]);
+        if (have_next && t < n) xnext = gather_x(x, gn[t], ps);
         const int *g = gtol + p * n;
         const double *L = ring + stage_doubles * s;
         mbar_wait(&bar[s], parity);
@@ -1129,8 +1136,18 @@ ssc_apply_sym_persistent_kernel(const double *__restrict__ packed, ll pstride, u
         }
         if (have_next) {
             if (t < n) xn[t] = xnext;
-            for (int i = t + blockDim.x; i < n; i += blockDim.x) xn[i] = __ldg(x + gn[i]);
+            for (int i = t + blockDim.x; i < n; i += blockDim.x) xn[i] = gather_x(x, gn[i], ps);
         }
         __syncthreads();          // stage s and xs are free again
+    }
+}
+
+// after the second neighbour barrier: fold what the neighbours added for this rank's interface dofs into y and clear it
+__global__ void ssc_peer_fold_kernel(ll n, const int *__restrict__ iface, double *__restrict__ yin, double *__restrict__ y)
+{
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) {
+        const int d = iface[i];
+        y[d] += yin[d];
+        yin[d] = 0.0;
     }
 }

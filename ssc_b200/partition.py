@@ -105,8 +105,9 @@ def connect_peers(pc, sf, rank, allgather):
     """Switch ``pc`` (star forest ``sf`` already set) to the NVLink peer exchange: gather every rank's IPC handles and
     index lists, pick out what concerns this rank's neighbours, and call SSCPatchPeerConnect."""
     _, _, neigh, send_off, send_root, recv_off, recv_leaf = sf
+    nowned = int(sf[0].size)
     mine = {"handles": pc.peerExport(), "neigh": [int(q) for q in neigh], "send_off": send_off, "send_root": send_root,
-            "recv_off": recv_off, "recv_leaf": recv_leaf}
+            "recv_off": recv_off, "recv_leaf": recv_leaf, "nowned": nowned}
     world = allgather(mine)
     handles, slots, rleaf, rroot = [], [], [], []
     for q in mine["neigh"]:
@@ -114,7 +115,7 @@ def connect_peers(pc, sf, rank, allgather):
         kq = other["neigh"].index(rank)
         handles.append(other["handles"])
         slots.append(kq)
-        rleaf.append(other["recv_leaf"][other["recv_off"][kq]:other["recv_off"][kq + 1]])
+        rleaf.append(other["recv_leaf"][other["recv_off"][kq]:other["recv_off"][kq + 1]] - other["nowned"])   # ghost slot numbers
         rroot.append(other["send_root"][other["send_off"][kq]:other["send_off"][kq + 1]])
     cat = lambda xs: np.concatenate(xs).astype(IntType) if xs else np.zeros(0, dtype=IntType)   # noqa: E731
     pc.peerConnect(handles, slots, cat(rleaf), cat(rroot))
