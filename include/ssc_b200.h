@@ -162,7 +162,9 @@ int SSCDeviceFree(SSCPatchPC pc, void *ptr);
 int SSCHostAlloc(SSCPatchPC pc, SSCInt bytes, void **ptr);  /* pinned */
 int SSCHostFree(SSCPatchPC pc, void *ptr);
 int SSCMemcpy(SSCPatchPC pc, void *dst, const void *src, SSCInt bytes, int dstSpace, int srcSpace);
-int SSCDeviceFlushL2(SSCPatchPC pc);                        /* overwrite a buffer larger than L2 (bench hygiene) */
+int SSCDeviceFlushL2(SSCPatchPC pc);
+/* streaming-read bandwidth (GB/s) of this GPU over the resident blocks: roofline calibration, best of `reps` passes */
+int SSCDeviceMeasureReadBandwidth(SSCPatchPC pc, int reps, double *gbs);                        /* overwrite a buffer larger than L2 (bench hygiene) */
 /* CUDA events on the PC's stream */
 int SSCEventCreate(SSCPatchPC pc, void **ev);
 int SSCEventRecord(SSCPatchPC pc, void *ev);

@@ -71,6 +71,7 @@ _sigs = {
     "SSCHostFree": [_H, C.c_void_p],
     "SSCMemcpy": [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int],
     "SSCDeviceFlushL2": [_H],
+    "SSCDeviceMeasureReadBandwidth": [_H, C.c_int, f64p],
     "SSCEventCreate": [_H, C.POINTER(C.c_void_p)],
     "SSCEventRecord": [_H, C.c_void_p],
     "SSCEventElapsed": [_H, C.c_void_p, C.c_void_p, f64p],

@@ -1639,6 +1639,37 @@ extern "C" int SSCDeviceFlushL2(SSCPatchPC pc)
     CUDA_OK(cudaGetLastError());
     return 0;
 }
+// Streaming-read bandwidth of this GPU in GB/s, measured by summing the resident patch blocks (or a 4 GiB scratch buffer
+// when no blocks are resident) `reps` times: the read-only counterpart of the copy-measured peak in MEASURED_PEAKS.json.
+extern "C" int SSCDeviceMeasureReadBandwidth(SSCPatchPC pc, int reps, double *gbs)
+{
+    CHK(set_device(pc));
+    const double *buf = pc->symmetric ? pc->d_packed : pc->d_blocks;
+    i64 elems = pc->symmetric ? pc->packed_elems : pc->block_elems;
+    double *scratch = nullptr;
+    if (!buf || elems < ((i64)1 << 27)) {
+        elems = (i64)1 << 29;
+        CHK(dev_alloc(&scratch, elems));
+        CUDA_OK(cudaMemsetAsync(scratch, 0, (size_t)elems * sizeof(double), pc->stream));
+        buf = scratch;
+    }
+    double *sink = nullptr;
+    CHK(dev_alloc(&sink, 1));
+    const ll n2 = elems / 2;
+    float best = 1e30f;
+    for (int r = 0; r < std::max(reps, 1) + 1; ++r) {
+        CUDA_OK(cudaEventRecord(pc->ev0, pc->stream));
+        ssc_stream_read_kernel<<<pc->sm_count * 32, 256, 0, pc->stream>>>(reinterpret_cast<const double2 *>(buf), n2, sink);
+        CUDA_OK(cudaEventRecord(pc->ev1, pc->stream));
+        CUDA_OK(cudaEventSynchronize(pc->ev1));
+        float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, pc->ev0, pc->ev1));
+        if (r > 0) best = std::min(best, ms);
+    }
+    *gbs = (double)n2 * 16.0 / (best * 1e-3) / 1e9;
+    cudaFree(sink);
+    if (scratch) cudaFree(scratch);
+    return 0;
+}
 extern "C" int SSCEventCreate(SSCPatchPC pc, void **ev) { CHK(set_device(pc)); cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); *ev = e; return 0; }
 extern "C" int SSCEventRecord(SSCPatchPC pc, void *ev) { CHK(set_device(pc)); CUDA_OK(cudaEventRecord((cudaEvent_t)ev, pc->stream)); return 0; }
 extern "C" int SSCEventElapsed(SSCPatchPC pc, void *start, void *stop, double *ms)

@@ -1151,3 +1151,19 @@ __global__ void ssc_peer_fold_kernel(ll n, const int *__restrict__ iface, double
         yin[d] = 0.0;
     }
 }
+
+// calibration: plain streaming read (sum) of a buffer, the read-only counterpart of the driver's copy-measured HBM peak
+__global__ void __launch_bounds__(256)
+ssc_stream_read_kernel(const double2 *__restrict__ a, ll n2, double *__restrict__ sink)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const ll stride = (ll)gridDim.x * blockDim.x;
+    ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n2; i += 4 * stride) {
+        const double2 v0 = __ldcs(a + i), v1 = __ldcs(a + i + stride), v2 = __ldcs(a + i + 2 * stride), v3 = __ldcs(a + i + 3 * stride);
+        s0 += v0.x + v0.y; s1 += v1.x + v1.y; s2 += v2.x + v2.y; s3 += v3.x + v3.y;
+    }
+    for (; i < n2; i += stride) { const double2 v = __ldcs(a + i); s0 += v.x + v.y; }
+    const double s = (s0 + s1) + (s2 + s3);
+    if (s == 1.2345678e300) sink[0] = s;          // keeps the loads alive without a store per thread
+}

@@ -357,6 +357,11 @@ class PC(object):
         CHKERR(lib.SSCPatchKernelTimerRead(self.handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def measureReadBandwidth(self, reps=5):
+        v = C.c_double(0)
+        CHKERR(lib.SSCDeviceMeasureReadBandwidth(self.handle, int(reps), C.byref(v)))
+        return v.value
+
     def flushL2(self):
         CHKERR(lib.SSCDeviceFlushL2(self.handle))
 
