@@ -537,7 +537,17 @@ extern "C" int SSCPatchSetPatches(SSCPatchPC pc, SSCInt npatch, const SSCInt *of
     L.gtolOff.assign(offsets, offsets + npatch + 1);
     L.gtol.assign(gtol, gtol + offsets[npatch]);
     L.cellOff.assign(npatch + 1, 0);
+    if (offsets[0] != 0) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "offsets[0] must be 0");
+    for (i64 p = 0; p < npatch; ++p) if (offsets[p + 1] < offsets[p]) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "patch offsets must not decrease (patch %lld)", (long long)p);
     for (i64 g : L.gtol) if (g < 0 || g >= nlocal) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "patch dof %lld outside [0,%lld)", (long long)g, (long long)nlocal);
+    {   // a dof may appear once per patch (the reference's hash map guarantees it, ssc/libssc.c:763-767)
+        std::vector<i64> stamp((size_t)std::max<i64>(nlocal, 1), -1);
+        for (i64 p = 0; p < npatch; ++p)
+            for (i64 k = offsets[p]; k < offsets[p + 1]; ++k) {
+                if (stamp[(size_t)gtol[k]] == p) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "dof %lld is listed twice in patch %lld", (long long)gtol[k], (long long)p);
+                stamp[(size_t)gtol[k]] = p;
+            }
+    }
     pc->nlocal = nlocal;
     if (!pc->sf_set) pc->nowned = nowned;
     pc->globalBc.assign(globalBcNodes, globalBcNodes + numGlobalBcs);

@@ -95,3 +95,13 @@ def test_setup_without_inputs_is_an_error():
     with pytest.raises(SSCError) as e:
         pc.buildPatches()
     assert "DM not yet set on patch PC" in e.value.message                             # ssc/libssc.c:475
+
+
+def test_set_patches_validates_input():
+    from ssc_b200 import PC, SSCError
+    pc = PC(device=-1)
+    pc.setPatches([0, 2, 3], [0, 1, 1], 4)                       # fine: dof 1 in two different patches
+    for off, g in (([0, 2, 1], [0, 1]), ([1, 2], [0, 1]), ([0, 2], [3, 3]), ([0, 1], [-1]), ([0, 1], [9])):
+        with pytest.raises(SSCError) as e:
+            pc.setPatches(off, g, 4)
+        assert e.value.ierr == 63
