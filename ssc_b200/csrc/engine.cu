@@ -8,6 +8,7 @@
 #include "../../include/ssc_b200.h"
 #include "common.h"
 #include "kernels.cuh"
+#include "patch_builder_device.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -157,6 +158,9 @@ struct SSCPatchPC_s {
     std::vector<std::vector<std::pair<i64, i64>>> colour_ranges;    // [colour][class] -> sorted positions
     double *d_r = nullptr;
     bool deterministic = false;      // slot-and-sum instead of atomics
+    bool device_construct = false;   // -ssc_device_patch_construction: build star patches on the GPU (N2); default: host builder
+                                     // (measured no faster end to end: the lists have to come back to the host, profiles/README.md)
+    bool lists_from_device = false;
     bool symmetric = false;          // packed lower triangle of the (symmetric) inverse only
     bool sym_bulk = true;            // packed apply: TMA bulk copy (true, 3.24 ms at 64^3 Q3) or per-thread cp.async (false, 4.46 ms)
     bool sym_persistent = false;     // persistent ring-buffered form of the packed apply kernel (measured slower: profiles/README.md)
@@ -424,6 +428,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     }
     if (name == "ssc_symmetric_persistent") return parse_bool(v, &pc->sym_persistent);
     if (name == "ssc_symmetric_bulk_copy") return parse_bool(v, &pc->sym_bulk);
+    if (name == "ssc_device_patch_construction") { CHK(parse_bool(v, &pc->device_construct)); pc->lists_valid = false; return 0; }
     if (name == "ssc_deterministic") {
         bool f = false;
         CHK(parse_bool(v, &f));
@@ -1489,6 +1494,7 @@ extern "C" int SSCPatchGetSize(SSCPatchPC pc, const char *what, SSCInt *value)
     else if (w == "num_dofs") *value = (i64)pc->lists.dofs.size();
     else if (w == "num_classes") *value = (i64)pc->classes.size();
     else if (w == "num_colours") *value = pc->ncolours;
+    else if (w == "lists_from_device") *value = pc->lists_from_device ? 1 : 0;
     else if (w == "block_bytes") *value = (pc->symmetric ? pc->packed_elems : pc->block_elems) * 8;
     else if (w == "bytes_apply") *value = (pc->symmetric ? 4 * (pc->sum_n2 + pc->sum_n) : 8 * pc->sum_n2) + (4 + 8 + 8) * pc->sum_n + 16 * pc->nowned;   // SURVEY.md 8(d); packed: 4 sum n(n+1)
     else if (w == "bytes_extract") { if (pc->csr_set && pc->csr_space == SSC_MEM_HOST) nnz = pc->csr_rowptr[pc->csr_nrows]; *value = 12 * nnz + 8 * (pc->nlocal + 1) + 4 * pc->sum_n + 8 * pc->sum_n2; }
@@ -1499,9 +1505,137 @@ extern "C" int SSCPatchGetSize(SSCPatchPC pc, const char *what, SSCInt *value)
     return 0;
 }
 
+// N2: star patches built on the device.  Returns 0 when pc->lists was filled, 1 when the case is not covered (or a patch
+// did not fit the kernel's shared-memory tables) and the host builder must run, an error code otherwise.
+static int build_lists_on_device(PC *pc)
+{
+    using namespace devbuild;
+    const HostPlex &P = pc->plex;
+    const Discretisation &D = pc->disc;
+    const BuildOptions &O = pc->bopt;
+    if (pc->device < 0 || !pc->device_construct || !P.set || !D.set || !D.cn_set) return 1;
+    if (O.construct_type != 0 || O.exclude_subspace >= 0 || O.keep_dofs || O.print_patches || D.nsub > kMaxSub) return 1;
+    const i64 nlocal = D.subspaceOffsets[D.nsub];
+    if (nlocal > 2147483647LL || P.pEnd > 2147483647LL || (i64)P.cones.size() > 2147483647LL) return 1;
+    const i64 cStart = P.depthStart[P.dim], cEnd = P.depthEnd[P.dim];
+    i64 vStart, vEnd;
+    if (O.codim < 0) { const i64 d = O.dim < 0 ? 0 : O.dim; if (d > P.dim) return 1; vStart = P.depthStart[d]; vEnd = P.depthEnd[d]; }
+    else { if (O.codim > P.dim) return 1; vStart = P.depthStart[P.dim - O.codim]; vEnd = P.depthEnd[P.dim - O.codim]; }
+    const i64 np = vEnd - vStart;
+    if (np < 4096) return 1;                                        // small meshes: the host builder is instant
+    i64 ncellrows = 0;
+    for (i64 c = cStart; c < cEnd; ++c) { if (D.cnDof[c] <= 0) return 1; ncellrows = std::max(ncellrows, D.cnOff[c] + 1); }
+    for (i64 g : D.ghostBcNodes) if (g < 0 || g >= nlocal) return 1;
+    CHK(set_device(pc));
+    std::vector<void *> tmp;                                         // every device temporary, freed at the end
+    auto cleanup = [&]() { for (void *q : tmp) cudaFree(q); };
+    auto up64 = [&](const i64 *src, i64 n, int **dst) -> int {       // upload int64, narrow on the device
+        i64 *d64 = nullptr; int *d32 = nullptr;
+        if (dev_alloc(&d64, n) || dev_alloc(&d32, n)) return SSC_ERR_MEM;
+        tmp.push_back(d64); tmp.push_back(d32);
+        if (n) {
+            if (cudaMemcpyAsync(d64, src, (size_t)n * sizeof(i64), cudaMemcpyHostToDevice, pc->stream) != cudaSuccess) return SSC_ERR_GPU;
+            narrow_kernel<<<grid_for(n, 256), 256, 0, pc->stream>>>(n, (const long long *)d64, d32);
+        }
+        *dst = d32;
+        return 0;
+    };
+#define UP(src, n, dst) do { int rc_ = up64(src, n, dst); if (rc_) { cleanup(); return ssc_set_error(rc_, "device patch construction: upload failed"); } } while (0)
+    Topo T;
+    memset(&T, 0, sizeof(T));
+    int *d;
+    UP(P.coneOff.data(), P.pEnd + 1, &d); T.coneOff = d;
+    UP(P.cones.data(), (i64)P.cones.size(), &d); T.cones = d;
+    UP(P.suppOff.data(), P.pEnd + 1, &d); T.suppOff = d;
+    UP(P.supports.data(), (i64)P.supports.size(), &d); T.supports = d;
+    UP(D.cnOff.data(), P.pEnd, &d); T.cnOff = d;
+    unsigned char *d_ghost = nullptr, *d_bc = nullptr;
+    if (!P.ghost.empty()) {
+        if (dev_alloc(&d_ghost, P.pEnd)) { cleanup(); return SSC_ERR_MEM; }
+        tmp.push_back(d_ghost);
+        cudaMemcpyAsync(d_ghost, P.ghost.data(), (size_t)P.pEnd, cudaMemcpyHostToDevice, pc->stream);
+    }
+    T.ghost = d_ghost;
+    {
+        std::vector<unsigned char> isbc((size_t)nlocal, 0);
+        for (i64 g : D.ghostBcNodes) isbc[(size_t)g] = 1;
+        if (dev_alloc(&d_bc, nlocal)) { cleanup(); return SSC_ERR_MEM; }
+        tmp.push_back(d_bc);
+        cudaMemcpy(d_bc, isbc.data(), (size_t)nlocal, cudaMemcpyHostToDevice);
+    }
+    T.isBc = d_bc;
+    T.cStart = (int)cStart; T.cEnd = (int)cEnd; T.vStart = (int)vStart; T.npatch = (int)np; T.nlocal = (int)nlocal; T.nsub = (int)D.nsub;
+    for (i64 k = 0; k < D.nsub; ++k) {
+        UP(D.secDof[k].data(), P.pEnd, &d); T.secDof[k] = d;
+        UP(D.secOff[k].data(), P.pEnd, &d); T.secOff[k] = d;
+        UP(D.cellNodeMap[k], ncellrows * D.nodesPerCell[k], &d); T.cnm[k] = d;
+        T.bs[k] = (int)D.bs[k]; T.npc[k] = (int)D.nodesPerCell[k]; T.subOff[k] = (int)D.subspaceOffsets[k];
+    }
+#undef UP
+    int *d_gc = nullptr, *d_cc = nullptr, *d_over = nullptr;
+    if (dev_alloc(&d_gc, np) || dev_alloc(&d_cc, np) || dev_alloc(&d_over, 1)) { cleanup(); return SSC_ERR_MEM; }
+    tmp.push_back(d_gc); tmp.push_back(d_cc); tmp.push_back(d_over);
+    cudaMemsetAsync(d_over, 0, sizeof(int), pc->stream);
+    cudaFuncSetAttribute(build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaFuncSetAttribute(build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    const int grid = (int)std::min<i64>(np, (i64)pc->sm_count * 16);
+    build_kernel<false><<<grid, kThreads, kSmemBytes, pc->stream>>>(T, d_gc, d_cc, nullptr, nullptr, nullptr, nullptr, d_over);
+    pc->launches++;
+    std::vector<int> gc((size_t)np), cc((size_t)np);
+    int over = 0;
+    if (cudaMemcpyAsync(gc.data(), d_gc, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost, pc->stream) != cudaSuccess ||
+        cudaMemcpyAsync(cc.data(), d_cc, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost, pc->stream) != cudaSuccess ||
+        cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, pc->stream) != cudaSuccess ||
+        cudaStreamSynchronize(pc->stream) != cudaSuccess) {
+        cudaError_t err = cudaGetLastError();
+        cleanup();
+        return ssc_set_error(SSC_ERR_GPU, "device patch construction failed: %s", cudaGetErrorString(err));
+    }
+    if (over) { cleanup(); return 1; }
+    PatchLists &L = pc->lists;
+    L = PatchLists();
+    L.npatch = np; L.vStart = vStart;
+    L.gtolOff.assign((size_t)np + 1, 0); L.cellOff.assign((size_t)np + 1, 0);
+    for (i64 p = 0; p < np; ++p) { L.gtolOff[(size_t)p + 1] = L.gtolOff[(size_t)p] + gc[(size_t)p]; L.cellOff[(size_t)p + 1] = L.cellOff[(size_t)p] + cc[(size_t)p]; }
+    const i64 ng = L.gtolOff[(size_t)np], ncl = L.cellOff[(size_t)np];
+    i64 *d_goff = nullptr, *d_coff = nullptr;
+    int *d_g = nullptr, *d_c = nullptr;
+    if (dev_alloc(&d_goff, np + 1) || dev_alloc(&d_coff, np + 1) || dev_alloc(&d_g, ng) || dev_alloc(&d_c, ncl)) { cleanup(); return SSC_ERR_MEM; }
+    tmp.push_back(d_goff); tmp.push_back(d_coff); tmp.push_back(d_g); tmp.push_back(d_c);
+    cudaMemcpyAsync(d_goff, L.gtolOff.data(), (size_t)(np + 1) * sizeof(i64), cudaMemcpyHostToDevice, pc->stream);
+    cudaMemcpyAsync(d_coff, L.cellOff.data(), (size_t)(np + 1) * sizeof(i64), cudaMemcpyHostToDevice, pc->stream);
+    build_kernel<true><<<grid, kThreads, kSmemBytes, pc->stream>>>(T, nullptr, nullptr, (const long long *)d_goff, (const long long *)d_coff, d_g, d_c, d_over);
+    pc->launches++;
+    std::vector<int> g32((size_t)std::max<i64>(ng, 1)), c32((size_t)std::max<i64>(ncl, 1));
+    if (cudaMemcpyAsync(g32.data(), d_g, (size_t)ng * sizeof(int), cudaMemcpyDeviceToHost, pc->stream) != cudaSuccess ||
+        cudaMemcpyAsync(c32.data(), d_c, (size_t)ncl * sizeof(int), cudaMemcpyDeviceToHost, pc->stream) != cudaSuccess ||
+        cudaStreamSynchronize(pc->stream) != cudaSuccess) {
+        cudaError_t err = cudaGetLastError();
+        cleanup();
+        return ssc_set_error(SSC_ERR_GPU, "device patch construction failed: %s", cudaGetErrorString(err));
+    }
+    cleanup();
+    L.gtol.resize((size_t)ng); L.cells.resize((size_t)ncl);
+    {   // widen to PetscInt with a few threads
+        const int Tn = 8;
+        std::vector<std::thread> th;
+        for (int t = 0; t < Tn; ++t) th.emplace_back([&, t]() {
+            for (i64 i = ng * t / Tn; i < ng * (t + 1) / Tn; ++i) L.gtol[(size_t)i] = g32[(size_t)i];
+            for (i64 i = ncl * t / Tn; i < ncl * (t + 1) / Tn; ++i) L.cells[(size_t)i] = c32[(size_t)i];
+        });
+        for (auto &x : th) x.join();
+    }
+    pc->lists_from_device = true;
+    return 0;
+}
+
 static int need_lists(PC *pc)
 {
     if (pc->lists_valid) return 0;
+    pc->lists_from_device = false;
+    const int rc = build_lists_on_device(pc);
+    if (rc == 0) { pc->lists_valid = true; return 0; }
+    if (rc != 1) return rc;
     CHK(ssc_build_patches(pc->plex, pc->disc, pc->user, pc->bopt, pc->lists));
     pc->lists_valid = true;
     if (pc->print_patches) fputs(pc->lists.printout.c_str(), stdout);     // PetscSynchronizedPrintf of ssc/libssc.c:679-728
