@@ -118,3 +118,31 @@ def test_unsupported_combinations_are_errors():
     # out-of-range dof in a patch list
     with pytest.raises(SSCError):
         PC(device=0).setPatches([0, 1], [N + 5], N)
+
+
+def test_degenerate_inputs():
+    """No patches at all / only empty patches: PCApply is zero on free dofs and the identity on Dirichlet dofs."""
+    from ssc_b200 import PC
+    import scipy.sparse as sp
+    N = 10
+    A = sp.identity(N, format="csr")
+    x = rhs_vector(N)
+    for off in ([0], [0, 0, 0]):
+        pc = PC(device=0)
+        pc.setPatches(off, [], N, global_bc_nodes=[2, 7])
+        pc.setOperatorCSR(A.indptr, A.indices, A.data)
+        pc.setUp()
+        y = np.full(N, np.nan)
+        pc.apply(x, y)
+        ref = np.zeros(N)
+        ref[[2, 7]] = x[[2, 7]]
+        assert np.array_equal(y, ref)
+        assert pc.size("sum_n") == 0 and pc.size("num_classes") == 0
+    # a single 1x1 patch
+    pc = PC(device=0)
+    pc.setPatches([0, 1], [4], N)
+    pc.setOperatorCSR((A * 4.0).indptr, A.indices, (A * 4.0).data)
+    pc.setUp()
+    y = np.zeros(N)
+    pc.apply(x, y)
+    assert y[4] == x[4] / 4.0 and np.count_nonzero(y) == 1
