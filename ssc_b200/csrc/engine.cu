@@ -1011,7 +1011,7 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
     int H = 32;
     while (H < 2 * n) H <<= 1;
     const int bd = 128, nw = bd / 32;
-    const size_t smem_e = (size_t)H * 2 * sizeof(int) + (size_t)nw * n * sizeof(double);
+    const size_t smem_e = (size_t)H * 2 * sizeof(int) + (size_t)n * sizeof(i64) + (size_t)((n + 2) & ~1) * sizeof(int) + (size_t)2 * nw * n * sizeof(double);
     if (smem_e > 200 * 1024) return ssc_set_error(SSC_ERR_SUP, "patch with %d dofs is too large for the extract kernel", n);
     if (smem_e > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
     if (time_it) CUDA_OK(cudaEventRecord(pc->ev0, pc->stream));

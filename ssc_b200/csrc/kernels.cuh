@@ -61,14 +61,20 @@ ssc_extract_kernel(const ll *__restrict__ rowptr, const int *__restrict__ colidx
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *keys = reinterpret_cast<int *>(smem_raw);
     int *slotval = keys + H;
-    double *rowbuf = reinterpret_cast<double *>(slotval + H);
+    ll *rbeg = reinterpret_cast<ll *>(slotval + H);            // n: start of every patch row in the CSR arrays
+    int *rlen = reinterpret_cast<int *>(rbeg + n);            // n (+1 pad): its length
+    double *rowbuf = reinterpret_cast<double *>(rlen + ((n + 2) & ~1));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     for (ll p = blockIdx.x; p < count; p += gridDim.x) {
         const int *g = gtol + p * n;
         for (int t = tid; t < H; t += blockDim.x) keys[t] = -1;
         __syncthreads();
+        // one round of dependent loads for the whole patch: dof -> row extent; and the column hash
         for (int t = tid; t < n; t += blockDim.x) {
             const int key = g[t];
+            const ll a = rowptr[key];
+            rbeg[t] = a;
+            rlen[t] = (int)(rowptr[key + 1] - a);
             unsigned s = hash_dof(key) & (H - 1);
             while (true) {
                 const int prev = atomicCAS(&keys[s], -1, key);
@@ -78,23 +84,37 @@ ssc_extract_kernel(const ll *__restrict__ rowptr, const int *__restrict__ colidx
         }
         __syncthreads();
         double *B = blocks + p * stride;
-        double *rb = rowbuf + warp * n;
-        for (int i = warp; i < n; i += nwarps) {
-            for (int t = lane; t < n; t += 32) rb[t] = 0.0;
+        // a warp owns two output rows at a time: both rows' index/value loads are issued before either is consumed
+        double *rb0 = rowbuf + (2 * warp) * n, *rb1 = rb0 + n;
+        for (int i0 = 2 * warp; i0 < n; i0 += 2 * nwarps) {
+            const int i1 = i0 + 1;
+            const bool two = i1 < n;
+            for (int t = lane; t < n; t += 32) { rb0[t] = 0.0; rb1[t] = 0.0; }
             __syncwarp();
-            const int grow = g[i];
-            const ll a = rowptr[grow], b = rowptr[grow + 1];
-            for (ll k = a + lane; k < b; k += 32) {
-                const int col = colidx[k];
-                unsigned s = hash_dof(col) & (H - 1);
-                int kk;
-                while ((kk = keys[s]) != -1) {
-                    if (kk == col) { atomicAdd(&rb[slotval[s]], vals[k]); break; }
-                    s = (s + 1) & (H - 1);
+            const ll a0 = rbeg[i0], a1 = two ? rbeg[i1] : 0;
+            const int l0 = rlen[i0], l1 = two ? rlen[i1] : 0;
+            const int lmax = l0 > l1 ? l0 : l1;
+            for (int k = lane; k < lmax; k += 32) {
+                int c0 = -1, c1 = -1;
+                double v0 = 0.0, v1 = 0.0;
+                if (k < l0) { c0 = colidx[a0 + k]; v0 = vals[a0 + k]; }
+                if (k < l1) { c1 = colidx[a1 + k]; v1 = vals[a1 + k]; }
+                if (c0 >= 0) {
+                    unsigned s = hash_dof(c0) & (H - 1);
+                    int kk;
+                    while ((kk = keys[s]) != -1) { if (kk == c0) { atomicAdd(&rb0[slotval[s]], v0); break; } s = (s + 1) & (H - 1); }
+                }
+                if (c1 >= 0) {
+                    unsigned s = hash_dof(c1) & (H - 1);
+                    int kk;
+                    while ((kk = keys[s]) != -1) { if (kk == c1) { atomicAdd(&rb1[slotval[s]], v1); break; } s = (s + 1) & (H - 1); }
                 }
             }
             __syncwarp();
-            for (int t = lane; t < ld; t += 32) B[(ll)i * ld + t] = t < n ? rb[t] : 0.0;
+            for (int t = lane; t < ld; t += 32) {
+                B[(ll)i0 * ld + t] = t < n ? rb0[t] : 0.0;
+                if (two) B[(ll)i1 * ld + t] = t < n ? rb1[t] : 0.0;
+            }
             __syncwarp();
         }
         __syncthreads();
