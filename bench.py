@@ -292,6 +292,10 @@ def main():
              "factor_ms": pc.eventTime("PCPATCHSolve"), "lists_ms": pc.eventTime("SSCSetupLists"), "upload_operator_ms": pc.eventTime("SSCSetupUploadOperator"),
              "alloc_blocks_ms": pc.eventTime("SSCSetupAllocBlocks"), "setup_wall_s": info["t_setup_wall"],
              "assemble_wall_s": info["t_assemble"], "mesh_wall_s": info["t_mesh"]}
+    if setup["extract_ms"] > 0:
+        setup["extract_gbs"] = pc.size("bytes_extract") / (setup["extract_ms"] * 1e-3) / 1e9      # algorithmic bytes of SURVEY.md 8(d)
+    if setup["factor_ms"] > 0:
+        setup["factor_tflops"] = pc.size("flops_factor") / (setup["factor_ms"] * 1e-3) / 1e12     # 2 n^3 per block (fp64)
     nowned = pc.size("nowned")
     nglobal = nowned
     if nranks > 1:
