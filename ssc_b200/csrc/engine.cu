@@ -143,7 +143,7 @@ struct SSCPatchPC_s {
     int *d_timeout = nullptr;
     std::vector<void *> ipc_opened;
     // operator (borrowed)
-    i64 csr_nrows = 0;
+    i64 csr_nrows = 0, csr_nnz = 0;
     const i64 *csr_rowptr = nullptr;
     const int32_t *csr_colidx = nullptr;
     const double *csr_vals = nullptr;
@@ -986,6 +986,7 @@ static int upload_csr(PC *pc)
         return 0;
     }
     const i64 nnz = pc->csr_rowptr[pc->csr_nrows];
+    pc->csr_nnz = nnz;
     CHK(dev_alloc(&pc->d_rowptr, pc->csr_nrows + 1));
     CHK(dev_alloc(&pc->d_colidx, nnz));
     CHK(dev_alloc(&pc->d_vals, nnz));
@@ -1497,7 +1498,7 @@ extern "C" int SSCPatchGetSize(SSCPatchPC pc, const char *what, SSCInt *value)
     else if (w == "lists_from_device") *value = pc->lists_from_device ? 1 : 0;
     else if (w == "block_bytes") *value = (pc->symmetric ? pc->packed_elems : pc->block_elems) * 8;
     else if (w == "bytes_apply") *value = (pc->symmetric ? 4 * (pc->sum_n2 + pc->sum_n) : 8 * pc->sum_n2) + (4 + 8 + 8) * pc->sum_n + 16 * pc->nowned;   // SURVEY.md 8(d); packed: 4 sum n(n+1)
-    else if (w == "bytes_extract") { if (pc->csr_set && pc->csr_space == SSC_MEM_HOST) nnz = pc->csr_rowptr[pc->csr_nrows]; *value = 12 * nnz + 8 * (pc->nlocal + 1) + 4 * pc->sum_n + 8 * pc->sum_n2; }
+    else if (w == "bytes_extract") { nnz = pc->csr_nnz; *value = 12 * nnz + 8 * (pc->nlocal + 1) + 4 * pc->sum_n + 8 * pc->sum_n2; }   // nnz as of the last host-space SetUp
     else if (w == "flops_factor") { i64 f = 0; for (auto &c : pc->classes) f += 2 * c.count * (i64)c.n * c.n * c.n; *value = f; }
     else if (w == "failed_patches") *value = pc->failed;
     else if (w == "gpu_launches") *value = pc->launches;
