@@ -715,10 +715,19 @@ static int build_device_lists(PC *pc)
     if (pc->nlocal > 2147483647LL) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "local vector too long for 32-bit device indices");
     // dof lists in sorted order, int32
     std::vector<int> g32((size_t)pc->sum_n);
-    i64 w = 0;
-    for (i64 q = 0; q < (i64)order.size(); ++q) {
-        const i64 p = order[q];
-        for (i64 k = L.gtolOff[p]; k < L.gtolOff[p + 1]; ++k) g32[w++] = (int)L.gtol[k];
+    {
+        std::vector<i64> woff(order.size() + 1, 0);              // write offset of every sorted patch
+        for (size_t q = 0; q < order.size(); ++q) woff[q + 1] = woff[q] + (L.gtolOff[(size_t)order[q] + 1] - L.gtolOff[(size_t)order[q]]);
+        const int Tn = (int)std::min<size_t>(8, std::max<size_t>(1, order.size() / 4096));
+        auto work = [&](int t) {
+            for (size_t q = order.size() * t / Tn; q < order.size() * (t + 1) / Tn; ++q) {
+                const i64 p = order[q];
+                i64 w = woff[q];
+                for (i64 k = L.gtolOff[(size_t)p]; k < L.gtolOff[(size_t)p + 1]; ++k) g32[(size_t)w++] = (int)L.gtol[(size_t)k];
+            }
+        };
+        if (Tn == 1) work(0);
+        else { std::vector<std::thread> th; for (int t = 0; t < Tn; ++t) th.emplace_back(work, t); for (auto &x : th) x.join(); }
     }
     CHK(dev_alloc(&pc->d_gtol, pc->sum_n));
     if (pc->sum_n) CUDA_OK(cudaMemcpyAsync(pc->d_gtol, g32.data(), (size_t)pc->sum_n * sizeof(int), cudaMemcpyHostToDevice, pc->stream));
