@@ -395,3 +395,22 @@ def test_device_patch_construction_matches_host_and_oracle(case):
     for a, b in zip(out[True][0] + out[True][1], out[False][0] + out[False][1]):
         assert np.array_equal(a, b)
     assert out[True][0][0][-1] > 0
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_p_sweep_on_triangles(p):
+    """BASELINE.json configs[1]: 2D Poisson P_p, p = 1..8, vertex-star patches (interior n = 1, 7, 19, 37, 61, 91, 127, 169:
+    every factor kernel is hit -- register tiles up to 128, the blocked DMMA kernel above)."""
+    mesh = plex.UnitSquareMesh(6, 6)
+    form, bcs, disc, A = _problem(mesh, p, "scalar")
+    o = make_oracle(disc, A)
+    pc = make_gpu(form, bcs)
+    pc.setUp()
+    off, gtol = pc.getPatches()
+    assert all(np.array_equal(a, b) for a, b in zip(o.patches(), (off, gtol)))
+    assert np.diff(off).max() == 1 + 6 * (p - 1) + 3 * (p - 1) * (p - 2)
+    x = rhs_vector(disc.total_dofs)
+    y = np.zeros_like(x)
+    pc.apply(x, y)
+    # equispaced Lagrange bases get ill-conditioned with p: the bound is the tolerance of north_star up to p = 6
+    assert relerr(y, o.apply(x)) < (1e-12 if p <= 6 else 1e-10)
