@@ -162,6 +162,7 @@ struct SSCPatchPC_s {
                                      // (measured no faster end to end: the lists have to come back to the host, profiles/README.md)
     bool lists_from_device = false;
     bool symmetric = false;          // packed lower triangle of the (symmetric) inverse only
+    bool sym_two_chunk = false;      // packed apply: two bulk copies split at a column, two threads per row
     bool sym_bulk = true;            // packed apply: TMA bulk copy (true, 3.24 ms at 64^3 Q3) or per-thread cp.async (false, 4.46 ms)
     bool sym_persistent = false;     // persistent ring-buffered form of the packed apply kernel (measured slower: profiles/README.md)
     double *d_packed = nullptr;
@@ -428,6 +429,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     }
     if (name == "ssc_symmetric_persistent") return parse_bool(v, &pc->sym_persistent);
     if (name == "ssc_symmetric_bulk_copy") return parse_bool(v, &pc->sym_bulk);
+    if (name == "ssc_symmetric_two_chunk") return parse_bool(v, &pc->sym_two_chunk);
     if (name == "ssc_device_patch_construction") { CHK(parse_bool(v, &pc->device_construct)); pc->lists_valid = false; return 0; }
     if (name == "ssc_deterministic") {
         bool f = false;
@@ -695,7 +697,7 @@ static int build_device_lists(PC *pc)
         for (SizeClass &c : pc->classes) { c.poff = po; po += c.count * c.pstride; }
         pc->packed_elems = po;
         if (pc->symmetric) for (const SizeClass &c : pc->classes)
-            if ((size_t)c.pbytes + (size_t)c.n * 8 > 225 * 1024) return ssc_set_error(SSC_ERR_SUP, "ssc_symmetric_storage holds a whole packed block in shared memory: patches up to 238 dofs (found %d)", c.n);
+            if ((size_t)c.pbytes + (size_t)(2 * c.n + 32) * 8 > 225 * 1024) return ssc_set_error(SSC_ERR_SUP, "ssc_symmetric_storage holds a whole packed block in shared memory: patches up to 238 dofs (found %d)", c.n);
     }
     if (pc->multiplicative) {
         pc->colour_ranges.assign((size_t)pc->ncolours, std::vector<std::pair<i64, i64>>(pc->classes.size(), {0, 0}));
@@ -1208,6 +1210,24 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
             CUDA_OK(cudaFuncSetAttribute(ssc_apply_sym_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
             ssc_apply_sym_persistent_kernel<<<pc->sm_count, threads_p, smem_p, pc->stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, stages, gt,
                                                                                         c.n, cnt, xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch);
+            pc->launches++;
+            CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+        if (pc->sym_bulk && pc->sym_two_chunk && 2 * ((c.n + 31) / 32 * 32) <= 1024) {
+            const int rp = (c.n + 31) / 32 * 32;
+            int j1 = c.n;                                       // split column: about half of the bytes, 16-byte aligned start
+            unsigned bytes0 = c.pbytes;
+            if (c.pbytes >= 8192) {
+                for (int j = (int)(0.2929 * c.n); j < c.n; ++j) {
+                    const i64 cs = (i64)j * c.n - (i64)j * (j - 1) / 2;
+                    if ((cs & 1) == 0) { j1 = j; bytes0 = (unsigned)(cs * 8); break; }
+                }
+            }
+            const size_t smem2 = (size_t)c.pbytes + (size_t)(c.n + rp) * sizeof(double);
+            if (smem2 > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_apply_sym2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            ssc_apply_sym2_kernel<<<(unsigned)cnt, 2 * rp, smem2, pc->stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, j1, bytes0, gt, c.n, cnt,
+                                                                           xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch);
             pc->launches++;
             CUDA_OK(cudaGetLastError());
             return 0;

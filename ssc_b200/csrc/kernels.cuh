@@ -1021,6 +1021,37 @@ __device__ __forceinline__ double sym_col_pass(const double *__restrict__ L, con
     return (a0 + a1) + (a2 + a3);
 }
 
+// sum over m = q (mod F), mlo <= m < mhi, of L[colstart(min(i, m)) + |i - m|] * x_m  -- one thread's share of y_i when F
+// threads split a row.  Indices advance incrementally: in the row part (m <= i) the step from m to m + F is
+// F (n - m - 1) - F (F - 1) / 2 and shrinks by F^2 each time; in the column part (m > i) it is F.
+__device__ __forceinline__ double sym_terms(const double *__restrict__ L, const double *__restrict__ xs, int n, int i, int q, int F, int mlo, int mhi)
+{
+    double a0 = 0.0, a1 = 0.0;
+    int m = mlo + ((q - mlo) % F + F) % F;
+    const int rend = min(mhi, i + 1);
+    if (m < rend) {
+        int idx = m * n - ((m * (m - 1)) >> 1) + (i - m);
+        int step = F * (n - m - 1) - ((F * (F - 1)) >> 1);
+        const int dstep = F * F;
+        for (; m + F < rend; m += 2 * F) {
+            const double l0 = L[idx];
+            const int idx1 = idx + step;
+            const double l1 = L[idx1];
+            a0 = fma(l0, xs[m], a0);
+            a1 = fma(l1, xs[m + F], a1);
+            idx = idx1 + step - dstep;
+            step -= 2 * dstep;
+        }
+        if (m < rend) { a0 = fma(L[idx], xs[m], a0); m += F; }
+    }
+    // column part: first m > i (and >= mlo) in this thread's residue class
+    if (m <= i) m += ((i - m) / F + 1) * F;
+    const double *col = L + (i * n - ((i * (i - 1)) >> 1) - i);
+    for (; m + F < mhi; m += 2 * F) { a0 = fma(col[m], xs[m], a0); a1 = fma(col[m + F], xs[m + F], a1); }
+    if (m < mhi) a0 = fma(col[m], xs[m], a0);
+    return a0 + a1;
+}
+
 __global__ void ssc_pack_sym_kernel(const double *__restrict__ blocks, int n, int ld, ll stride, double *__restrict__ packed, ll pstride, ll count)
 {
     for (ll p = blockIdx.x; p < count; p += gridDim.x) {
@@ -1072,6 +1103,60 @@ ssc_apply_sym_kernel(const double *__restrict__ packed, ll pstride, unsigned cop
     const double sc = mult ? scale * mult[p] : scale;
     for (int i = t; i < n; i += blockDim.x)
         emit(y, g[i], (sym_row_pass(L, xs, n, i) + sym_col_pass(L, xs, n, i)) * sc, ps, ypatch, p * n + i);
+}
+
+// Two-chunk, two-threads-per-row form of the packed apply (the default): the triangle arrives as two bulk copies split
+// at a column boundary j1 (about half the bytes each); everything that only needs columns < j1 is computed while the
+// second copy is still in flight, and the n terms of a row are shared by two threads.  With
+//   y_i = sum_m L[colstart(min(i, m)) + |i - m|] x_m
+// the terms available after the first chunk are exactly those with min(i, m) < j1.
+__global__ void __launch_bounds__(1024)
+ssc_apply_sym2_kernel(const double *__restrict__ packed, ll pstride, unsigned copy_bytes, int j1, unsigned bytes0, const int *__restrict__ gtol, int n,
+                      ll count, const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
+                      const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *L = reinterpret_cast<double *>(smem_raw);
+    double *xs = L + (copy_bytes >> 3);
+    double *ypart = xs + n;
+    __shared__ __align__(8) unsigned long long bar[2];
+    const ll p = blockIdx.x;
+    const int t = threadIdx.x;
+    const int rp = blockDim.x >> 1;                              // row slots; thread (i, q) = (t % rp, t / rp)
+    const unsigned bytes1 = copy_bytes - bytes0;
+    if (t == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0) {
+        const double *src = packed + p * pstride;
+        mbar_expect_tx(&bar[0], bytes0);
+        bulk_copy_g2s(L, src, bytes0, &bar[0]);
+        if (bytes1) {
+            mbar_expect_tx(&bar[1], bytes1);
+            bulk_copy_g2s(L + (bytes0 >> 3), src + (bytes0 >> 3), bytes1, &bar[1]);
+        }
+    }
+    const int *g = gtol + p * n;
+    for (int i = t; i < n; i += blockDim.x) xs[i] = gather_x(x, g[i], ps);
+    __syncthreads();
+    const int i = t < rp ? t : t - rp, q = t < rp ? 0 : 1;
+    const bool valid = i < n;
+    double a0 = 0.0, a1 = 0.0;
+    mbar_wait(&bar[0], 0);
+    if (valid) a0 = sym_terms(L, xs, n, i, q, 2, 0, i < j1 ? n : j1);          // everything with min(i, m) < j1
+    if (bytes1) {
+        mbar_wait(&bar[1], 0);
+        if (valid && i >= j1) a1 = sym_terms(L, xs, n, i, q, 2, j1, n);
+    }
+    if (q == 1 && valid) ypart[i] = a0 + a1;
+    __syncthreads();
+    if (q == 0 && valid) {
+        const double sc = mult ? scale * mult[p] : scale;
+        emit(y, g[i], (a0 + a1 + ypart[i]) * sc, ps, ypatch, p * n + i);
+    }
 }
 
 // Persistent form of the packed-symmetric apply: one CTA per SM walks its share of the patches with a ring of kStages
@@ -1135,17 +1220,8 @@ ssc_apply_sym_persistent_kernel(const double *__restrict__ packed, ll pstride, u
             const int i = t % rp, q = t / rp;
             double a0 = 0.0, a1 = 0.0;
             if (i < n && q < F) {
-                const int ci = i * n - ((i * (i - 1)) >> 1) - i;          // colstart(i) - i
-                int m = q;
-                for (; m + F < n; m += 2 * F) {
-                    const int m1 = m + F;
-                    const int i0 = m <= i ? m * n - ((m * (m - 1)) >> 1) + (i - m) : ci + m;
-                    const int i1 = m1 <= i ? m1 * n - ((m1 * (m1 - 1)) >> 1) + (i - m1) : ci + m1;
-                    a0 = fma(L[i0], xs[m], a0);
-                    a1 = fma(L[i1], xs[m1], a1);
-                }
-                if (m < n) { const int i0 = m <= i ? m * n - ((m * (m - 1)) >> 1) + (i - m) : ci + m; a0 = fma(L[i0], xs[m], a0); }
-                if (q > 0) ypart[(q - 1) * rp + i] = a0 + a1;
+                a0 = sym_terms(L, xs, n, i, q, F, 0, n);
+                if (q > 0) ypart[(q - 1) * rp + i] = a0;
             }
             __syncthreads();
             if (i < n && q == 0) {

@@ -339,9 +339,10 @@ def test_packed_symmetric_storage_needs_cholesky():
     assert e.value.ierr == 75
 
 
+@pytest.mark.parametrize("two_chunk", [True, False])
 @pytest.mark.parametrize("bulk", [True, False])
 @pytest.mark.parametrize("persistent", [True, False])
-def test_packed_symmetric_persistent_ring(persistent, bulk):
+def test_packed_symmetric_persistent_ring(persistent, bulk, two_chunk):
     """Enough patches of one size (> 8 per SM) to take the persistent ring-buffered form of the packed apply kernel."""
     from ssc_b200 import synth
     mesh = plex.TensorPlex((12, 12, 12))
@@ -351,7 +352,7 @@ def test_packed_symmetric_persistent_ring(persistent, bulk):
     r, c, v = synth.tensor_poisson_csr(V, disc.ghost_bc_nodes)
     A = sp.csr_matrix((v, c, r), shape=(V.node_count,) * 2)
     o = make_oracle(disc, A)
-    pc = make_gpu(disc, None, sub_pc_type="cholesky", ssc_symmetric_storage=True, ssc_symmetric_persistent=persistent, ssc_symmetric_bulk_copy=bulk)
+    pc = make_gpu(disc, None, sub_pc_type="cholesky", ssc_symmetric_storage=True, ssc_symmetric_persistent=persistent, ssc_symmetric_bulk_copy=bulk, ssc_symmetric_two_chunk=two_chunk)
     pc._compute_op = None
     pc.setOperatorCSR(r, c, v)
     pc.setUp()

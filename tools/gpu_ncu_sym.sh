@@ -20,5 +20,5 @@ python /tmp/run_sym.py true true > gpurun_out/plain_sym.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:ssc_apply_sym_persistent --launch-skip 2 --launch-count 1 -o gpurun_out/sym_persistent python /tmp/run_sym.py true true > gpurun_out/ncu_sym.log 2>&1
 echo "rc=$?"
 python /tmp/run_sym.py false true > gpurun_out/plain_sym2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:ssc_apply_sym_kernel --launch-skip 11 --launch-count 1 -o gpurun_out/sym_simple python /tmp/run_sym.py false true > gpurun_out/ncu_sym2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:ssc_apply_sym2_kernel --launch-skip 11 --launch-count 1 -o gpurun_out/sym_simple python /tmp/run_sym.py false true > gpurun_out/ncu_sym2.log 2>&1
 echo "rc=$?"
