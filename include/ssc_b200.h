@@ -114,6 +114,19 @@ int SSCPatchPeerConnect(SSCPatchPC pc, const char *neighHandles, const int *slot
 int SSCPatchSetOperatorCSR(SSCPatchPC pc, SSCInt nrows, const SSCInt *rowptr, const int32_t *colidx,
                            const double *vals, int memspace);
 
+/* The reference's own source of the patch operators: element matrices added cell by cell through the per-cell
+ * dof table with negative (BC) indices dropped -- PCPatchSetComputeOperator / PCPatchComputeOperator
+ * (ssc/libssc.h:8, ssc/libssc.c:1120-1156), the callback trampoline ssc/PatchPC.pyx:54-72 and the element kernel
+ * call ssc/patch.py:28-62, 210-213.  Ke holds one dofs_per_cell x dofs_per_cell row-major matrix per cell, rows of
+ * Ke indexed by the cell numbering (SSCPatchSetCellNumbering), cell dofs ordered subspace by subspace, node by node,
+ * component by component (the order of the dofs table, ssc/libssc.c:846-889); cell_stride is the distance in
+ * doubles between two cells' matrices, 0 = one matrix shared by all cells (congruent cells, constant coefficients).
+ * Replaces a previous SSCPatchSetOperatorCSR (and vice versa).  Borrowed until SSCPatchSetUp returns (until
+ * SSCPatchReset when save_operators is off).  The blocks are summed in the reference's order, cell after cell, so
+ * they are bit-identical to the oracle's element-wise assembly.  Needs patches built from the mesh (not
+ * SSCPatchSetPatches); multiplicative sweeps need the assembled operator instead. */
+int SSCPatchSetElementMatrices(SSCPatchPC pc, SSCInt ncells, SSCInt dofs_per_cell, const double *Ke, SSCInt cell_stride, int memspace);
+
 /* ---- setup and apply ----------------------------------------------------------------------- */
 int SSCPatchSetUp(SSCPatchPC pc);                         /* PCSetUp_PATCH ssc/libssc.c:1201-1299 (+ the lazy factorisation inside :1374) */
 /* PCApply_PATCH ssc/libssc.c:1301-1426: y = sum_p R_p^T B_p^{-1} R_p x on free dofs, y = x on owned Dirichlet dofs,

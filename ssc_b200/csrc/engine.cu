@@ -188,6 +188,18 @@ struct SSCPatchPC_s {
     int *d_colidx = nullptr;
     double *d_vals = nullptr;
     bool csr_owned = false;
+    // element matrices (the reference's own source of the patch operators, ssc/libssc.c:1120-1156): borrowed like the CSR arrays
+    bool elem_set = false, elem_owned = false, elem_lists_ready = false;
+    bool asm_shared = false;         // assemble kernel: accumulate in place through L2 (13.7 ms at 64^3 Q3) or in shared memory when the block fits (26 ms)
+    int asm_threads = 256;
+    const double *elem_K = nullptr;
+    i64 elem_ncells = 0, elem_t = 0, elem_stride = 0;
+    int elem_space = 0;
+    double *d_elemK = nullptr;
+    i64 *d_pcelloff = nullptr;       // cells of every patch, patches in size-sorted order
+    int *d_pcells = nullptr;
+    std::vector<int *> d_cnm;        // device copies of the cell-node maps
+    ElemSpaces espaces;
     void *d_flush = nullptr;
     void *stage[3] = {nullptr, nullptr, nullptr};      // pinned staging ring for large pageable uploads
     cudaEvent_t stage_ev[3] = {nullptr, nullptr, nullptr};
@@ -293,6 +305,11 @@ static void free_device_state(PC *pc)
     dev_free(pc->d_sendbuf); dev_free(pc->d_recvbuf);
     if (pc->csr_owned) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); }
     pc->d_rowptr = nullptr; pc->d_colidx = nullptr; pc->d_vals = nullptr; pc->csr_owned = false;
+    if (pc->elem_owned) dev_free(pc->d_elemK);
+    pc->d_elemK = nullptr; pc->elem_owned = false;
+    dev_free(pc->d_pcelloff); dev_free(pc->d_pcells);
+    for (int *&q : pc->d_cnm) dev_free(q);
+    pc->d_cnm.clear(); pc->elem_lists_ready = false;
     pc->classes.clear(); pc->device_ready = false; pc->setup_done = false; pc->pipe_ready = false;
 }
 
@@ -306,7 +323,7 @@ extern "C" int SSCPatchReset(SSCPatchPC pc)
     }
     pc->lists = PatchLists(); pc->lists_valid = false; pc->direct_patches = false;
     pc->plex = HostPlex(); pc->disc = Discretisation(); pc->user = UserPatches();
-    pc->csr_set = false; pc->sf_set = false;
+    pc->csr_set = false; pc->elem_set = false; pc->sf_set = false;
     return 0;
 }
 
@@ -430,6 +447,8 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_symmetric_persistent") return parse_bool(v, &pc->sym_persistent);
     if (name == "ssc_symmetric_bulk_copy") return parse_bool(v, &pc->sym_bulk);
     if (name == "ssc_symmetric_two_chunk") return parse_bool(v, &pc->sym_two_chunk);
+    if (name == "ssc_assemble_shared") return parse_bool(v, &pc->asm_shared);
+    if (name == "ssc_assemble_threads") { pc->asm_threads = atoi(v); if (pc->asm_threads != 128 && pc->asm_threads != 256 && pc->asm_threads != 512 && pc->asm_threads != 1024) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "ssc_assemble_threads must be 128, 256, 512 or 1024"); return 0; }
     if (name == "ssc_device_patch_construction") { CHK(parse_bool(v, &pc->device_construct)); pc->lists_valid = false; return 0; }
     if (name == "ssc_deterministic") {
         bool f = false;
@@ -606,6 +625,21 @@ extern "C" int SSCPatchSetOperatorCSR(SSCPatchPC pc, SSCInt nrows, const SSCInt 
     if (!rowptr || !colidx || !vals) return ssc_set_error(SSC_ERR_ARG_NULL, "null CSR array");
     pc->csr_nrows = nrows; pc->csr_rowptr = rowptr; pc->csr_colidx = colidx; pc->csr_vals = vals;
     pc->csr_space = memspace; pc->csr_set = true;
+    pc->elem_set = false;
+    return 0;
+}
+
+// The reference's route to the patch operators: one totalDofsPerCell x totalDofsPerCell matrix per cell, what its
+// compute-operator callback hands to MatSetValues cell by cell (ssc/libssc.c:1150, ssc/patch.py:28-62,210-213).
+extern "C" int SSCPatchSetElementMatrices(SSCPatchPC pc, SSCInt ncells, SSCInt dofs_per_cell, const double *Ke, SSCInt cell_stride, int memspace)
+{
+    if (!pc) return ssc_set_error(SSC_ERR_ARG_NULL, "null PC");
+    if (!Ke) return ssc_set_error(SSC_ERR_ARG_NULL, "null element matrices");
+    if (ncells < 1 || dofs_per_cell < 1) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "need at least one cell and one dof per cell");
+    if (cell_stride != 0 && cell_stride < dofs_per_cell * dofs_per_cell) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "cell stride %lld is smaller than one %lld x %lld matrix (0 = one matrix shared by all cells)", (long long)cell_stride, (long long)dofs_per_cell, (long long)dofs_per_cell);
+    pc->elem_K = Ke; pc->elem_ncells = ncells; pc->elem_t = dofs_per_cell; pc->elem_stride = cell_stride; pc->elem_space = memspace;
+    pc->elem_set = true;
+    pc->csr_set = false;
     return 0;
 }
 
@@ -715,6 +749,8 @@ static int build_device_lists(PC *pc)
         CHK(dev_alloc(&pc->d_r, pc->nlocal));
     }
     if (pc->nlocal > 2147483647LL) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "local vector too long for 32-bit device indices");
+    pc->event_ms["SSCListsSort"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() - pc->event_ms["PCPATCHCreate"];
+    auto t1 = std::chrono::steady_clock::now();
     // dof lists in sorted order, int32
     std::vector<int> g32((size_t)pc->sum_n);
     {
@@ -731,9 +767,12 @@ static int build_device_lists(PC *pc)
         if (Tn == 1) work(0);
         else { std::vector<std::thread> th; for (int t = 0; t < Tn; ++t) th.emplace_back(work, t); for (auto &x : th) x.join(); }
     }
+    pc->event_ms["SSCListsPack"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    t1 = std::chrono::steady_clock::now();
     CHK(dev_alloc(&pc->d_gtol, pc->sum_n));
     if (pc->sum_n) CUDA_OK(cudaMemcpyAsync(pc->d_gtol, g32.data(), (size_t)pc->sum_n * sizeof(int), cudaMemcpyHostToDevice, pc->stream));
     CUDA_OK(cudaStreamSynchronize(pc->stream));
+    pc->event_ms["SSCListsUpload"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     CHK(dev_alloc(&pc->d_fail, (i64)order.size()));
     if (pc->deterministic) {
         if (pc->sf_set) return ssc_set_error(SSC_ERR_SUP, "ssc_deterministic is a single-rank mode in this build");
@@ -1008,6 +1047,67 @@ static int upload_csr(PC *pc)
     return 0;
 }
 
+static int upload_elements(PC *pc)
+{
+    if (pc->multiplicative) return ssc_set_error(SSC_ERR_SUP, "multiplicative sweeps update the residual with the assembled operator: use SSCPatchSetOperatorCSR()");
+    if (pc->elem_owned) { dev_free(pc->d_elemK); pc->elem_owned = false; }
+    if (pc->elem_space == SSC_MEM_DEVICE) { pc->d_elemK = const_cast<double *>(pc->elem_K); return 0; }
+    const i64 t2 = pc->elem_t * pc->elem_t;
+    const i64 len = pc->elem_stride == 0 ? t2 : (pc->elem_ncells - 1) * pc->elem_stride + t2;
+    CHK(dev_alloc(&pc->d_elemK, len));
+    pc->elem_owned = true;
+    CHK(staged_upload(pc, pc->d_elemK, pc->elem_K, (size_t)len * sizeof(double)));
+    return 0;
+}
+
+static int upload_operator(PC *pc) { return pc->elem_set ? upload_elements(pc) : upload_csr(pc); }
+
+// cells of every patch in size-sorted order + the cell-node maps: what the assemble kernel turns into the `dofs` table on the fly
+static int upload_element_lists(PC *pc)
+{
+    const PatchLists &L = pc->lists;
+    const Discretisation &D = pc->disc;
+    if (pc->direct_patches || !D.set || L.cells.empty()) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "element matrices need patches built from the mesh and the discretisation (cells per patch, cell-node maps)");
+    if (D.nsub > 8) return ssc_set_error(SSC_ERR_SUP, "element matrices: at most 8 subspaces");
+    if (pc->elem_t != D.totalDofsPerCell) return ssc_set_error(SSC_ERR_ARG_INCOMP, "element matrices have %lld dofs per cell but the discretisation has %lld", (long long)pc->elem_t, (long long)D.totalDofsPerCell);
+    i64 maxcell = -1;
+    for (i64 c : L.cells) maxcell = std::max(maxcell, c);
+    if (pc->elem_stride != 0 && maxcell >= pc->elem_ncells) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "patches use cell %lld but only %lld element matrices were given", (long long)maxcell, (long long)pc->elem_ncells);
+    if (pc->elem_lists_ready) return 0;
+    const i64 ns = (i64)pc->sorted2orig.size();
+    std::vector<i64> off((size_t)ns + 1, 0);
+    std::vector<int> cells;
+    cells.reserve(L.cells.size());
+    for (i64 q = 0; q < ns; ++q) {
+        const i64 p = pc->sorted2orig[(size_t)q];
+        for (i64 k = L.cellOff[p]; k < L.cellOff[p + 1]; ++k) cells.push_back((int)L.cells[(size_t)k]);
+        off[(size_t)q + 1] = (i64)cells.size();
+    }
+    CHK(dev_alloc(&pc->d_pcelloff, ns + 1));
+    CHK(dev_alloc(&pc->d_pcells, std::max<i64>(1, (i64)cells.size())));
+    CUDA_OK(cudaMemcpyAsync(pc->d_pcelloff, off.data(), (size_t)(ns + 1) * sizeof(i64), cudaMemcpyHostToDevice, pc->stream));
+    CUDA_OK(cudaMemcpyAsync(pc->d_pcells, cells.data(), cells.size() * sizeof(int), cudaMemcpyHostToDevice, pc->stream));
+    ElemSpaces &E = pc->espaces;
+    memset(&E, 0, sizeof(E));
+    E.nsub = (int)D.nsub; E.t = (int)D.totalDofsPerCell;
+    std::vector<int> narrow;
+    for (i64 k = 0; k < D.nsub; ++k) {
+        const i64 len = (maxcell + 1) * D.nodesPerCell[k];
+        narrow.resize((size_t)len);
+        for (i64 i = 0; i < len; ++i) narrow[(size_t)i] = (int)D.cellNodeMap[k][i];
+        int *d = nullptr;
+        CHK(dev_alloc(&d, len));
+        pc->d_cnm.push_back(d);
+        CUDA_OK(cudaMemcpy(d, narrow.data(), (size_t)len * sizeof(int), cudaMemcpyHostToDevice));
+        E.cnm[k] = d; E.bs[k] = (int)D.bs[k]; E.npc[k] = (int)D.nodesPerCell[k]; E.subOff[k] = (int)D.subspaceOffsets[k];
+        E.tOff[k + 1] = E.tOff[k] + E.npc[k] * E.bs[k];
+    }
+    if (E.tOff[D.nsub] != E.t) return ssc_set_error(SSC_ERR_ARG_INCOMP, "subspaces add up to %d dofs per cell, expected %d", E.tOff[D.nsub], E.t);
+    CUDA_OK(cudaStreamSynchronize(pc->stream));
+    pc->elem_lists_ready = true;
+    return 0;
+}
+
 static size_t invert_smem_bytes(int n, bool shared)
 {
     const size_t ld = (size_t)(n | 1);
@@ -1027,9 +1127,22 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
     if (smem_e > 200 * 1024) return ssc_set_error(SSC_ERR_SUP, "patch with %d dofs is too large for the extract kernel", n);
     if (smem_e > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
     if (time_it) CUDA_OK(cudaEventRecord(pc->ev0, pc->stream));
+    if (pc->elem_set) {
+        const int tpad = ((int)pc->elem_t + 1) & ~1;
+        const size_t base = ((size_t)H * 2 + 2 * (size_t)tpad) * sizeof(int);
+        const size_t accb = (size_t)n * c.ld * sizeof(double);
+        const int acc_shared = pc->asm_shared && base + accb <= 200 * 1024;
+        const size_t smem_a = base + (acc_shared ? accb : 0);
+        if (smem_a > 200 * 1024) return ssc_set_error(SSC_ERR_SUP, "patch with %d dofs is too large for the assemble kernel", n);
+        if (smem_a > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+        const int grid_a = (int)std::min<i64>(cnt, (i64)pc->sm_count * 16);
+        ssc_assemble_kernel<<<grid_a, pc->asm_threads, smem_a, pc->stream>>>(pc->espaces, pc->d_elemK, (ll)pc->elem_stride, (const ll *)pc->d_pcelloff + q0, pc->d_pcells,
+                                                               pc->d_gtol + c.goff + (q0 - c.first) * n, blocks, n, c.ld, c.stride, cnt, H, acc_shared);
+    } else {
     const int grid_e = (int)std::min<i64>(cnt, (i64)pc->sm_count * 64);
     ssc_extract_kernel<<<grid_e, bd, smem_e, pc->stream>>>((const ll *)pc->d_rowptr, pc->d_colidx, pc->d_vals, pc->d_gtol + c.goff + (q0 - c.first) * n,
                                                           blocks, n, c.ld, c.stride, cnt, H);
+    }
     pc->launches++;
     CUDA_OK(cudaGetLastError());
     if (time_it) {
@@ -1139,7 +1252,7 @@ extern "C" int SSCPatchSetUp(SSCPatchPC pc)
     std::string up_msg;
     std::thread uploader([&]() {
         cudaSetDevice(pc->device);
-        up_rc = upload_csr(pc);
+        up_rc = upload_operator(pc);
         if (up_rc) up_msg = SSCGetLastError();
     });
     int list_rc = first ? build_device_lists(pc) : 0;
@@ -1149,6 +1262,7 @@ extern "C" int SSCPatchSetUp(SSCPatchPC pc)
     if (list_rc) return ssc_set_error(list_rc, "%s", list_msg.c_str());
     if (up_rc) return ssc_set_error(up_rc, "%s", up_msg.c_str());
     CUDA_OK(cudaStreamSynchronize(pc->up_stream));
+    if (pc->elem_set) CHK(upload_element_lists(pc));
     lap("SSCSetupUploadOperator");                                      // what is left of the upload after the patches are built
     if (first && pc->partition_of_unity) CHK(compute_weights(pc));      // only on the first setup, ssc/libssc.c:1254
     pc->event_ms["PCPATCHComputeOp"] = 0; pc->event_ms["PCPATCHSolve"] = 0;
@@ -1177,6 +1291,7 @@ extern "C" int SSCPatchSetUp(SSCPatchPC pc)
         pc->failed_list.clear();
         for (size_t q = 0; q < fail.size(); ++q) if (fail[q]) { if (firstbad < 0) firstbad = pc->sorted2orig[q]; pc->failed++; pc->failed_list.push_back(pc->sorted2orig[q]); }
         if (pc->csr_owned && !pc->multiplicative) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); pc->csr_owned = false; }
+        if (pc->elem_owned) { dev_free(pc->d_elemK); pc->elem_owned = false; }
         if (pc->failed) return ssc_set_error(SSC_ERR_MAT_LU_ZRPVT, "%lld patch operators could not be factorised (first: patch %lld)%s", (long long)pc->failed,
                                              (long long)firstbad, pc->sub_pc == SSC_SUB_CHOLESKY ? "; sub_pc_type cholesky needs SPD blocks" : "");
     } else {

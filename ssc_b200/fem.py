@@ -529,6 +529,27 @@ def poisson_problem(mesh, degree, kind="scalar"):
     return form, bcs
 
 
+def poisson_element_matrices(spaces):
+    """Element matrices of poisson_problem's form: what the reference's compute-operator callback feeds to
+    MatSetValues cell by cell (ssc/patch.py:28-62).  Cell dofs run subspace by subspace, node by node, component by
+    component (the order of the per-cell dof table, ssc/libssc.c:846-889).  Returns (ncells, t, t) on simplices and
+    one shared (t, t) matrix on tensor meshes (all cells congruent)."""
+    V0 = spaces[0]
+    if V0.mesh.cell_type == "simplex":
+        K0 = assemble_poisson_simplex(V0)[1]
+    else:
+        K0 = element_matrix_tensor(V0)[None]
+    nb = K0.shape[-1]
+    t = sum(nb * W.bs for W in spaces)
+    Ke = np.zeros((K0.shape[0], t, t))
+    o = 0
+    for W in spaces:
+        blk = np.einsum("cij,ab->ciajb", K0, np.eye(W.bs)).reshape(K0.shape[0], nb * W.bs, nb * W.bs)
+        Ke[:, o:o + nb * W.bs, o:o + nb * W.bs] = blk
+        o += nb * W.bs
+    return Ke if V0.mesh.cell_type == "simplex" else Ke[0]
+
+
 def load_vector(spaces):
     """inner(Constant(1), v)*dx for every component (the right-hand side of the reference's tests)."""
     out = []

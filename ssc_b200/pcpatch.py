@@ -21,7 +21,7 @@ PATCH_OPTIONS = ("pc_patch_save_operators", "pc_patch_partition_of_unity", "pc_p
                  "pc_patch_vanka_dim", "pc_patch_vanka_space", "pc_patch_sub_mat_type", "pc_patch_print_patches",
                  "pc_patch_symmetrise_sweep", "pc_patch_exclude_subspace", "sub_ksp_type", "sub_pc_type",
                  "sub_pc_factor_mat_solver_type", "sub_pc_factor_mat_ordering_type",
-                 "ssc_keep_dofs_table", "ssc_keep_patch_operators", "ssc_builder_threads", "ssc_apply_variant", "ssc_factor_variant", "ssc_factor_panel", "ssc_factor_ctas", "ssc_factor_tile", "ssc_host_pipeline", "ssc_deterministic", "ssc_device_patch_construction", "ssc_symmetric_storage", "ssc_symmetric_persistent", "ssc_symmetric_bulk_copy", "ssc_symmetric_two_chunk")
+                 "ssc_keep_dofs_table", "ssc_keep_patch_operators", "ssc_builder_threads", "ssc_apply_variant", "ssc_factor_variant", "ssc_factor_panel", "ssc_factor_ctas", "ssc_factor_tile", "ssc_host_pipeline", "ssc_deterministic", "ssc_device_patch_construction", "ssc_symmetric_storage", "ssc_symmetric_persistent", "ssc_symmetric_bulk_copy", "ssc_symmetric_two_chunk", "ssc_assemble_shared", "ssc_assemble_threads")
 
 
 class DeviceVec(object):
@@ -240,6 +240,22 @@ class PC(object):
             return
         n, ptrs = indptr[0], [C.c_void_p(p) for p in (indptr[1], indices, data)]
         CHKERR(lib.SSCPatchSetOperatorCSR(self.handle, C.c_int64(n), ptrs[0], ptrs[1], ptrs[2], int(memspace)))
+
+    def setElementMatrices(self, Ke, memspace=MEM_HOST, ncells=None, dofs_per_cell=None):
+        """The reference's source of the patch operators (PCPatchSetComputeOperator, ssc/PatchPC.pyx:158-163 with the
+        element kernel of ssc/patch.py:28-62): Ke[cell] is the element matrix of that cell, rows/columns in the order
+        of the per-cell dof table; a 2-D Ke is one matrix shared by every cell.  Replaces setOperatorCSR."""
+        if memspace == MEM_HOST:
+            Ke = np.ascontiguousarray(Ke, dtype=np.float64)
+            if Ke.ndim not in (2, 3) or Ke.shape[-1] != Ke.shape[-2]:
+                raise ValueError("element matrices must be (ncells, t, t) or one shared (t, t) matrix")
+            self._csr_keep = (Ke,)
+            t = Ke.shape[-1]
+            nc, stride, ptr = (1, 0, Ke.ctypes.data) if Ke.ndim == 2 else (Ke.shape[0], t * t, Ke.ctypes.data)
+        else:
+            t, nc = int(dofs_per_cell), int(ncells or 1)
+            stride, ptr = (0 if ncells is None else t * t), int(Ke)
+        CHKERR(lib.SSCPatchSetElementMatrices(self.handle, C.c_int64(nc), C.c_int64(t), C.c_void_p(ptr), C.c_int64(stride), int(memspace)))
 
     def releaseOperator(self):
         """Drop the host CSR arrays kept alive for the library (they are only borrowed until setUp returns)."""

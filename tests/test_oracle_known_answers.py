@@ -100,6 +100,23 @@ def test_patch_matrix_is_submatrix_and_equals_elementwise_assembly():
         assert np.all(np.linalg.eigvalsh((B + B.T) / 2) > 0)           # SPD (8c(iv))
 
 
+@pytest.mark.parametrize("mesh,p,kind", [(plex.RectangleMesh(4, 3, 1, 1), 2, "mixed"), (plex.TensorPlex((3, 3, 2)), 3, "scalar"),
+                                         (plex.TensorPlex((3, 4)), 2, "vector"), (plex.BoxMesh(2, 2, 2), 2, "tensor")],
+                         ids=["tri-mixed", "hex-q3", "quad-vector", "tet-tensor"])
+def test_elementwise_assembly_in_dof_table_order(mesh, p, kind):
+    """Cell dofs of the element matrices run subspace -> node -> component (ssc/libssc.c:846-889); with that order the
+    cell-by-cell assembly equals the submatrix of the assembled operator on every patch, also for mixed spaces."""
+    form, bcs, disc, A = _problem(mesh, p, kind)
+    Ke = fem.poisson_element_matrices(form.spaces)
+    if Ke.ndim == 2:
+        Ke = np.broadcast_to(Ke, (mesh.num_cells,) + Ke.shape).copy()
+    o = make_oracle(disc, A)
+    off, _ = o.patches()
+    for i in range(o.npatch):
+        if off[i + 1] > off[i]:
+            assert np.allclose(o.patchMatrixFromElements(i, Ke), o.patchMatrix(i), rtol=1e-12, atol=1e-13)
+
+
 def test_multiplicity_and_partition_of_unity():
     form, bcs, disc, A = _problem(plex.BoxMesh(3, 3, 3), 2, "vector")
     o = make_oracle(disc, A, partition_of_unity=1)
