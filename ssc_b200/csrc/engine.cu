@@ -1165,7 +1165,7 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
         if (smem_f > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_invert_kernel<P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
         ssc_invert_kernel<P, S><<<grid_f, bdf, smem_f, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail);             \
     } while (0)
-    if (n > 128 && pc->factor_variant == 1) {
+    if (n > 128 && pc->factor_variant >= 1) {
         // blocked Gauss-Jordan with DMMA updates, block resident in L2
         const int npad = (n + 7) & ~7, WP = ((npad + 15) & ~15) + 4;
         auto smem_for = [&](int nb) { return ((size_t)npad * (nb + 1) + (size_t)nb * WP + nb + 32) * sizeof(double) + (size_t)(34 + 2 * n + 2) * sizeof(int); };
@@ -1191,6 +1191,20 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
         const int threads = std::max((TC * TC + 31) / 32 * 32, (n + 31) / 32 * 32);
         if (pivot) ssc_invert_reg8_kernel<true><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC);
         else ssc_invert_reg8_kernel<false><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC);
+    }
+    else if (n <= 128 && pc->factor_variant == 3) {
+        // blocked look-ahead Gauss-Jordan: panels of 5 columns, (n/8) x (n/5) worker threads + one searcher warp
+        const int TC = (n + 4) / 5, TR = (n + 7) / 8;
+        const int W = (TR * TC + 31) / 32 * 32;
+        if (pivot) ssc_invert_panel_kernel<true><<<grid_f, W + 32, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W);
+        else ssc_invert_panel_kernel<false><<<grid_f, W + 32, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W);
+    }
+    else if (n <= 128 && pc->factor_variant == 2) {
+        // register-resident tiles with a look-ahead pivot search: (n/8) x (n/5) worker threads + one searcher warp
+        const int TC = (n + 4) / 5, TR = (n + 7) / 8;
+        const int W = (TR * TC + 31) / 32 * 32;
+        if (pivot) ssc_invert_la_kernel<true><<<grid_f, W + 32, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC, W);
+        else ssc_invert_la_kernel<false><<<grid_f, W + 32, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC, W);
     }
     else if (n <= 128 && pc->factor_variant == 1) {
         // register-resident tiles: (n/8) x (n/4) threads

@@ -467,6 +467,456 @@ ssc_invert_reg_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll
     }
 }
 
+// Look-ahead form of the register-resident Gauss-Jordan above.  ncu showed the kernel above issue- and latency-bound:
+// 295 warp instructions per warp and elimination step for 32 FMAs, because every warp repeats the pivot search and
+// the division, and the whole CTA waits for them twice per step.  Here an extra warp (the "searcher") owns the pivot
+// search and the reciprocal.  While the 16 worker warps apply step k to their tiles, the owners of column k+1 update
+// that column first, publish it and signal the searcher, which finds the pivot of step k+1 and its reciprocal in
+// parallel with the bulk of the update.  Named barriers: 1 = column published (workers arrive, searcher waits),
+// 2 = pivot ready (searcher arrives, workers wait), 3 = pivot row published (workers only).
+// Tiles are 8 x 5 here (16 x 25 workers + the searcher = 448 threads: the register file holds 128 per thread).
+// Same arithmetic, same pivot choice (largest magnitude, lowest row on ties), same stored layout as above.
+__device__ __forceinline__ void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <bool kPivot>
+__global__ void __launch_bounds__(448, 1)
+ssc_invert_la_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll count, int *__restrict__ fail_flags, int TC, int W)
+{
+    __shared__ __align__(16) double colv[2][136];
+    __shared__ __align__(16) double rowv[2][136];      // 26 column tiles of 5 reach slot 129
+    __shared__ double s_dinv[2];
+    __shared__ int s_prow[2];
+    __shared__ int s_fail;
+    __shared__ int perm[128], qinv[128];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int all = W + 32;
+    const bool searcher = tid >= W;
+    const int tr = tid / TC, tc = tid - tr * TC;
+    const bool owner = !searcher && tr < (n + 7) / 8;
+    const int r0 = owner ? 8 * tr : 0, c0 = owner ? 5 * tc : 0;
+    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
+        double *B = blocks + p * stride;
+        double a[8][5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const int j = c0 + c;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = r0 + r;
+                a[r][c] = (owner && i < n && j < n) ? B[(ll)j * ldg + i] : 0.0;      // transposed load: A = B^T
+            }
+        }
+        if (tid == 0) s_fail = 0;
+        if (owner && tc == 0) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { colv[0][r0 + r] = a[r][0]; a[r][0] = 0.0; }
+        }
+        __syncthreads();
+        if (searcher) {
+            unsigned usedmask = 0;      // bit s of lane l <-> row l + 32 s has been a pivot row
+            for (int k = 0; k < n; ++k) {
+                const int buf = k & 1;
+                if (k > 0) nbar_sync(1, all);                        // column k is in colv[buf]
+                int prow = k;
+                if (kPivot) {
+                    unsigned long long bestk = 0ull;
+                    int bi = 1 << 30;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const int i = lane + 32 * s;
+                        if (i < n && !((usedmask >> s) & 1u)) {
+                            const double v = fabs(colv[buf][i]);
+                            const unsigned long long key = (v == v) ? (unsigned long long)__double_as_longlong(v) : 0ull;   // |v| orders like its bits
+                            if (bi == (1 << 30) || key > bestk) { bestk = key; bi = i; }
+                        }
+                    }
+                    const bool have = bi < (1 << 30);
+                    const unsigned hi = (unsigned)(bestk >> 32), lo = (unsigned)bestk;
+                    const unsigned mh = __reduce_max_sync(0xffffffffu, have ? hi : 0u);
+                    const bool in1 = have && hi == mh;
+                    const unsigned ml = __reduce_max_sync(0xffffffffu, in1 ? lo : 0u);
+                    prow = (int)__reduce_min_sync(0xffffffffu, (in1 && lo == ml) ? (unsigned)bi : 0x7fffffffu);
+                }
+                bool bad = prow >= n;
+                double dinv = 0.0;
+                if (!bad) {
+                    const double d = colv[buf][prow];
+                    bad = !(fabs(d) > 0.0) || (!kPivot && !(d > 0.0));
+                    dinv = 1.0 / d;
+                    if ((prow & 31) == lane) usedmask |= 1u << (prow >> 5);
+                }
+                if (lane == 0) {
+                    s_prow[buf] = bad ? -1 : prow; s_dinv[buf] = dinv; perm[k] = bad ? k : prow;
+                    if (bad) s_fail = 1;
+                }
+                nbar_arrive(2, all);                                  // orders the stores above for the waiting workers
+                if (bad) break;
+            }
+        } else {
+            for (int k = 0; k < n; ++k) {
+                const int buf = k & 1;
+                nbar_sync(2, all);                                    // the pivot of step k is known
+                const int prow = s_prow[buf];
+                if (prow < 0) break;                                  // no usable pivot: uniform across the CTA
+                const double dinv = s_dinv[buf];
+                // the owners of the pivot row publish it scaled (slot k carries 1/d) and clear it; the multiplier of the
+                // pivot row becomes -1 so that the update below writes the scaled row back without a special case
+                if (owner && tr == (prow >> 3)) {
+                    if (tc == 0) colv[buf][prow] = -1.0;
+#define PUBLISH_ROW(R)                                                                                          \
+    _Pragma("unroll") for (int c = 0; c < 5; ++c) { rowv[buf][c0 + c] = (c0 + c == k) ? dinv : a[R][c] * dinv; a[R][c] = 0.0; }
+                    switch (prow & 7) {
+                    case 0: PUBLISH_ROW(0) break;
+                    case 1: PUBLISH_ROW(1) break;
+                    case 2: PUBLISH_ROW(2) break;
+                    case 3: PUBLISH_ROW(3) break;
+                    case 4: PUBLISH_ROW(4) break;
+                    case 5: PUBLISH_ROW(5) break;
+                    case 6: PUBLISH_ROW(6) break;
+                    default: PUBLISH_ROW(7) break;
+                    }
+#undef PUBLISH_ROW
+                }
+                nbar_sync(3, W);
+                const double2 *cp = reinterpret_cast<const double2 *>(&colv[buf][r0]);
+                double cv[8], rv[5];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) { const double2 t = cp[h]; cv[2 * h] = t.x; cv[2 * h + 1] = t.y; }
+#pragma unroll
+                for (int c = 0; c < 5; ++c) rv[c] = rowv[buf][c0 + c];
+                // look-ahead: column k+1 first, published for the searcher and cleared like column k was
+                const int k1 = k + 1;
+                const int t1 = k1 / 5, w1 = k1 - 5 * t1;
+                const bool early = owner && k1 < n && tc == t1;
+                if (early) {
+#define EARLY_COL(C)                                                                                            \
+    _Pragma("unroll") for (int r = 0; r < 8; ++r) { colv[buf ^ 1][r0 + r] = fma(-cv[r], rv[C], a[r][C]); a[r][C] = 0.0; }
+                    switch (w1) {
+                    case 0: EARLY_COL(0) break;
+                    case 1: EARLY_COL(1) break;
+                    case 2: EARLY_COL(2) break;
+                    case 3: EARLY_COL(3) break;
+                    default: EARLY_COL(4) break;
+                    }
+#undef EARLY_COL
+                }
+                if (k1 < n) nbar_arrive(1, all);
+                const int skip = early ? w1 : -1;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    if (c != skip) {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) a[r][c] = fma(-cv[r], rv[c], a[r][c]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const int fail = s_fail;
+        if (tid < n) qinv[perm[tid]] = tid;
+        __syncthreads();
+        if (tid == 0) fail_flags[p] = fail;
+        if (!fail && owner) {
+            // A^-1[kk][cc] = W[perm[kk]][qinv[cc]]  <=>  W[i][j] goes to row qinv[i], column perm[j]
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = r0 + r;
+                if (i < n) {
+                    const ll row = (ll)qinv[i] * ldg;
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        const int j = c0 + c;
+                        if (j < n) B[row + perm[j]] = a[r][c];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Blocked form of the look-ahead kernel: panels of 5 columns.  Applying the 5 Gauss-Jordan steps of a panel to the
+// whole matrix is  A <- T A  with  T = T_5 ... T_1, and T differs from the identity only in the columns of the 5 pivot
+// rows.  So every other column gets the rank-5 update  A[:, j] += (T - I)[:, P] A_old[P, j]  (P = the pivot rows, raw
+// values from before the panel), and the panel's own slots receive T[:, P] -- which is exactly what the same in-place
+// Gauss-Jordan steps leave behind when they are run on the n x 5 panel alone.  The searcher warp does that small
+// factorisation (pivot searches, reciprocals) for the next panel while the worker warps apply the current one:
+// 200 FMAs per worker thread between barriers instead of 40, and the serial pivot chain runs beside them.
+// A panel is NOT five neighbouring columns: it takes the same local column w of five neighbouring column tiles
+// (columns 5 (5 g + q) + w, q = 0..4), so its columns belong to 80 threads instead of 16 and the look-ahead update of
+// the next panel -- which sits on the critical path between two panel factorisations -- is 40 FMAs per owner, not 200.
+// Columns are therefore eliminated in a different order than in the kernels above (any order is a valid partial-pivot
+// elimination; perm[] is indexed by column); the inverse agrees to rounding.
+// The searcher keeps its working panel row-major in shared memory (S) and re-reads its rows every step, so the row
+// that just served as pivot row can be replaced by one lane without dynamic register indexing (a register-only
+// version with selects measured 6 % slower).
+// position of matrix row i inside a panel column in shared memory: the 16-byte chunks (row pairs) that the 16 row
+// tiles of a warp read together are neighbours, so those reads are conflict-free (a plain row order puts them 64
+// bytes apart: 8-way bank conflicts, which also starved the searcher's own shared-memory traffic)
+__device__ __forceinline__ int ppos(int i) { return ((((i >> 1) & 3) * 16 + (i >> 3)) << 1) | (i & 1); }
+
+template <bool kPivot>
+__global__ void __launch_bounds__(448, 1)
+ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll count, int *__restrict__ fail_flags, int TR, int TC, int W)
+{
+    constexpr int PB = 5, LDP = 136, SR = 6;
+    __shared__ __align__(16) double Pcol[2][PB][LDP];      // panel columns: raw from their owners, then (T - I)[:, P] from the searcher
+    __shared__ __align__(16) double Rrow[2][PB][LDP];      // the raw pivot rows of a panel
+    __shared__ __align__(16) double S[128][SR];            // the searcher's working panel, one row per matrix row
+    __shared__ int s_prow[2][8];
+    __shared__ int perm[128], qinv[128];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int all = W + 32;
+    const bool searcher = tid >= W;
+    const int tc = tid / TR, tr = tid - tc * TR;
+    const bool owner = !searcher && tc < TC;
+    const int r0 = owner ? 8 * tr : 0, c0 = owner ? PB * tc : 0;
+    const int gt = tc / PB, qt = tc - PB * gt;               // column-tile group of this thread, its panel column there
+    const int NPAN = PB * ((TC + PB - 1) / PB);
+    // width of panel j = (g, w): tiles 5 g + q < TC with column 5 (5 g + q) + w < n form a prefix in q
+    auto width = [&](int j) {
+        const int g = j / PB, w = j - PB * g;
+        int bw = 0;
+        for (int q = 0; q < PB; ++q) bw += (PB * g + q < TC && PB * (PB * g + q) + w < n) ? 1 : 0;
+        return bw;
+    };
+    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
+        double *B = blocks + p * stride;
+        if (searcher) {
+            unsigned usedmask = 0;      // bit s of lane l <-> row l + 32 s has been a pivot row
+            int it = 0;
+            for (int j = 0; j < NPAN; ++j) {
+                const int bw = width(j);
+                if (bw == 0) continue;
+                const int buf = it & 1, g = j / PB, w = j - PB * g;
+                ++it;
+                nbar_sync(1, all);                                    // panel j is in Pcol[buf]
+                double x[4][PB];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int i = lane + 32 * s;
+#pragma unroll
+                    for (int c = 0; c < PB; ++c) x[s][c] = (i < n && c < bw) ? Pcol[buf][c][ppos(i)] : 0.0;
+                    double2 *row = reinterpret_cast<double2 *>(&S[i][0]);
+                    row[0] = make_double2(x[s][0], x[s][1]); row[1] = make_double2(x[s][2], x[s][3]); S[i][4] = x[s][4];
+                }
+                __syncwarp();
+                int pl[PB];
+                bool bad = false;
+#pragma unroll
+                for (int t = 0; t < PB; ++t) {
+                    pl[t] = 0;
+                    if (t < bw && !bad) {
+                        int prow = PB * (PB * g + t) + w;            // unpivoted: the diagonal entry of this column
+                        if (kPivot) {
+                            unsigned long long bestk = 0ull;
+                            int bi = 1 << 30;
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) {
+                                const int i = lane + 32 * s;
+                                if (i < n && !((usedmask >> s) & 1u)) {
+                                    const double v = fabs(x[s][t]);
+                                    const unsigned long long key = (v == v) ? (unsigned long long)__double_as_longlong(v) : 0ull;   // |v| orders like its bits
+                                    if (bi == (1 << 30) || key > bestk) { bestk = key; bi = i; }
+                                }
+                            }
+                            const bool have = bi < (1 << 30);
+                            const unsigned hi = (unsigned)(bestk >> 32), lo = (unsigned)bestk;
+                            const unsigned mh = __reduce_max_sync(0xffffffffu, have ? hi : 0u);
+                            const bool in1 = have && hi == mh;
+                            const unsigned ml = __reduce_max_sync(0xffffffffu, in1 ? lo : 0u);
+                            prow = (int)__reduce_min_sync(0xffffffffu, (in1 && lo == ml) ? (unsigned)bi : 0x7fffffffu);
+                        }
+                        if (prow >= n) bad = true;
+                        else {
+                            const double2 *prw = reinterpret_cast<const double2 *>(&S[prow][0]);
+                            const double2 p01 = prw[0], p23 = prw[1];
+                            const double pr[PB] = {p01.x, p01.y, p23.x, p23.y, S[prow][4]};
+                            const double d = pr[t];
+                            if (!(fabs(d) > 0.0) || (!kPivot && !(d > 0.0))) bad = true;
+                            const double dinv = __drcp_rn(d);        // correctly rounded, = 1.0 / d
+                            double rr[PB];
+#pragma unroll
+                            for (int c = 0; c < PB; ++c) rr[c] = (c == t) ? dinv : pr[c] * dinv;
+                            __syncwarp();                            // everybody has read the pivot row
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) {
+                                const int i = lane + 32 * s;
+                                const double mlt = -x[s][t];
+#pragma unroll
+                                for (int c = 0; c < PB; ++c) x[s][c] = (c == t) ? mlt * dinv : fma(mlt, rr[c], x[s][c]);
+                                double2 *row = reinterpret_cast<double2 *>(&S[i][0]);
+                                row[0] = make_double2(x[s][0], x[s][1]); row[1] = make_double2(x[s][2], x[s][3]); S[i][4] = x[s][4];
+                            }
+                            // the pivot row itself becomes the scaled row, slot t carries 1/d (its lane stored it above:
+                            // the same lane overwrites it here, in program order)
+                            if ((prow & 31) == lane) {
+                                double2 *row = reinterpret_cast<double2 *>(&S[prow][0]);
+                                row[0] = make_double2(rr[0], rr[1]); row[1] = make_double2(rr[2], rr[3]); S[prow][4] = rr[4];
+                                usedmask |= 1u << (prow >> 5);
+                            }
+                            __syncwarp();
+                            // re-read the own rows: only the pivot row changed under its owner's feet
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) {
+                                const double2 *row = reinterpret_cast<const double2 *>(&S[lane + 32 * s][0]);
+                                const double2 a01 = row[0], a23 = row[1];
+                                x[s][0] = a01.x; x[s][1] = a01.y; x[s][2] = a23.x; x[s][3] = a23.y; x[s][4] = S[lane + 32 * s][4];
+                            }
+                            pl[t] = prow;
+                        }
+                    }
+                }
+                // (T - I)[:, P]: take the unit entries of the pivot rows out again
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int i = lane + 32 * s;
+#pragma unroll
+                    for (int c = 0; c < PB; ++c)
+                        if (i < n && c < bw) Pcol[buf][c][ppos(i)] = x[s][c] - ((i == pl[c]) ? 1.0 : 0.0);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int t = 0; t < PB; ++t) { s_prow[buf][t] = bad ? -1 : pl[t]; if (t < bw) perm[PB * (PB * g + t) + w] = bad ? PB * (PB * g + t) + w : pl[t]; }
+                }
+                nbar_arrive(2, all);                                  // orders the stores above for the waiting workers
+                if (bad) break;
+            }
+        } else {
+            // the tile lives only in the workers' registers (the searcher's registers hold its panel)
+            double a[8][PB];
+#pragma unroll
+            for (int c = 0; c < PB; ++c) {
+                const int j = c0 + c;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i = r0 + r;
+                    a[r][c] = (owner && i < n && j < n) ? B[(ll)j * ldg + i] : 0.0;      // transposed load: A = B^T
+                }
+            }
+            if (owner && gt == 0) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) Pcol[0][qt][ppos(r0 + r)] = a[r][0];
+            }
+            nbar_arrive(1, all);
+            int fail = 0, it = 0;
+            int j = 0;
+            while (j < NPAN && width(j) == 0) ++j;
+            while (j < NPAN) {
+                const int bw = width(j), buf = it & 1, g = j / PB, w = j - PB * g;
+                ++it;
+                int jn = j + 1;                                       // the next non-empty panel
+                while (jn < NPAN && width(jn) == 0) ++jn;
+                const int gn = jn / PB, wn = jn - PB * gn, bwn = jn < NPAN ? width(jn) : 0;
+                nbar_sync(2, all);                                    // the pivots of panel j are known
+                int pl[PB];
+#pragma unroll
+                for (int t = 0; t < PB; ++t) pl[t] = s_prow[buf][t];
+                if (pl[0] < 0) { fail = 1; break; }                   // no usable pivot: uniform across the CTA
+                // the owners of the pivot rows publish them as they are
+#pragma unroll
+                for (int t = 0; t < PB; ++t) {
+                    if (t < bw && owner && tr == (pl[t] >> 3)) {
+#define PUBLISH_ROW(R) _Pragma("unroll") for (int c = 0; c < PB; ++c) Rrow[buf][t][c0 + c] = a[R][c];
+                        switch (pl[t] & 7) {
+                        case 0: PUBLISH_ROW(0) break;
+                        case 1: PUBLISH_ROW(1) break;
+                        case 2: PUBLISH_ROW(2) break;
+                        case 3: PUBLISH_ROW(3) break;
+                        case 4: PUBLISH_ROW(4) break;
+                        case 5: PUBLISH_ROW(5) break;
+                        case 6: PUBLISH_ROW(6) break;
+                        default: PUBLISH_ROW(7) break;
+                        }
+#undef PUBLISH_ROW
+                    }
+                }
+                nbar_sync(3, W);
+                const bool in_panel = owner && gt == g && qt < bw;
+                const bool in_next = owner && jn < NPAN && gt == gn && qt < bwn;
+                // look-ahead: the next panel's columns first, then they go to the searcher
+                if (in_next) {
+#define EARLY_COL(C)                                                                                                    \
+    _Pragma("unroll") for (int t = 0; t < PB; ++t) {                                                                   \
+        if (t < bw) {                                                                                                   \
+            const double rvc = Rrow[buf][t][c0 + C];                                                                    \
+            _Pragma("unroll") for (int h = 0; h < 4; ++h) {                                                             \
+                const double2 q2 = *reinterpret_cast<const double2 *>(&Pcol[buf][t][ppos(r0 + 2 * h)]);                 \
+                a[2 * h][C] = fma(q2.x, rvc, a[2 * h][C]); a[2 * h + 1][C] = fma(q2.y, rvc, a[2 * h + 1][C]);           \
+            }                                                                                                           \
+        }                                                                                                               \
+    }                                                                                                                   \
+    _Pragma("unroll") for (int r = 0; r < 8; ++r) Pcol[buf ^ 1][qt][ppos(r0 + r)] = a[r][C];
+                    switch (wn) {
+                    case 0: EARLY_COL(0) break;
+                    case 1: EARLY_COL(1) break;
+                    case 2: EARLY_COL(2) break;
+                    case 3: EARLY_COL(3) break;
+                    default: EARLY_COL(4) break;
+                    }
+#undef EARLY_COL
+                }
+                if (jn < NPAN) nbar_arrive(1, all);
+                const int skip1 = in_panel ? w : -1, skip2 = in_next ? wn : -1;
+                if (owner) {
+#pragma unroll
+                    for (int t = 0; t < PB; ++t) {
+                        if (t < bw) {
+                            double cv[8], rv[PB];
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) { const double2 q = *reinterpret_cast<const double2 *>(&Pcol[buf][t][ppos(r0 + 2 * h)]); cv[2 * h] = q.x; cv[2 * h + 1] = q.y; }
+#pragma unroll
+                            for (int c = 0; c < PB; ++c) rv[c] = Rrow[buf][t][c0 + c];
+#pragma unroll
+                            for (int c = 0; c < PB; ++c) {
+                                if (c != skip1 && c != skip2) {
+#pragma unroll
+                                    for (int r = 0; r < 8; ++r) a[r][c] = fma(cv[r], rv[c], a[r][c]);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (in_panel) {
+                    // this thread's column w is column qt of the panel: it receives T[:, P] = (T - I)[:, P] + unit entry
+                    const int prow = s_prow[buf][qt];
+#define TAKE_COL(C) _Pragma("unroll") for (int r = 0; r < 8; ++r) a[r][C] = Pcol[buf][qt][ppos(r0 + r)] + ((r0 + r == prow) ? 1.0 : 0.0);
+                    switch (w) {
+                    case 0: TAKE_COL(0) break;
+                    case 1: TAKE_COL(1) break;
+                    case 2: TAKE_COL(2) break;
+                    case 3: TAKE_COL(3) break;
+                    default: TAKE_COL(4) break;
+                    }
+#undef TAKE_COL
+                }
+                j = jn;
+            }
+            // all pivots are known (the last pivot barrier has been passed): invert the permutation and store
+            if (!fail && tid < n) qinv[perm[tid]] = tid;       // perm is incomplete after a failure
+            nbar_sync(3, W);
+            if (tid == 0) fail_flags[p] = fail;
+            if (!fail && owner) {
+                // A^-1[kk][cc] = W[perm[kk]][qinv[cc]]  <=>  W[i][j] goes to row qinv[i], column perm[j]
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i = r0 + r;
+                    if (i < n) {
+                        const ll row = (ll)qinv[i] * ldg;
+#pragma unroll
+                        for (int c = 0; c < PB; ++c) {
+                            const int j2 = c0 + c;
+                            if (j2 < n) B[row + perm[j2]] = a[r][c];
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Same algorithm with 8 x 8 tiles: (n/8)^2 threads, 64 FMAs per thread and step against 16 shared-memory loads and
 // half as many warps repeating the pivot search -- the 8 x 4 form above is issue-bound on exactly that overhead.
 template <bool kPivot>
