@@ -112,7 +112,9 @@ struct SSCPatchPC_s {
     int factor_tile = 4;          // register tiles of the n <= 128 factor kernel: 4 (8x4, default) or 8 (8x8, measured slower)
     int factor_ctas = 0;          // concurrent CTAs of the blocked factor kernel (0 = fill the SMs)
     int factor_panel = 16;        // panel width of the blocked factor kernel (16 or 32)
-    int factor_variant = 1;       // 1: register-resident Gauss-Jordan for n <= 128, 0: shared-memory kernel
+    bool factor_remap = true;     // blocked look-ahead kernel: keep the searcher's SM sub-partition nearly free of worker warps
+    int factor_variant = -1;      // n <= 128: 0 shared-memory Gauss-Jordan, 1 register-resident, 2 + look-ahead pivot search, 3 blocked look-ahead;
+                                  // -1 (default): 3 for 100 <= n <= 128 (one CTA per SM anyway), 1 below (many small CTAs per SM hide the latency)
     int apply_variant = 1;        // 0: simple loop, 1: pipelined LDG.64, 2: pipelined LDG.128 (even row stride)
     std::string sub_mat_type, sub_ksp_type = "preonly";
     BuildOptions bopt;
@@ -436,7 +438,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_keep_dofs_table") return parse_bool(v, &pc->bopt.keep_dofs);
     if (name == "ssc_keep_patch_operators") return parse_bool(v, &pc->keep_operators);
     if (name == "ssc_builder_threads") { pc->bopt.nthreads = atoi(v); return 0; }
-    if (name == "ssc_factor_variant") { pc->factor_variant = atoi(v); return 0; }
+    if (name == "ssc_factor_variant") { pc->factor_variant = atoi(v); if (pc->factor_variant < -1 || pc->factor_variant > 3) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "ssc_factor_variant must be -1 (automatic), 0, 1, 2 or 3"); return 0; }
     if (name == "ssc_symmetric_storage") {
         bool f = false;
         CHK(parse_bool(v, &f));
@@ -457,6 +459,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
         pc->deterministic = f;
         return 0;
     }
+    if (name == "ssc_factor_remap") return parse_bool(v, &pc->factor_remap);
     if (name == "ssc_factor_panel") { pc->factor_panel = atoi(v); return 0; }
     if (name == "ssc_factor_ctas") { pc->factor_ctas = atoi(v); return 0; }
     if (name == "ssc_factor_tile") { pc->factor_tile = atoi(v); return 0; }
@@ -1165,7 +1168,8 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
         if (smem_f > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_invert_kernel<P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
         ssc_invert_kernel<P, S><<<grid_f, bdf, smem_f, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail);             \
     } while (0)
-    if (n > 128 && pc->factor_variant >= 1) {
+    const int fvar = pc->factor_variant >= 0 ? pc->factor_variant : ((n >= 100 && n <= 128) ? 3 : 1);
+    if (n > 128 && fvar >= 1) {
         // blocked Gauss-Jordan with DMMA updates, block resident in L2
         const int npad = (n + 7) & ~7, WP = ((npad + 15) & ~15) + 4;
         auto smem_for = [&](int nb) { return ((size_t)npad * (nb + 1) + (size_t)nb * WP + nb + 32) * sizeof(double) + (size_t)(34 + 2 * n + 2) * sizeof(int); };
@@ -1185,28 +1189,30 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
         else LAUNCH_BLK(false, 16);
 #undef LAUNCH_BLK
     }
-    else if (n <= 128 && pc->factor_variant == 1 && pc->factor_tile == 8) {
+    else if (n <= 128 && fvar == 1 && pc->factor_tile == 8) {
         // register-resident 8 x 8 tiles: (n/8)^2 threads; needs tid < n for the permutation arrays -> at least n threads
         const int TC = (n + 7) / 8;
         const int threads = std::max((TC * TC + 31) / 32 * 32, (n + 31) / 32 * 32);
         if (pivot) ssc_invert_reg8_kernel<true><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC);
         else ssc_invert_reg8_kernel<false><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC);
     }
-    else if (n <= 128 && pc->factor_variant == 3) {
+    else if (n <= 128 && fvar == 3) {
         // blocked look-ahead Gauss-Jordan: panels of 5 columns, (n/8) x (n/5) worker threads + one searcher warp
         const int TC = (n + 4) / 5, TR = (n + 7) / 8;
         const int W = (TR * TC + 31) / 32 * 32;
-        if (pivot) ssc_invert_panel_kernel<true><<<grid_f, W + 32, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W);
-        else ssc_invert_panel_kernel<false><<<grid_f, W + 32, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W);
+        const int remap = (W == 416 && pc->factor_remap) ? 1 : 0;
+        const int threads = remap ? 512 : W + 32;
+        if (pivot) ssc_invert_panel_kernel<true><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W, remap);
+        else ssc_invert_panel_kernel<false><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W, remap);
     }
-    else if (n <= 128 && pc->factor_variant == 2) {
+    else if (n <= 128 && fvar == 2) {
         // register-resident tiles with a look-ahead pivot search: (n/8) x (n/5) worker threads + one searcher warp
         const int TC = (n + 4) / 5, TR = (n + 7) / 8;
         const int W = (TR * TC + 31) / 32 * 32;
         if (pivot) ssc_invert_la_kernel<true><<<grid_f, W + 32, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC, W);
         else ssc_invert_la_kernel<false><<<grid_f, W + 32, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC, W);
     }
-    else if (n <= 128 && pc->factor_variant == 1) {
+    else if (n <= 128 && fvar == 1) {
         // register-resident tiles: (n/8) x (n/4) threads
         const int TC = (n + 3) / 4, TR = (n + 7) / 8;
         const int threads = (TR * TC + 31) / 32 * 32;

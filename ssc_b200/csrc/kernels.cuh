@@ -657,40 +657,54 @@ ssc_invert_la_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll 
 __device__ __forceinline__ int ppos(int i) { return ((((i >> 1) & 3) * 16 + (i >> 3)) << 1) | (i & 1); }
 
 template <bool kPivot>
-__global__ void __launch_bounds__(448, 1)
-ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll count, int *__restrict__ fail_flags, int TR, int TC, int W)
+__global__ void __launch_bounds__(512, 1)
+ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll count, int *__restrict__ fail_flags, int TR, int TC, int W, int remap)
 {
     constexpr int PB = 5, LDP = 136, SR = 6;
     __shared__ __align__(16) double Pcol[2][PB][LDP];      // panel columns: raw from their owners, then (T - I)[:, P] from the searcher
     __shared__ __align__(16) double Rrow[2][PB][LDP];      // the raw pivot rows of a panel
     __shared__ __align__(16) double S[128][SR];            // the searcher's working panel, one row per matrix row
     __shared__ int s_prow[2][8];
+    __shared__ int s_pj[32], s_pbw[32], s_np;
     __shared__ int perm[128], qinv[128];
-    const int tid = threadIdx.x, lane = tid & 31;
+    // remap (13 worker warps, 512 threads): warp 13 is the searcher and warps 5 and 9 -- the other two warps of its SM
+    // sub-partition besides worker warp 1 -- stay idle, so the serial pivot chain shares its scheduler and fp64 pipe
+    // with one worker warp instead of three; the other sub-partitions run four worker warps each
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the non-empty panels in elimination order: panel j = (g, w) holds the columns 5 (5 g + q) + w < n of the tiles
+    // 5 g + q < TC, a prefix in q; the list is the same for every block of the class
+    if (threadIdx.x == 0) {
+        int cntp = 0;
+        for (int j = 0; j < PB * ((TC + PB - 1) / PB); ++j) {
+            const int g = j / PB, w = j - PB * g;
+            int bw = 0;
+            for (int q = 0; q < PB; ++q) bw += (PB * g + q < TC && PB * (PB * g + q) + w < n) ? 1 : 0;
+            if (bw) { s_pj[cntp] = j; s_pbw[cntp] = bw; ++cntp; }
+        }
+        s_np = cntp;
+    }
+    __syncthreads();
+    const int NPE = s_np;
+    if (remap && (wid == 5 || wid == 9)) {
+        for (ll p = blockIdx.x; p < count; p += gridDim.x) __syncthreads();
+        return;
+    }
+    const bool searcher = remap ? wid == 13 : (int)threadIdx.x >= W;
+    const int tid = remap ? ((wid - (wid > 5) - (wid > 9) - (wid > 13)) << 5) + lane : (int)threadIdx.x;   // logical thread: tiles, permutation arrays
     const int all = W + 32;
-    const bool searcher = tid >= W;
     const int tc = tid / TR, tr = tid - tc * TR;
     const bool owner = !searcher && tc < TC;
     const int r0 = owner ? 8 * tr : 0, c0 = owner ? PB * tc : 0;
     const int gt = tc / PB, qt = tc - PB * gt;               // column-tile group of this thread, its panel column there
-    const int NPAN = PB * ((TC + PB - 1) / PB);
-    // width of panel j = (g, w): tiles 5 g + q < TC with column 5 (5 g + q) + w < n form a prefix in q
-    auto width = [&](int j) {
-        const int g = j / PB, w = j - PB * g;
-        int bw = 0;
-        for (int q = 0; q < PB; ++q) bw += (PB * g + q < TC && PB * (PB * g + q) + w < n) ? 1 : 0;
-        return bw;
-    };
     for (ll p = blockIdx.x; p < count; p += gridDim.x) {
         double *B = blocks + p * stride;
         if (searcher) {
-            unsigned usedmask = 0;      // bit s of lane l <-> row l + 32 s has been a pivot row
-            int it = 0;
-            for (int j = 0; j < NPAN; ++j) {
-                const int bw = width(j);
-                if (bw == 0) continue;
+            unsigned usedmask = 0;      // bit s of lane l <-> row l + 32 s has been a pivot row (rows >= n count as used)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) if (lane + 32 * s >= n) usedmask |= 1u << s;
+            for (int it = 0; it < NPE; ++it) {
+                const int j = s_pj[it], bw = s_pbw[it];
                 const int buf = it & 1, g = j / PB, w = j - PB * g;
-                ++it;
                 nbar_sync(1, all);                                    // panel j is in Pcol[buf]
                 double x[4][PB];
 #pragma unroll
@@ -710,23 +724,21 @@ ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, 
                     if (t < bw && !bad) {
                         int prow = PB * (PB * g + t) + w;            // unpivoted: the diagonal entry of this column
                         if (kPivot) {
-                            unsigned long long bestk = 0ull;
+                            // largest |x|, lowest row on ties; integer compares on the bit pattern (|v| orders like its
+                            // bits); exact zeros are no candidates, so a zero column ends with prow >= n (singular)
+                            unsigned bh = 0u, bl = 0u;
                             int bi = 1 << 30;
 #pragma unroll
                             for (int s = 0; s < 4; ++s) {
-                                const int i = lane + 32 * s;
-                                if (i < n && !((usedmask >> s) & 1u)) {
-                                    const double v = fabs(x[s][t]);
-                                    const unsigned long long key = (v == v) ? (unsigned long long)__double_as_longlong(v) : 0ull;   // |v| orders like its bits
-                                    if (bi == (1 << 30) || key > bestk) { bestk = key; bi = i; }
-                                }
+                                const unsigned kh = (unsigned)__double2hiint(x[s][t]) & 0x7fffffffu, kl = (unsigned)__double2loint(x[s][t]);
+                                const bool better = !((usedmask >> s) & 1u) && (kh > bh || (kh == bh && kl > bl));
+                                if (better) { bh = kh; bl = kl; bi = lane + 32 * s; }
                             }
                             const bool have = bi < (1 << 30);
-                            const unsigned hi = (unsigned)(bestk >> 32), lo = (unsigned)bestk;
-                            const unsigned mh = __reduce_max_sync(0xffffffffu, have ? hi : 0u);
-                            const bool in1 = have && hi == mh;
-                            const unsigned ml = __reduce_max_sync(0xffffffffu, in1 ? lo : 0u);
-                            prow = (int)__reduce_min_sync(0xffffffffu, (in1 && lo == ml) ? (unsigned)bi : 0x7fffffffu);
+                            const unsigned mh = __reduce_max_sync(0xffffffffu, have ? bh : 0u);
+                            const bool in1 = have && bh == mh;
+                            const unsigned ml = __reduce_max_sync(0xffffffffu, in1 ? bl : 0u);
+                            prow = (int)__reduce_min_sync(0xffffffffu, (in1 && bl == ml) ? (unsigned)bi : 0x7fffffffu);
                         }
                         if (prow >= n) bad = true;
                         else {
@@ -800,15 +812,12 @@ ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, 
                 for (int r = 0; r < 8; ++r) Pcol[0][qt][ppos(r0 + r)] = a[r][0];
             }
             nbar_arrive(1, all);
-            int fail = 0, it = 0;
-            int j = 0;
-            while (j < NPAN && width(j) == 0) ++j;
-            while (j < NPAN) {
-                const int bw = width(j), buf = it & 1, g = j / PB, w = j - PB * g;
-                ++it;
-                int jn = j + 1;                                       // the next non-empty panel
-                while (jn < NPAN && width(jn) == 0) ++jn;
-                const int gn = jn / PB, wn = jn - PB * gn, bwn = jn < NPAN ? width(jn) : 0;
+            int fail = 0;
+            for (int it = 0; it < NPE; ++it) {
+                const int j = s_pj[it], bw = s_pbw[it], buf = it & 1, g = j / PB, w = j - PB * g;
+                const bool more = it + 1 < NPE;                        // the next non-empty panel
+                const int jn = more ? s_pj[it + 1] : 0, bwn = more ? s_pbw[it + 1] : 0;
+                const int gn = jn / PB, wn = jn - PB * gn;
                 nbar_sync(2, all);                                    // the pivots of panel j are known
                 int pl[PB];
 #pragma unroll
@@ -834,7 +843,7 @@ ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, 
                 }
                 nbar_sync(3, W);
                 const bool in_panel = owner && gt == g && qt < bw;
-                const bool in_next = owner && jn < NPAN && gt == gn && qt < bwn;
+                const bool in_next = owner && more && gt == gn && qt < bwn;
                 // look-ahead: the next panel's columns first, then they go to the searcher
                 if (in_next) {
 #define EARLY_COL(C)                                                                                                    \
@@ -857,7 +866,7 @@ ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, 
                     }
 #undef EARLY_COL
                 }
-                if (jn < NPAN) nbar_arrive(1, all);
+                if (more) nbar_arrive(1, all);
                 const int skip1 = in_panel ? w : -1, skip2 = in_next ? wn : -1;
                 if (owner) {
 #pragma unroll
@@ -891,7 +900,6 @@ ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, 
                     }
 #undef TAKE_COL
                 }
-                j = jn;
             }
             // all pivots are known (the last pivot barrier has been passed): invert the permutation and store
             if (!fail && tid < n) qinv[perm[tid]] = tid;       // perm is incomplete after a failure
