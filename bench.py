@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--workload", default="poisson_hex", choices=["poisson_hex", "elasticity_tets"],
                     help="poisson_hex = BASELINE.json configs[2] (default); elasticity_tets = configs[3]: vector P2 linear elasticity on a Freudenthal tet mesh (N=1 only)")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="patches in the CPU-baseline sample")
+    ap.add_argument("--operator", default="csr", choices=["csr", "elements"],
+                    help="source of the patch operators: the assembled CSR (extract kernel, default) or element matrices (the reference's own route; hex workloads, no CSR is built: the CPU baseline and the packed-symmetric extra are skipped)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--apply-variant", type=int, default=None, help="ssc_apply_variant (kernel selection; default = library default)")
@@ -101,8 +103,29 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------------------------
+def bind_near_gpu(local_rank):
+    """Pin this process to the CPUs NVML reports as local to its GPU, before any pinned host memory is allocated, so
+    the staging buffers of the host<->device copies sit on the GPU's own NUMA node (8 ranks sharing one node's memory
+    controllers halve each other's PCIe throughput).  Best effort: silently does nothing where NVML or the CPU set is
+    unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {i for i in range(64 * words) if (int(mask[i // 64]) >> (i % 64)) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def build_problem(args, rank, nranks):
-    """Local slab of the (c, c, c*nranks) Q_p problem: discretisation, CSR provider, SF description."""
+    """Local slab of the (c*nranks, c, c) Q_p problem: discretisation, CSR provider, SF description."""
     from ssc_b200 import fem, plex
     from ssc_b200 import partition
     t0 = time.time()
@@ -120,7 +143,7 @@ def build_problem(args, rank, nranks):
         disc = fem.Discretisation([V])
         slab = None
     else:
-        slab = partition.ZSlab((c, c, c * nranks), p, rank, nranks)
+        slab = partition.XSlab((c * nranks, c, c), p, rank, nranks)   # cut along the slowest axis: interface dofs contiguous at the ends
         V, disc = slab.space, slab.discretisation
     info = {"t_mesh": time.time() - t0}
     return V, disc, slab, info
@@ -215,8 +238,9 @@ def workload_config(args, nranks):
                 "cells_per_gpu": 6 * c ** 3, "degree": 2, "parallelism": "single GPU", "exchange": None,
                 "l2": "L2 flushed between timed steps" }
     return {"workload": "3D Q%d Poisson, %dx%dx%d hex cells%s, vertex-star patches, additive, stored inverse (sub_pc_type lu)"
-                        % (p, c, c, c * nranks, " (z-slabs of %d^3 per GPU)" % c if nranks > 1 else ""),
+                        % (p, c * nranks, c, c, " (x-slabs of %d^3 per GPU)" % c if nranks > 1 else ""),
             "cells_per_gpu": c ** 3, "degree": p, "parallelism": "patches by mesh slab x%d" % nranks, "exchange": getattr(args, "exchange_used", None),
+            "operator": "assembled CSR -> extract kernel" if args.operator == "csr" else "one shared element matrix -> assemble kernel (no CSR)",
             "l2": "inputs larger than L2 (patch blocks %.1f GB per GPU), no flush" % (8 * ((2 * p - 1) ** 3) ** 2 * (c - 1) ** 3 / 1e9)}
 
 
@@ -230,6 +254,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, nranks)
         return
+    ncpus_bound = bind_near_gpu(local_rank) if nranks > 1 else 0
     dist = None
     if nranks > 1:
         import torch.distributed as dist          # rendezvous + barrier only (gloo); the data path is the library's own NCCL
@@ -241,7 +266,10 @@ def main():
 
     V, disc, slab, info = build_problem(args, rank, nranks)
     t0 = time.time()
-    csr = operator_csr(V, disc)
+    elements = args.operator == "elements"
+    if elements and args.workload != "poisson_hex":
+        raise SystemExit("--operator elements is wired for the hex workloads")
+    csr = None if elements else operator_csr(V, disc)
     info["t_assemble"] = time.time() - t0
 
     pc = PC(device=local_rank)
@@ -249,7 +277,11 @@ def main():
     pc.setOption("ssc_builder_threads", max(1, min(32, (os.cpu_count() or 1) // nranks)))
     setup_patch_pc(pc, disc, None)
     pc._compute_op = None
-    pc.setOperatorCSR(*csr)
+    if elements:
+        from ssc_b200 import fem
+        pc.setElementMatrices(fem.element_matrix_tensor(V))      # all cells of the tensor mesh are congruent: one shared matrix
+    else:
+        pc.setOperatorCSR(*csr)
     if args.apply_variant is not None:
         pc.setOption("ssc_apply_variant", args.apply_variant)
     if args.deterministic:
@@ -288,11 +320,11 @@ def main():
     if nranks > 1:
         pc.releaseOperator()         # the CSR was only borrowed until SetUp returned; N=1 keeps it for the CPU baseline
         csr = None
-    setup = {"note": "setup_wall_s = SSCPatchSetUp with the CSR in pageable host memory: patch construction on the host, H2D of dof lists and CSR, extract, factor", "create_patches_ms": pc.eventTime("PCPATCHCreate"), "extract_ms": pc.eventTime("PCPATCHComputeOp"),
+    setup = {"note": "setup_wall_s = SSCPatchSetUp with the CSR in pageable host memory: patch construction on the host, H2D of dof lists and CSR, extract, factor" if not elements else "setup_wall_s = SSCPatchSetUp from one shared element matrix: patch construction on the host, H2D of dof lists / cell lists / cell-node maps, assemble kernel (extract_ms), factor", "create_patches_ms": pc.eventTime("PCPATCHCreate"), "extract_ms": pc.eventTime("PCPATCHComputeOp"),
              "factor_ms": pc.eventTime("PCPATCHSolve"), "lists_ms": pc.eventTime("SSCSetupLists"), "upload_operator_ms": pc.eventTime("SSCSetupUploadOperator"),
              "alloc_blocks_ms": pc.eventTime("SSCSetupAllocBlocks"), "setup_wall_s": info["t_setup_wall"],
              "assemble_wall_s": info["t_assemble"], "mesh_wall_s": info["t_mesh"]}
-    if setup["extract_ms"] > 0:
+    if setup["extract_ms"] > 0 and not elements:
         setup["extract_gbs"] = pc.size("bytes_extract") / (setup["extract_ms"] * 1e-3) / 1e9      # algorithmic bytes of SURVEY.md 8(d)
     if setup["factor_ms"] > 0:
         setup["factor_tflops"] = pc.size("flops_factor") / (setup["factor_ms"] * 1e-3) / 1e12     # 2 n^3 per block (fp64)
@@ -362,7 +394,7 @@ def main():
         ems = _max_over_ranks(dist, pc.eventElapsed(e0, e1), nranks) / args.steps
         barrier()
         e2e = {"value": nglobal / (ems * 1e-3), "unit": "dofs/s", "h2d_bytes_per_step": 8 * nowned, "d2h_bytes_per_step": 8 * nowned,
-               "ms_per_step": ems, "api": "ssc_b200.PC.apply(x, y) on pinned host vectors (SSCPatchApply, SSC_MEM_HOST)"}
+               "ms_per_step": ems, "api": "ssc_b200.PC.apply(x, y) on pinned host vectors (SSCPatchApply, SSC_MEM_HOST)", "cpus_bound_near_gpu": ncpus_bound}
 
     # size-independent property at full size (all N): the additive operator is symmetric for an SPD problem, so
     # <M a, b> == <a, M b> over the whole (distributed) vector; a broken halo fill or overlap sum breaks it
@@ -416,12 +448,12 @@ def main():
            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "setup": setup, "symmetry_check": symmetry}
     if flush:
         out["config"]["l2"] = "working set %.2f GB: L2 flushed (256 MB write) before every timed step, each step timed on its own" % (pc.size("block_bytes") / 1e9)
-    if nranks == 1 and not args.no_spd_packed and args.workload == "poisson_hex":
+    if nranks == 1 and not args.no_spd_packed and args.workload == "poisson_hex" and not elements:
         try:
             out["spd_packed"] = spd_packed_line(args, disc, csr, dx, dy, peak)
         except Exception as exc:                     # an extra, never allowed to take the main line down
             out["spd_packed"] = {"error": str(exc)}
-    if nranks == 1 and not args.no_cpu_baseline:
+    if nranks == 1 and not args.no_cpu_baseline and not elements:
         pc.apply(dx, dy)
         pc.synchronize()
         out["cpu_baseline"] = cpu_baseline(V, disc, csr, args, x=np.array(xh.array), y_gpu=dy.get())

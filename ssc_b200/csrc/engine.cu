@@ -213,6 +213,15 @@ struct SSCPatchPC_s {
     std::vector<std::vector<std::pair<i64, i64>>> pipe_ranges;   // [slab][class] -> sorted positions [q0, q1)
     std::vector<i64> pipe_in, pipe_out, pipe_bc;                 // x piece bounds, y piece bounds, bc list offsets per y piece
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    // the same with neighbour ranks (peer exchange): pieces of x / y over the owned dofs, slabs that touch ghosts first
+    struct PeerPipe {
+        std::vector<i64> cut, bc_off;                 // piece p = owned dofs [cut[p], cut[p+1]); Dirichlet list offsets per piece
+        std::vector<int> copy_order, slab_order;      // H2D order of the pieces (those holding interface values first); launch order of the slabs
+        std::vector<std::pair<int, int>> slab_pieces; // pieces [first, last] a slab reads owned entries from
+        std::vector<char> slab_ghost, piece_late;     // slab touches ghost dofs; piece holds interface dofs (final only after the fold)
+        std::vector<int> piece_ready;                 // position in slab_order after which the piece is complete
+        int nsend_pieces = 0, nghost_slabs = 0;
+    } pp;
     std::vector<cudaEvent_t> ev_in, ev_k;
     // timing
     std::map<std::string, double> event_ms;
@@ -1236,6 +1245,7 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
 }
 
 static int build_host_pipeline(PC *pc);
+static int build_peer_pipeline(PC *pc);
 static int compute_weights(PC *pc)
 {
     // ssc/libssc.c:1254-1284: scatter ones through every patch, reduce to owners, reciprocal
@@ -1498,6 +1508,148 @@ static int apply_device(PC *pc, const double *x, double *y)
     return 0;
 }
 
+// Slab schedule for host-space applies when neighbour ranks take part (peer exchange).  Same slabs by patch number as
+// below, but (i) the pieces of x that hold interface values travel first, so the halo push and the first neighbour
+// barrier happen a fraction of a millisecond into the apply, (ii) the slabs that touch ghost dofs run first and the
+// rank announces the second barrier right after them -- the neighbours' contributions to this rank's interface dofs
+// are complete long before the interior slabs are -- and (iii) the pieces of y that hold interface dofs leave last,
+// after the fold; every other piece leaves as soon as the slabs that write into it are done.
+static int build_peer_pipeline(PC *pc)
+{
+    const int S = pc->pipe_slabs;
+    const PatchLists &L = pc->lists;
+    const i64 np = L.npatch, N = pc->nowned;
+    PC::PeerPipe &P = pc->pp;
+    std::vector<i64> lo(S, N), hi(S, -1);
+    P.slab_ghost.assign(S, 0);
+    pc->pipe_ranges.assign(S, std::vector<std::pair<i64, i64>>(pc->classes.size()));
+    for (int s = 0; s < S; ++s) {
+        const i64 p0 = np * s / S, p1 = np * (s + 1) / S;
+        for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
+            const SizeClass &c = pc->classes[ci];
+            auto first = pc->sorted2orig.begin() + c.first, last = first + c.count;
+            pc->pipe_ranges[s][ci] = {std::lower_bound(first, last, p0) - pc->sorted2orig.begin(), std::lower_bound(first, last, p1) - pc->sorted2orig.begin()};
+        }
+        for (i64 p = p0; p < p1; ++p)
+            for (i64 k = L.gtolOff[p]; k < L.gtolOff[p + 1]; ++k) {
+                const i64 g = L.gtol[k];
+                if (g >= N) P.slab_ghost[s] = 1;
+                else { lo[s] = std::min(lo[s], g); hi[s] = std::max(hi[s], g); }
+            }
+    }
+    P.cut.assign(S + 1, 0);
+    i64 run = 0;
+    for (int s = 0; s < S; ++s) { run = std::max(run, hi[s] + 1); P.cut[s + 1] = s == S - 1 ? N : run; }
+    auto piece_of = [&](i64 g) { return (int)(std::upper_bound(P.cut.begin() + 1, P.cut.end(), g) - (P.cut.begin() + 1)); };
+    P.slab_pieces.assign(S, {0, -1});
+    for (int s = 0; s < S; ++s) if (hi[s] >= 0) P.slab_pieces[s] = {std::min(piece_of(lo[s]), S - 1), std::min(piece_of(hi[s]), S - 1)};
+    // launch order: ghost-touching slabs first
+    P.slab_order.clear();
+    for (int s = 0; s < S; ++s) if (P.slab_ghost[s]) P.slab_order.push_back(s);
+    P.nghost_slabs = (int)P.slab_order.size();
+    for (int s = 0; s < S; ++s) if (!P.slab_ghost[s]) P.slab_order.push_back(s);
+    // copy order: pieces with interface values first, then the pieces in the order the slabs ask for them
+    std::vector<char> has_send(S, 0), placed(S, 0);
+    P.piece_late.assign(S, 0);
+    for (i64 g : pc->sendRoot) if (g >= 0 && g < N) { const int q = std::min(piece_of(g), S - 1); has_send[q] = 1; P.piece_late[q] = 1; }
+    P.copy_order.clear();
+    for (int q = 0; q < S; ++q) if (has_send[q]) { P.copy_order.push_back(q); placed[q] = 1; }
+    P.nsend_pieces = (int)P.copy_order.size();
+    for (int s : P.slab_order)
+        for (int q = P.slab_pieces[s].first; q <= P.slab_pieces[s].second; ++q) if (!placed[q]) { P.copy_order.push_back(q); placed[q] = 1; }
+    for (int q = 0; q < S; ++q) if (!placed[q]) P.copy_order.push_back(q);
+    // a piece of y is complete after the last (in launch order) slab that writes into it
+    P.piece_ready.assign(S, -1);
+    for (int pos = 0; pos < S; ++pos) {
+        const int s = P.slab_order[pos];
+        for (int q = P.slab_pieces[s].first; q <= P.slab_pieces[s].second; ++q) P.piece_ready[q] = std::max(P.piece_ready[q], pos);
+    }
+    std::vector<i64> bc;
+    for (i64 d : pc->globalBc) if (d >= 0 && d < N) bc.push_back(d);
+    if (!std::is_sorted(bc.begin(), bc.end())) return 0;
+    P.bc_off.assign(S + 1, 0);
+    for (int q = 0; q <= S; ++q) P.bc_off[q] = std::lower_bound(bc.begin(), bc.end(), P.cut[q]) - bc.begin();
+    if (!pc->s_in) {
+        CUDA_OK(cudaStreamCreateWithFlags(&pc->s_in, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&pc->s_out, cudaStreamNonBlocking));
+    }
+    while ((int)pc->ev_in.size() < S + 1) {
+        cudaEvent_t a, b;
+        CUDA_OK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        pc->ev_in.push_back(a); pc->ev_k.push_back(b);
+    }
+    pc->pipe_ready = true;
+    return 0;
+}
+
+static int apply_host_pipelined_peer(PC *pc, const double *x, double *y)
+{
+    const int S = pc->pipe_slabs, nn = (int)pc->neigh.size();
+    const PC::PeerPipe &P = pc->pp;
+    double *dx = pc->d_xs, *dy = pc->d_ys;
+    const double scale = pc->symmetrise_sweep ? 2.0 : 1.0;
+    // SSC_PIPE_TRACE=1: per-apply timeline on stderr (ms after the start: halo barrier passed, ghost slabs done, all
+    // slabs done, neighbours' second barrier collected, last byte of y on the host)
+    static const bool trace = getenv("SSC_PIPE_TRACE") != nullptr;
+    static cudaEvent_t tev[6];
+    if (trace && !tev[0]) for (auto &e : tev) cudaEventCreate(&e);
+    if (trace) cudaEventRecord(tev[0], pc->stream);
+    CUDA_OK(cudaMemsetAsync(dy, 0, (size_t)pc->nowned * sizeof(double), pc->stream));
+    CUDA_OK(cudaEventRecord(pc->ev_k[S], pc->stream));
+    CUDA_OK(cudaStreamWaitEvent(pc->s_in, pc->ev_k[S], 0));        // do not overwrite x while an earlier apply still reads it
+    for (int q : P.copy_order) {
+        const i64 a = P.cut[q], b = P.cut[q + 1];
+        if (b > a) CUDA_OK(cudaMemcpyAsync(dx + a, x + a, (size_t)(b - a) * sizeof(double), cudaMemcpyHostToDevice, pc->s_in));
+        CUDA_OK(cudaEventRecord(pc->ev_in[q], pc->s_in));
+    }
+    // halo push as soon as the interface values are on the device, then the first neighbour barrier
+    for (int i = 0; i < P.nsend_pieces; ++i) CUDA_OK(cudaStreamWaitEvent(pc->stream, pc->ev_in[P.copy_order[i]], 0));
+    CHK(peer_bcast(pc, dx));
+    if (trace) cudaEventRecord(tev[1], pc->stream);
+    const unsigned long long e2 = ++pc->epoch;                    // the second barrier of this apply, in two halves
+    auto emit_piece = [&](int q) -> int {
+        const i64 a = P.cut[q], b = P.cut[q + 1];
+        const i64 nb = P.bc_off[q + 1] - P.bc_off[q];
+        if (nb > 0) { ssc_bc_kernel<<<grid_for(nb, 256), 256, 0, pc->stream>>>(pc->d_bc + P.bc_off[q], nb, dx, dy); pc->launches++; }
+        if (pc->partition_of_unity && b > a) { ssc_scale_kernel<<<grid_for(b - a, 256), 256, 0, pc->stream>>>(b - a, pc->d_w + a, dy + a); pc->launches++; }
+        CUDA_OK(cudaEventRecord(pc->ev_k[q], pc->stream));
+        CUDA_OK(cudaStreamWaitEvent(pc->s_out, pc->ev_k[q], 0));
+        if (b > a) CUDA_OK(cudaMemcpyAsync(y + a, dy + a, (size_t)(b - a) * sizeof(double), cudaMemcpyDeviceToHost, pc->s_out));
+        return 0;
+    };
+    auto signal = [&]() -> int {
+        if (nn) { ssc_peer_signal_kernel<<<1, 32, 0, pc->stream>>>(nn, pc->h_flags, e2); pc->launches++; }
+        return 0;
+    };
+    if (P.nghost_slabs == 0) CHK(signal());
+    for (int pos = 0; pos < S; ++pos) {
+        const int s = P.slab_order[pos];
+        for (int q = P.slab_pieces[s].first; q <= P.slab_pieces[s].second; ++q) CUDA_OK(cudaStreamWaitEvent(pc->stream, pc->ev_in[q], 0));
+        for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
+            const SizeClass &c = pc->classes[ci];
+            const i64 q0 = pc->pipe_ranges[s][ci].first, q1 = pc->pipe_ranges[s][ci].second;
+            if (q1 > q0) CHK(launch_apply_class(pc, c, q0, q1, nullptr, dx, dy, scale));
+        }
+        if (pos == P.nghost_slabs - 1) { CHK(signal()); if (trace) cudaEventRecord(tev[2], pc->stream); }   // nothing after this point writes to a neighbour
+        for (int q = 0; q < S; ++q) if (P.piece_ready[q] == pos && !P.piece_late[q]) CHK(emit_piece(q));
+    }
+    if (trace) cudaEventRecord(tev[3], pc->stream);
+    if (nn) { ssc_peer_wait_kernel<<<1, 32, 0, pc->stream>>>(nn, pc->d_flags, e2, pc->d_timeout); pc->launches++; }
+    if (trace) cudaEventRecord(tev[4], pc->stream);
+    if (pc->niface) { ssc_peer_fold_kernel<<<grid_for(pc->niface, 256), 256, 0, pc->stream>>>(pc->niface, pc->d_iface, pc->d_yin, dy); pc->launches++; }
+    for (int q = 0; q < S; ++q) if (P.piece_late[q] || P.piece_ready[q] < 0) CHK(emit_piece(q));
+    CUDA_OK(cudaGetLastError());
+    if (trace) cudaEventRecord(tev[5], pc->s_out);
+    CUDA_OK(cudaStreamSynchronize(pc->s_out));
+    CUDA_OK(cudaStreamSynchronize(pc->stream));
+    if (trace) {
+        float t[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 1; i < 6; ++i) cudaEventElapsedTime(&t[i], tev[0], tev[i]);
+        fprintf(stderr, "[ssc pipe rank %d] halo %.2f  ghost slabs %.2f  all slabs %.2f  neighbours %.2f  y home %.2f ms\n", getenv("RANK") ? atoi(getenv("RANK")) : 0, t[1], t[2], t[3], t[4], t[5]);
+    }
+    return 0;
+}
+
 // Slab schedule for host-space applies.  Patches keep their construction (mesh) order inside a size class, and dof
 // numbers follow the mesh too, so consecutive patches touch a moving window of x and y.  The patch list is cut into
 // S slabs by original patch number; slab s can start once x[0, in[s+1]) has arrived and, once it is done,
@@ -1507,8 +1659,9 @@ static int build_host_pipeline(PC *pc)
 {
     pc->pipe_ready = false;
     const int S = pc->pipe_slabs;
-    if (S < 2 || pc->sf_set || pc->multiplicative || pc->deterministic || !pc->save_operators || (!pc->pipe_force && pc->sum_n2 * 8 < ((i64)64 << 20))) return 0;
+    if (S < 2 || (pc->sf_set && !pc->p2p) || pc->multiplicative || pc->deterministic || !pc->save_operators || (!pc->pipe_force && pc->sum_n2 * 8 < ((i64)64 << 20))) return 0;
     if (pc->lists.npatch < S) return 0;
+    if (pc->sf_set) return build_peer_pipeline(pc);
     const PatchLists &L = pc->lists;
     const i64 np = L.npatch, N = pc->nowned;
     std::vector<i64> lo(S, N), hi(S, -1);
@@ -1594,7 +1747,7 @@ extern "C" int SSCPatchApply(SSCPatchPC pc, const double *x, double *y, int mems
     if (!pc->d_xs) { CHK(dev_alloc(&pc->d_xs, pc->nowned)); CHK(dev_alloc(&pc->d_ys, pc->nowned)); }
     if (!pc->pipe_ready && !pc->pipe_tried) { pc->pipe_tried = true; CHK(build_host_pipeline(pc)); }
     if (pc->pipe_ready && pc->partition_of_unity && !pc->d_w) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "partition of unity was switched on after the first setup");
-    if (pc->pipe_ready) return apply_host_pipelined(pc, x, y);
+    if (pc->pipe_ready) return pc->sf_set ? apply_host_pipelined_peer(pc, x, y) : apply_host_pipelined(pc, x, y);
     CUDA_OK(cudaMemcpyAsync(pc->d_xs, x, (size_t)pc->nowned * sizeof(double), cudaMemcpyHostToDevice, pc->stream));
     CHK(apply_device(pc, pc->d_xs, pc->d_ys));
     CUDA_OK(cudaMemcpyAsync(y, pc->d_ys, (size_t)pc->nowned * sizeof(double), cudaMemcpyDeviceToHost, pc->stream));

@@ -1471,6 +1471,28 @@ __global__ void ssc_peer_barrier_kernel(int nneigh, PeerFlags peers, volatile un
     __threadfence_system();
 }
 
+// The two halves of the neighbour barrier as separate launches: a rank can announce "my patches that touch other
+// ranks' dofs are done" early and collect the neighbours' announcements late (pipelined host-space apply).
+__global__ void ssc_peer_signal_kernel(int nneigh, PeerFlags peers, unsigned long long epoch)
+{
+    const int k = threadIdx.x;
+    if (k >= nneigh) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flags[k] + peers.slot[k]), "l"(epoch) : "memory");
+}
+__global__ void ssc_peer_wait_kernel(int nneigh, volatile unsigned long long *mine, unsigned long long epoch, int *timeout)
+{
+    const int k = threadIdx.x;
+    if (k >= nneigh) return;
+    const long long t0 = clock64();
+    unsigned long long v;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + k) : "memory");
+        if (clock64() - t0 > 8000000000LL) { *timeout = 1; break; }      // ~4 s
+    } while (v < epoch);
+    __threadfence_system();
+}
+
 // r = x - A y, one warp per row (residual between the colours of a multiplicative sweep)
 __global__ void ssc_residual_kernel(ll nrows, const ll *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals,
                                     const double *__restrict__ x, const double *__restrict__ y, double *__restrict__ r)

@@ -12,36 +12,55 @@ from . import fem, plex
 from .plex import IntType
 
 
-class ZSlab(object):
-    """Rank ``rank`` of ``nranks`` z-slabs of a structured (cx, cy, cz) box of tensor cells, degree p.
+class Slab(object):
+    """Rank ``rank`` of ``nranks`` slabs of a structured (cx, cy, cz) box of tensor cells, degree p, cut along ``axis``.
 
     Vertex planes are dealt out in contiguous ranges; the local mesh holds every cell that touches an owned
     vertex.  Local dofs are numbered owned first, then ghosts.  ``global_ids`` maps local node -> node of the
     global lattice (used only to match ghosts with their owners at set-up).
+
+    ``axis = 0`` (the slowest axis of the cell, patch and dof numbering) keeps a rank's interface dofs and the patches
+    that touch ghosts contiguous at the two ends of its numbering -- what the overlapped host-space apply wants;
+    ``axis = 2`` scatters them through the whole numbering (every x-range of the slab touches the interface).
     """
 
-    def __init__(self, cells, p, rank, nranks):
-        cx, cy, cz = cells
-        k0 = rank * cz // nranks
-        k1 = (rank + 1) * cz // nranks if rank < nranks - 1 else cz + 1     # owned vertex planes [k0, k1)
-        lo, hi = max(k0 - 1, 0), min(k1 - 1, cz - 1)                        # local cell layers [lo, hi]
+    def __init__(self, cells, p, rank, nranks, axis=2):
+        cells = tuple(int(c) for c in cells)
+        ca = cells[axis]
+        k0 = rank * ca // nranks
+        k1 = (rank + 1) * ca // nranks if rank < nranks - 1 else ca + 1     # owned vertex planes [k0, k1)
+        lo, hi = max(k0 - 1, 0), min(k1 - 1, ca - 1)                        # local cell layers [lo, hi]
         nl = hi - lo + 1
-        h = 1.0 / cx
-        mesh = plex.TensorPlex((cx, cy, nl), lengths=(cx * h, cy * h, nl * h))
-        mesh.mark_ghost_vertices(2, k0 - lo, k1 - 1 - lo)
+        h = 1.0 / cells[(axis + 1) % 3]
+        local = list(cells)
+        local[axis] = nl
+        mesh = plex.TensorPlex(tuple(local), lengths=tuple(c * h for c in local))
+        mesh.mark_ghost_vertices(axis, k0 - lo, k1 - 1 - lo)
         V = fem.FunctionSpace(mesh, p)
-        self.mesh, self.space, self.rank, self.nranks = mesh, V, rank, nranks
+        self.mesh, self.space, self.rank, self.nranks, self.axis = mesh, V, rank, nranks, axis
         self.nowned = V.owned_node_count
-        L = np.indices(V.lattice_shape).reshape(3, -1)
-        gz = L[2] + p * lo
-        gshape = (p * cx + 1, p * cy + 1, p * cz + 1)
-        gid = np.ravel_multi_index((L[0], L[1], gz), gshape)
+        L = list(np.indices(V.lattice_shape).reshape(3, -1))
+        L[axis] = L[axis] + p * lo
+        gshape = tuple(p * c + 1 for c in cells)
+        gid = np.ravel_multi_index(tuple(L), gshape)
         self.global_ids = np.empty(V.node_count, dtype=IntType)
         self.global_ids[V.lattice_node.ravel()] = gid
-        onb = (L[0] == 0) | (L[0] == gshape[0] - 1) | (L[1] == 0) | (L[1] == gshape[1] - 1) | (gz == 0) | (gz == gshape[2] - 1)
+        onb = np.zeros(gid.size, dtype=bool)
+        for a in range(3):
+            onb |= (L[a] == 0) | (L[a] == gshape[a] - 1)
         bc_nodes = np.sort(V.lattice_node.ravel()[onb])
         self.discretisation = fem.Discretisation([V], bc_nodes=[bc_nodes], owned_nodes=[self.nowned])
         self.global_shape = gshape
+
+
+class ZSlab(Slab):
+    def __init__(self, cells, p, rank, nranks):
+        Slab.__init__(self, cells, p, rank, nranks, axis=2)
+
+
+class XSlab(Slab):
+    def __init__(self, cells, p, rank, nranks):
+        Slab.__init__(self, cells, p, rank, nranks, axis=0)
 
 
 def star_forest(global_ids, nowned, rank, nranks, allgather):

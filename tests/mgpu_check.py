@@ -22,6 +22,7 @@ def main():
     p = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     pou = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     p2p = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    slabs = int(sys.argv[5]) if len(sys.argv) > 5 else 0      # ssc_host_pipeline: negative forces the overlapped host-space apply on a small case
     rank, nranks, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     dist.init_process_group("gloo", rank=rank, world_size=nranks)
 
@@ -29,13 +30,18 @@ def main():
         out = [None] * nranks
         dist.all_gather_object(out, obj)
         return out
-    slab = partition.ZSlab((c, c, c * nranks), p, rank, nranks)
+    axis = int(sys.argv[6]) if len(sys.argv) > 6 else 0       # slabs cut along x (default) or z
+    cells, lengths = [c, c, c], [1, 1, 1]
+    cells[axis], lengths[axis] = c * nranks, nranks
+    slab = partition.Slab(tuple(cells), p, rank, nranks, axis=axis)
     pc = PC(device=local)
     setup_patch_pc(pc, slab.discretisation, None)
     pc._compute_op = None
     pc.setOperatorCSR(*synth.tensor_poisson_csr(slab.space, slab.discretisation.ghost_bc_nodes))
     if pou:
         pc.setOption("pc_patch_partition_of_unity", True)
+    if slabs:
+        pc.setOption("ssc_host_pipeline", slabs)
     sf = partition.star_forest(slab.global_ids, slab.nowned, rank, nranks, allgather)
     pc.setStarForest(slab.nowned, *sf)
     if p2p:
@@ -49,13 +55,14 @@ def main():
     x = np.ascontiguousarray(xlat[slab.global_ids[:slab.nowned]])
     y = np.zeros_like(x)
     for _ in range(3):
+        y[:] = np.nan
         pc.apply(x, y)
     pc.synchronize()
     parts = allgather((slab.global_ids[:slab.nowned], y))
     ok = True
     if rank == 0:
         from helpers import make_oracle
-        mesh = plex.TensorPlex((c, c, c * nranks), lengths=(1, 1, nranks))
+        mesh = plex.TensorPlex(tuple(cells), lengths=tuple(lengths))
         V = fem.FunctionSpace(mesh, p)
         disc = fem.Discretisation([V])
         r, ci, v = synth.tensor_poisson_csr(V, disc.ghost_bc_nodes)
@@ -69,7 +76,7 @@ def main():
             ygpu[gid] = yy
         err = np.linalg.norm(ygpu - yref) / np.linalg.norm(yref)
         ok = bool(err < 1e-12)
-        print("mgpu_check ranks=%d cells=%d^2x%d p=%d pou=%d exchange=%s relerr=%.3e %s" % (nranks, c, c * nranks, p, pou, "p2p" if p2p else "nccl", err, "OK" if ok else "FAIL"))
+        print("mgpu_check ranks=%d cells=%d^2x%d p=%d pou=%d exchange=%s host_pipeline=%d axis=%d relerr=%.3e %s" % (nranks, c, c * nranks, p, pou, "p2p" if p2p else "nccl", slabs, axis, err, "OK" if ok else "FAIL"))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -34,7 +34,7 @@ def _oracle_for(disc, V):
     return o
 
 
-def _worker(rank, nranks, port, outdir):
+def _worker(rank, nranks, port, outdir, axis=2):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -48,7 +48,9 @@ def _worker(rank, nranks, port, outdir):
         out = [None] * nranks
         dist.all_gather_object(out, obj)
         return out
-    slab = partition.ZSlab((C, C, C * nranks), P, rank, nranks)
+    cells = [C, C, C]
+    cells[axis] = C * nranks
+    slab = partition.Slab(tuple(cells), P, rank, nranks, axis=axis)
     sl, sr, neigh, so, sroot, ro, rleaf = partition.star_forest(slab.global_ids, slab.nowned, rank, nranks, allgather)
     o = _oracle_for(slab.discretisation, slab.space)
     xlat = np.random.default_rng(7).uniform(-1, 1, int(np.prod(slab.global_shape)))     # same on every rank
@@ -85,12 +87,16 @@ def _worker(rank, nranks, port, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nranks", [2, 3])
-def test_slabs_over_gloo_match_single_rank(nranks, tmp_path):
+@pytest.mark.parametrize("nranks,axis", [(2, 2), (3, 2), (2, 0), (3, 0)])
+def test_slabs_over_gloo_match_single_rank(nranks, axis, tmp_path):
+    """Slabs cut along z (interface dofs scattered through the local numbering) and along x (contiguous at the ends:
+    the layout the overlapped multi-rank host apply is built for)."""
     import torch.multiprocessing as mp
     from ssc_b200 import fem, plex
-    mp.spawn(_worker, args=(nranks, _free_port(), str(tmp_path)), nprocs=nranks, join=True)
-    mesh = plex.TensorPlex((C, C, C * nranks), lengths=(1, 1, nranks))
+    mp.spawn(_worker, args=(nranks, _free_port(), str(tmp_path), axis), nprocs=nranks, join=True)
+    cells, lengths = [C, C, C], [1, 1, 1]
+    cells[axis], lengths[axis] = C * nranks, nranks
+    mesh = plex.TensorPlex(tuple(cells), lengths=tuple(lengths))
     V = fem.FunctionSpace(mesh, P)
     disc = fem.Discretisation([V])
     o = _oracle_for(disc, V)
