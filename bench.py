@@ -2,7 +2,8 @@
 """bench.py -- PCApply throughput of the vertex-star patch preconditioner (BASELINE.json metric).
 
 Workload (config.workload): 3D Q3 Poisson on a 64^3 hex mesh per GPU, vertex-star patches, additive, fp64
-(BASELINE.json configs[2]).  With N GPUs the mesh is (64, 64, 64*N) split into N z-slabs (weak scaling): every rank
+(BASELINE.json configs[2]).  With N GPUs the mesh is (64*N, 64, 64) split into N x-slabs (weak scaling; x is the slowest
+axis of the numbering, so a rank's interface dofs are contiguous at the ends of its vectors): every rank
 builds its own slab (owned vertices + one cell layer of ghosts), patches never cross ranks, and the only exchange is
 the halo fill before and the overlap sum after the patch kernel (SFBcast/SFReduce of ssc/libssc.c:1323, :1399).
 
