@@ -268,8 +268,6 @@ def main():
     V, disc, slab, info = build_problem(args, rank, nranks)
     t0 = time.time()
     elements = args.operator == "elements"
-    if elements and args.workload != "poisson_hex":
-        raise SystemExit("--operator elements is wired for the hex workloads")
     csr = None if elements else operator_csr(V, disc)
     info["t_assemble"] = time.time() - t0
 
@@ -280,7 +278,10 @@ def main():
     pc._compute_op = None
     if elements:
         from ssc_b200 import fem
-        pc.setElementMatrices(fem.element_matrix_tensor(V))      # all cells of the tensor mesh are congruent: one shared matrix
+        if V.mesh.cell_type == "simplex":
+            pc.setElementMatrices(fem.elasticity_element_matrices(V))   # one matrix per tet
+        else:
+            pc.setElementMatrices(fem.element_matrix_tensor(V))      # all cells of the tensor mesh are congruent: one shared matrix
     else:
         pc.setOperatorCSR(*csr)
     if args.apply_variant is not None:

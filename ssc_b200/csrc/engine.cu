@@ -104,6 +104,9 @@ struct SizeClass {
 struct SSCPatchPC_s {
     int device = 0;
     cudaStream_t stream = nullptr, up_stream = nullptr;
+    cudaStream_t side_stream = nullptr, launch_stream = nullptr;   // the small size classes of an apply run beside the big one; launch_apply_class launches on launch_stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap_classes = true;
     int sm_count = 148;
     // options (defaults: PCCreate_PATCH ssc/libssc.c:1697-1711)
     bool save_operators = true, partition_of_unity = false, multiplicative = false, print_patches = false;
@@ -295,6 +298,14 @@ extern "C" int SSCPatchCreate(int device, SSCPatchPC *out)
     CUDA_OK(cudaSetDevice(device));
     CUDA_OK(cudaStreamCreateWithFlags(&pc->stream, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&pc->up_stream, cudaStreamNonBlocking));
+    {
+        int lo_pri = 0, hi_pri = 0;                       // the small classes' blocks take free SM slots first
+        CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        CUDA_OK(cudaStreamCreateWithPriority(&pc->side_stream, cudaStreamNonBlocking, hi_pri));
+    }
+    CUDA_OK(cudaEventCreateWithFlags(&pc->ev_fork, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&pc->ev_join, cudaEventDisableTiming));
+    pc->launch_stream = pc->stream;
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     pc->sm_count = prop.multiProcessorCount;
@@ -360,6 +371,7 @@ extern "C" int SSCPatchDestroy(SSCPatchPC *ppc)
     cudaEventDestroy(pc->ev0); cudaEventDestroy(pc->ev1);
     cudaStreamDestroy(pc->stream);
     cudaStreamDestroy(pc->up_stream);
+    if (pc->side_stream) { cudaStreamDestroy(pc->side_stream); cudaEventDestroy(pc->ev_fork); cudaEventDestroy(pc->ev_join); }
     delete pc;
     *ppc = nullptr;
     return 0;
@@ -469,6 +481,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
         return 0;
     }
     if (name == "ssc_factor_remap") return parse_bool(v, &pc->factor_remap);
+    if (name == "ssc_overlap_classes") return parse_bool(v, &pc->overlap_classes);
     if (name == "ssc_factor_panel") { pc->factor_panel = atoi(v); return 0; }
     if (name == "ssc_factor_ctas") { pc->factor_ctas = atoi(v); return 0; }
     if (name == "ssc_factor_tile") { pc->factor_tile = atoi(v); return 0; }
@@ -1353,7 +1366,7 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
             const int threads_p = rp * Fp;
             const size_t smem_p = (size_t)stages * c.pbytes + (2 * (size_t)c.n + (size_t)(Fp - 1) * rp) * sizeof(double);
             CUDA_OK(cudaFuncSetAttribute(ssc_apply_sym_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-            ssc_apply_sym_persistent_kernel<<<pc->sm_count, threads_p, smem_p, pc->stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, stages, gt,
+            ssc_apply_sym_persistent_kernel<<<pc->sm_count, threads_p, smem_p, pc->launch_stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, stages, gt,
                                                                                         c.n, cnt, xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch);
             pc->launches++;
             CUDA_OK(cudaGetLastError());
@@ -1371,7 +1384,7 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
             }
             const size_t smem2 = (size_t)c.pbytes + (size_t)(c.n + rp) * sizeof(double);
             if (smem2 > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_apply_sym2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            ssc_apply_sym2_kernel<<<(unsigned)cnt, 2 * rp, smem2, pc->stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, j1, bytes0, gt, c.n, cnt,
+            ssc_apply_sym2_kernel<<<(unsigned)cnt, 2 * rp, smem2, pc->launch_stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, j1, bytes0, gt, c.n, cnt,
                                                                            xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch);
             pc->launches++;
             CUDA_OK(cudaGetLastError());
@@ -1380,14 +1393,14 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
         const size_t smem = (size_t)c.pbytes + (size_t)c.n * sizeof(double);
         if (pc->sym_bulk) {
             if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_apply_sym_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ssc_apply_sym_kernel<true><<<(unsigned)cnt, threads, smem, pc->stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, gt, c.n, cnt,
+            ssc_apply_sym_kernel<true><<<(unsigned)cnt, threads, smem, pc->launch_stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, gt, c.n, cnt,
                                                                                   xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch);
             pc->launches++;
             CUDA_OK(cudaGetLastError());
             return 0;
         }
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_apply_sym_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ssc_apply_sym_kernel<false><<<(unsigned)cnt, threads, smem, pc->stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, gt, c.n, cnt,
+        ssc_apply_sym_kernel<false><<<(unsigned)cnt, threads, smem, pc->launch_stream>>>(pc->d_packed + c.poff + (q0 - c.first) * c.pstride, c.pstride, c.pbytes, gt, c.n, cnt,
                                                                         xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch);
         pc->launches++;
         CUDA_OK(cudaGetLastError());
@@ -1400,7 +1413,7 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
 #define LAUNCH_APPLY(K)                                                                                                  \
     do {                                                                                                                 \
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        K<<<(unsigned)grid, threads, smem, pc->stream>>>(blocks, c.stride, c.ld, gt, c.n, cnt, c.tp, c.ppb, xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch); \
+        K<<<(unsigned)grid, threads, smem, pc->launch_stream>>>(blocks, c.stride, c.ld, gt, c.n, cnt, c.tp, c.ppb, xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch); \
     } while (0)
     if (pc->apply_variant == 2 && threads <= 256) LAUNCH_APPLY((ssc_apply_pipe_kernel<2, 8>));
     else if (pc->apply_variant == 1 && threads <= 256) LAUNCH_APPLY((ssc_apply_pipe_kernel<1, 8>));
@@ -1476,7 +1489,29 @@ static int apply_device(PC *pc, const double *x, double *y)
         CUDA_OK(cudaEventRecord(k0, pc->stream));
     }
     if (pc->save_operators) {
-        for (const SizeClass &c : pc->classes) CHK(launch_apply_class(pc, c, c.first, c.first + c.count, nullptr, xl, yl, scale));
+        // the size class with the most bytes goes first on the apply stream; the others run beside it on a second
+        // stream (their launch gaps, ramps and tails disappear under the big kernel; the adds into y commute)
+        size_t big = 0;
+        for (size_t ci = 1; ci < pc->classes.size(); ++ci)
+            if (pc->classes[ci].count * pc->classes[ci].stride > pc->classes[big].count * pc->classes[big].stride) big = ci;
+        const bool fork = pc->overlap_classes && pc->classes.size() > 1 && !pc->deterministic;
+        if (fork) {
+            CUDA_OK(cudaEventRecord(pc->ev_fork, pc->stream));
+            CUDA_OK(cudaStreamWaitEvent(pc->side_stream, pc->ev_fork, 0));
+        }
+        if (!pc->classes.empty()) CHK(launch_apply_class(pc, pc->classes[big], pc->classes[big].first, pc->classes[big].first + pc->classes[big].count, nullptr, xl, yl, scale));
+        if (fork) pc->launch_stream = pc->side_stream;
+        for (size_t ci = pc->classes.size(); ci-- > 0;) {
+            if (ci == big) continue;
+            const SizeClass &c = pc->classes[ci];
+            const int rc = launch_apply_class(pc, c, c.first, c.first + c.count, nullptr, xl, yl, scale);
+            if (rc) { pc->launch_stream = pc->stream; return rc; }
+        }
+        pc->launch_stream = pc->stream;
+        if (fork) {
+            CUDA_OK(cudaEventRecord(pc->ev_join, pc->side_stream));
+            CUDA_OK(cudaStreamWaitEvent(pc->stream, pc->ev_join, 0));
+        }
     } else {
         // -pc_patch_save_operators false: rebuild, factorise, use and drop every patch operator inside the apply
         // (ssc/libssc.c:1363-1382), in batches that fit a bounded scratch buffer

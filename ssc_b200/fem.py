@@ -301,8 +301,10 @@ def assemble_poisson_simplex(V):
     return _coo_to_csr(V.node_count, rows, cols, Ke), Ke
 
 
-def assemble_elasticity_simplex(V, lmbda=1.0, mu=1.0):
-    """Linear elasticity 2 mu eps(u):eps(v) + lambda div u div v on a vector simplicial space (dof numbering)."""
+def elasticity_element_matrices(V, lmbda=1.0, mu=1.0):
+    """Element matrices of 2 mu eps(u):eps(v) + lambda div u div v on a vector simplicial space, one (nb d) x (nb d)
+    matrix per cell, cell dofs node by node, component by component (what the reference's element kernel computes per
+    cell, ssc/patch.py:28-62)."""
     m, d = V.mesh, V.mesh.dim
     assert V.bs == d
     lam, w = simplex_quadrature(d, V.degree + 1)
@@ -311,7 +313,7 @@ def assemble_elasticity_simplex(V, lmbda=1.0, mu=1.0):
     S = np.einsum("q,iqa,jqb->abij", w, dxi, dxi)
     _, Jinv, detJ = _simplex_geometry(m)
     # H[c, r, s, i, j] = int d_r phi_i d_s phi_j
-    H = np.einsum("c,car,cbs,abij->crsij", detJ, Jinv, Jinv, S)
+    H = np.einsum("c,car,cbs,abij->crsij", detJ, Jinv, Jinv, S, optimize=True)
     nb = V.nodes_per_cell
     Ke = np.zeros((m.num_cells, nb, d, nb, d))
     tr = np.einsum("crrij->cij", H)
@@ -320,7 +322,15 @@ def assemble_elasticity_simplex(V, lmbda=1.0, mu=1.0):
             Ke[:, :, a, :, b] = lmbda * H[:, a, b] + mu * H[:, b, a]
             if a == b:
                 Ke[:, :, a, :, b] += mu * tr
-    Ke = Ke.reshape(m.num_cells, nb * d, nb * d)
+    return Ke.reshape(m.num_cells, nb * d, nb * d)
+
+
+def assemble_elasticity_simplex(V, lmbda=1.0, mu=1.0):
+    """Linear elasticity 2 mu eps(u):eps(v) + lambda div u div v on a vector simplicial space (dof numbering).
+    Returns the assembled operator and the element matrices it was summed from."""
+    m, d = V.mesh, V.mesh.dim
+    nb = V.nodes_per_cell
+    Ke = elasticity_element_matrices(V, lmbda, mu)
     dofs = (V.cell_node_list[:, :, None] * d + np.arange(d)[None, None, :]).reshape(m.num_cells, nb * d)
     rows = np.repeat(dofs[:, :, None], nb * d, axis=2)
     cols = np.repeat(dofs[:, None, :], nb * d, axis=1)
