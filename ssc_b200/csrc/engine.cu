@@ -210,7 +210,7 @@ struct SSCPatchPC_s {
     cudaEvent_t stage_ev[3] = {nullptr, nullptr, nullptr};
     bool stage_busy[3] = {false, false, false};
     // pipelined host-space apply: H2D of x, patch kernels and D2H of y overlap slab by slab
-    int pipe_slabs = 8;
+    int pipe_slabs = 12;
     bool pipe_force = false;
     bool pipe_ready = false, pipe_tried = false;
     std::vector<std::vector<std::pair<i64, i64>>> pipe_ranges;   // [slab][class] -> sorted positions [q0, q1)
@@ -1617,6 +1617,40 @@ static int build_peer_pipeline(PC *pc)
     return 0;
 }
 
+// the classes of one slab of a pipelined host-space apply: biggest class on the apply stream, the rest beside it
+static int launch_slab_classes(PC *pc, int slab, const double *dx, double *dy, double scale, const std::vector<int> &input_events)
+{
+    size_t big = 0;
+    i64 best = -1;
+    for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
+        const i64 w = (pc->pipe_ranges[slab][ci].second - pc->pipe_ranges[slab][ci].first) * pc->classes[ci].stride;
+        if (w > best) { best = w; big = ci; }
+    }
+    const bool fork = pc->overlap_classes && pc->classes.size() > 1;
+    if (fork) for (int e : input_events) CUDA_OK(cudaStreamWaitEvent(pc->side_stream, pc->ev_in[e], 0));
+    if (fork) {                                               // and everything already on the apply stream (the memset of y, earlier slabs' Dirichlet rows)
+        CUDA_OK(cudaEventRecord(pc->ev_fork, pc->stream));
+        CUDA_OK(cudaStreamWaitEvent(pc->side_stream, pc->ev_fork, 0));
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
+            if ((pass == 0) != (ci == big)) continue;
+            const SizeClass &c = pc->classes[ci];
+            const i64 q0 = pc->pipe_ranges[slab][ci].first, q1 = pc->pipe_ranges[slab][ci].second;
+            if (q1 <= q0) continue;
+            pc->launch_stream = (fork && pass == 1) ? pc->side_stream : pc->stream;
+            const int rc = launch_apply_class(pc, c, q0, q1, nullptr, dx, dy, scale);
+            pc->launch_stream = pc->stream;
+            if (rc) return rc;
+        }
+    }
+    if (fork) {
+        CUDA_OK(cudaEventRecord(pc->ev_join, pc->side_stream));
+        CUDA_OK(cudaStreamWaitEvent(pc->stream, pc->ev_join, 0));
+    }
+    return 0;
+}
+
 static int apply_host_pipelined_peer(PC *pc, const double *x, double *y)
 {
     const int S = pc->pipe_slabs, nn = (int)pc->neigh.size();
@@ -1659,12 +1693,9 @@ static int apply_host_pipelined_peer(PC *pc, const double *x, double *y)
     if (P.nghost_slabs == 0) CHK(signal());
     for (int pos = 0; pos < S; ++pos) {
         const int s = P.slab_order[pos];
-        for (int q = P.slab_pieces[s].first; q <= P.slab_pieces[s].second; ++q) CUDA_OK(cudaStreamWaitEvent(pc->stream, pc->ev_in[q], 0));
-        for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
-            const SizeClass &c = pc->classes[ci];
-            const i64 q0 = pc->pipe_ranges[s][ci].first, q1 = pc->pipe_ranges[s][ci].second;
-            if (q1 > q0) CHK(launch_apply_class(pc, c, q0, q1, nullptr, dx, dy, scale));
-        }
+        std::vector<int> need;
+        for (int q = P.slab_pieces[s].first; q <= P.slab_pieces[s].second; ++q) { CUDA_OK(cudaStreamWaitEvent(pc->stream, pc->ev_in[q], 0)); need.push_back(q); }
+        CHK(launch_slab_classes(pc, s, dx, dy, scale, need));
         if (pos == P.nghost_slabs - 1) { CHK(signal()); if (trace) cudaEventRecord(tev[2], pc->stream); }   // nothing after this point writes to a neighbour
         for (int q = 0; q < S; ++q) if (P.piece_ready[q] == pos && !P.piece_late[q]) CHK(emit_piece(q));
     }
@@ -1755,11 +1786,7 @@ static int apply_host_pipelined(PC *pc, const double *x, double *y)
     }
     for (int s = 0; s < S; ++s) {
         CUDA_OK(cudaStreamWaitEvent(pc->stream, pc->ev_in[s], 0));
-        for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
-            const SizeClass &c = pc->classes[ci];
-            const i64 q0 = pc->pipe_ranges[s][ci].first, q1 = pc->pipe_ranges[s][ci].second;
-            if (q1 > q0) CHK(launch_apply_class(pc, c, q0, q1, nullptr, dx, dy, scale));
-        }
+        CHK(launch_slab_classes(pc, s, dx, dy, scale, std::vector<int>()));      // the fork event already carries the wait on x
         const i64 a = pc->pipe_out[s], b = pc->pipe_out[s + 1];
         const i64 nb = pc->pipe_bc[s + 1] - pc->pipe_bc[s];
         if (nb > 0) { ssc_bc_kernel<<<grid_for(nb, 256), 256, 0, pc->stream>>>(pc->d_bc + pc->pipe_bc[s], nb, dx, dy); pc->launches++; }
