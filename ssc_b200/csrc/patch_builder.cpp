@@ -178,9 +178,13 @@ struct Builder {
                         if (g < 0 || g >= nlocal) { out.msg = "cell node map entry outside the local dof range"; return SSC_ERR_ARG_OUTOFRANGE; }
                         i64 loc;
                         DofMark &m = s.dof[g];
-                        if (isGlobalBc[g] || (m.seen == stamp && m.owned != stamp)) loc = -1;
-                        else if (m.local == stamp) loc = m.idx;
-                        else { m.local = stamp; m.idx = next; loc = next++; out.gtol.push_back(g); }
+                        if (m.local == stamp) loc = m.idx;               // met before in this patch (kept or dropped): one load
+                        else {
+                            m.local = stamp;
+                            if (isGlobalBc[g] || (m.seen == stamp && m.owned != stamp)) m.idx = -1;   // global or artificial BC
+                            else { m.idx = next++; out.gtol.push_back(g); }
+                            loc = m.idx;
+                        }
                         if (opt.keep_dofs && disc.nsub == 1) out.dofs.push_back(loc);
                     }
                 }
