@@ -1,1824 +1,9 @@
-// sm_100a kernels of the patch preconditioner.  One file so that every launch site sees the same layouts.
-//
-// Layout in HBM (DESIGN.md "data layout"):
-//   * patches are sorted by size n into classes; inside a class patch q has its dof list at
-//     gtol[goff + q*n .. +n) (int32) and its dense block at blocks[moff + q*stride .. + n*n) (fp64),
-//     stride = n*n rounded up to 16 doubles so every block starts on a 128-byte line.
-//   * after setup a block holds S = (B^-1)^T row-major, i.e. S[j*n + i] = (B^-1)[i][j]: in the apply kernel
-//     thread i of a patch reads S[j*n + i] for j = 0..n-1, so a warp reads consecutive doubles (coalesced),
-//     every byte of the block is read exactly once, and no cross-thread reduction is needed.
+// sm_100a kernels of the patch preconditioner, by theme.  Layouts are described in kernels_common.cuh.
 #pragma once
-#include <cstdint>
-#include <cuda_runtime.h>
-
-typedef long long ll;
-
-__device__ __forceinline__ unsigned hash_dof(int key) { return (unsigned)key * 2654435761u; }
-
-// Peer-memory scatter (multi-GPU, NVLink P2P): a patch dof >= nowned is a ghost whose owner lives on another GPU of
-// the box; its correction is added straight into the owner's local vector through a mapped peer pointer, so the
-// overlap sum of ssc/libssc.c:1399-1400 travels over NVLink while the patch kernel is still streaming blocks.
-struct PeerScatter {
-    double *yl[16];          // "incoming" vector (one entry per owned dof) of every neighbour (cudaIpcOpenMemHandle)
-    const int *ghostPeer;    // ghost slot -> neighbour number
-    const int *ghostRemote;  // ghost slot -> owned index on that neighbour
-    const double *xg;        // this rank's ghost values of x, written by the neighbours (halo fill)
-    int nowned;
-};
-// residual entry of local dof gi: owned ones come from the caller's vector, ghosts from the array the neighbours filled
-__device__ __forceinline__ double gather_x(const double *__restrict__ x, int gi, const PeerScatter *__restrict__ ps)
-{
-    if (ps != nullptr && gi >= ps->nowned) return ps->xg[gi - ps->nowned];
-    return __ldg(x + gi);
-}
-// Deterministic mode: instead of reducing into y, every patch dof stores its correction in its own slot of `ypatch`
-// (coalesced plain stores); ssc_slot_sum_kernel then adds the slots of each dof in a fixed order.
-__device__ __forceinline__ void scatter_add(double *__restrict__ y, int gi, double v, const PeerScatter *__restrict__ ps);
-__device__ __forceinline__ void emit(double *__restrict__ y, int gi, double v, const PeerScatter *__restrict__ ps, double *__restrict__ ypatch, ll slot)
-{
-    if (ypatch != nullptr) ypatch[slot] = v;
-    else scatter_add(y, gi, v, ps);
-}
-__device__ __forceinline__ void scatter_add(double *__restrict__ y, int gi, double v, const PeerScatter *__restrict__ ps)
-{
-    if (ps != nullptr && gi >= ps->nowned) {
-        const int s = gi - ps->nowned;
-        atomicAdd(ps->yl[ps->ghostPeer[s]] + ps->ghostRemote[s], v);
-    } else {
-        atomicAdd(y + gi, v);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1 extract: B_p[i][j] = A[gtol_p[i], gtol_p[j]]   (replaces MatZeroEntries + callback assembly,
-// ssc/libssc.c:1286-1291, :1120-1156).  One CTA per patch; a shared-memory hash maps global column -> patch
-// column; each warp owns one output row at a time, accumulates it in shared memory and stores it coalesced.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-ssc_extract_kernel(const ll *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals,
-                   const int *__restrict__ gtol, double *__restrict__ blocks, int n, int ld, ll stride, ll count, int H)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    int *keys = reinterpret_cast<int *>(smem_raw);
-    int *slotval = keys + H;
-    ll *rbeg = reinterpret_cast<ll *>(slotval + H);            // n: start of every patch row in the CSR arrays
-    int *rlen = reinterpret_cast<int *>(rbeg + n);            // n (+1 pad): its length
-    double *rowbuf = reinterpret_cast<double *>(rlen + ((n + 2) & ~1));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
-        const int *g = gtol + p * n;
-        for (int t = tid; t < H; t += blockDim.x) keys[t] = -1;
-        __syncthreads();
-        // one round of dependent loads for the whole patch: dof -> row extent; and the column hash
-        for (int t = tid; t < n; t += blockDim.x) {
-            const int key = g[t];
-            const ll a = rowptr[key];
-            rbeg[t] = a;
-            rlen[t] = (int)(rowptr[key + 1] - a);
-            unsigned s = hash_dof(key) & (H - 1);
-            while (true) {
-                const int prev = atomicCAS(&keys[s], -1, key);
-                if (prev == -1 || prev == key) { slotval[s] = t; break; }
-                s = (s + 1) & (H - 1);
-            }
-        }
-        __syncthreads();
-        double *B = blocks + p * stride;
-        // a warp owns two output rows at a time: both rows' index/value loads are issued before either is consumed
-        double *rb0 = rowbuf + (2 * warp) * n, *rb1 = rb0 + n;
-        for (int i0 = 2 * warp; i0 < n; i0 += 2 * nwarps) {
-            const int i1 = i0 + 1;
-            const bool two = i1 < n;
-            for (int t = lane; t < n; t += 32) { rb0[t] = 0.0; rb1[t] = 0.0; }
-            __syncwarp();
-            const ll a0 = rbeg[i0], a1 = two ? rbeg[i1] : 0;
-            const int l0 = rlen[i0], l1 = two ? rlen[i1] : 0;
-            const int lmax = l0 > l1 ? l0 : l1;
-            for (int k = lane; k < lmax; k += 32) {
-                int c0 = -1, c1 = -1;
-                double v0 = 0.0, v1 = 0.0;
-                if (k < l0) { c0 = colidx[a0 + k]; v0 = vals[a0 + k]; }
-                if (k < l1) { c1 = colidx[a1 + k]; v1 = vals[a1 + k]; }
-                if (c0 >= 0) {
-                    unsigned s = hash_dof(c0) & (H - 1);
-                    int kk;
-                    while ((kk = keys[s]) != -1) { if (kk == c0) { atomicAdd(&rb0[slotval[s]], v0); break; } s = (s + 1) & (H - 1); }
-                }
-                if (c1 >= 0) {
-                    unsigned s = hash_dof(c1) & (H - 1);
-                    int kk;
-                    while ((kk = keys[s]) != -1) { if (kk == c1) { atomicAdd(&rb1[slotval[s]], v1); break; } s = (s + 1) & (H - 1); }
-                }
-            }
-            __syncwarp();
-            for (int t = lane; t < ld; t += 32) {
-                B[(ll)i0 * ld + t] = t < n ? rb0[t] : 0.0;
-                if (two) B[(ll)i1 * ld + t] = t < n ? rb1[t] : 0.0;
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1e assemble: B_p from ELEMENT matrices, the reference's own route to the patch operators
-// (PCPatchComputeOperator ssc/libssc.c:1120-1156 + the callback ssc/PatchPC.pyx:54-72, ssc/patch.py:28-62,210-213:
-// MatSetValues(ADD_VALUES) of one tdpc x tdpc matrix per patch cell through the per-cell `dofs` table, negative
-// indices dropped).  One CTA per patch.  The patch-local index of a cell dof is looked up in a shared-memory hash of
-// the patch's dof list (a dof that is not in the list is a global or artificial BC dof: the -1 of the `dofs` table).
-// Cells are added one after the other in the order of the `cells` list, so every entry is summed in the
-// reference's order and the result is bit-identical to the oracle's (oracle_patch_matrix_from_elements).
-// Inside one cell all targets are distinct, so no atomics are needed.
-// ---------------------------------------------------------------------------------------------
-struct ElemSpaces {
-    const int *cnm[8];            // cell-node map of every subspace, rows follow the cell numbering
-    int bs[8], npc[8], subOff[8], tOff[9];
-    int nsub, t;                  // t = totalDofsPerCell
-};
-
-__global__ void __launch_bounds__(1024)
-ssc_assemble_kernel(ElemSpaces E, const double *__restrict__ Ke, ll kstride, const ll *__restrict__ celloff, const int *__restrict__ cells,
-                    const int *__restrict__ gtol, double *blocks, int n, int ld, ll stride, ll count, int H, int acc_shared)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    int *keys = reinterpret_cast<int *>(smem_raw);
-    int *slotval = keys + H;
-    int *lidx = slotval + H;                                   // t: patch-local index of every cell dof (-1: dropped)
-    int *vi = lidx + ((E.t + 1) & ~1);                         // t: the cell dofs that are kept
-    double *acc_s = reinterpret_cast<double *>(vi + ((E.t + 1) & ~1));
-    __shared__ int nvalid[2];                                  // kept-dof counters of even and odd cells
-    const int tid = threadIdx.x;
-    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
-        const int *g = gtol + p * n;
-        for (int t = tid; t < H; t += blockDim.x) keys[t] = -1;
-        __syncthreads();
-        for (int t = tid; t < n; t += blockDim.x) {
-            const int key = g[t];
-            unsigned s = hash_dof(key) & (H - 1);
-            while (true) {
-                const int prev = atomicCAS(&keys[s], -1, key);
-                if (prev == -1 || prev == key) { slotval[s] = t; break; }
-                s = (s + 1) & (H - 1);
-            }
-        }
-        double *B = blocks + p * stride;
-        double *acc = acc_shared ? acc_s : B;
-        for (int e = tid; e < n * ld; e += blockDim.x) acc[e] = 0.0;
-        if (tid == 0) { nvalid[0] = 0; nvalid[1] = 0; }
-        __syncthreads();
-        int par = 0;
-        for (ll c = celloff[p]; c < celloff[p + 1]; ++c, par ^= 1) {
-            const ll cell = cells[c];
-            for (int t = tid; t < E.t; t += blockDim.x) {
-                int k = 0;
-                while (t >= E.tOff[k + 1]) ++k;
-                const int r = t - E.tOff[k], j = r / E.bs[k], l = r - j * E.bs[k];
-                const int key = E.cnm[k][cell * E.npc[k] + j] * E.bs[k] + l + E.subOff[k];
-                int loc = -1;
-                unsigned s = hash_dof(key) & (H - 1);
-                int kk;
-                while ((kk = keys[s]) != -1) { if (kk == key) { loc = slotval[s]; break; } s = (s + 1) & (H - 1); }
-                lidx[t] = loc;
-                if (loc >= 0) vi[atomicAdd(&nvalid[par], 1)] = t;
-            }
-            __syncthreads();
-            const int nv = nvalid[par];
-            if (tid == 0) nvalid[par ^ 1] = 0;                 // nobody touches the other counter before the next barrier
-            const double *K = Ke + cell * kstride;
-            for (int e = tid; e < nv * nv; e += blockDim.x) {
-                const int a = e / nv, b = e - a * nv;
-                const int i = vi[a], j = vi[b];
-                acc[lidx[i] * ld + lidx[j]] += K[i * E.t + j];
-            }
-            __syncthreads();
-        }
-        if (acc_shared) {
-            for (int e = tid; e < n * ld; e += blockDim.x) B[e] = acc_s[e];
-            __syncthreads();
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2 factor: in-place Gauss-Jordan inversion, one CTA per patch.  With kPivot the pivot of step k is the
-// largest entry of column k among rows >= k (partial pivoting: -sub_pc_type lu); without it the diagonal is
-// used (SPD blocks: -sub_pc_type cholesky).  The block is loaded TRANSPOSED, so what is inverted is B^T and
-// what is stored back is S = (B^T)^-1 = (B^-1)^T, the layout the apply kernel streams.
-// kShared: the working copy lives in shared memory (n <= 168); otherwise the block is inverted in place in
-// global memory (L2-resident) and transposed afterwards.
-// ---------------------------------------------------------------------------------------------
-template <bool kPivot>
-__device__ __forceinline__ int gauss_jordan(double *A, int n, int ld, double *rowv, double *colv, int *piv,
-                                            double *redv, int *redi)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    // thread -> fixed column, strided rows: the pivot-row entry stays in a register, the multiplier is a broadcast
-    const int ncol_threads = n < (int)blockDim.x ? n : (int)blockDim.x;
-    const int rgroups = blockDim.x / ncol_threads;          // >= 1
-    const int mycol = tid % ncol_threads, myrg = tid / ncol_threads;
-    int fail = 0;
-    for (int k = 0; k < n; ++k) {
-        int p = k;
-        if (kPivot) {
-            double best = -1.0; int bi = k;
-            for (int i = k + tid; i < n; i += blockDim.x) {
-                const double v = fabs(A[(ll)i * ld + k]);
-                if (v > best) { best = v; bi = i; }
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_down_sync(0xffffffffu, best, o);
-                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-            }
-            if (lane == 0) { redv[warp] = best; redi[warp] = bi; }
-            __syncthreads();
-            if (warp == 0) {
-                best = lane < nwarps ? redv[lane] : -1.0; bi = lane < nwarps ? redi[lane] : n;
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ov = __shfl_down_sync(0xffffffffu, best, o);
-                    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-                }
-                if (lane == 0) { redi[32] = bi; piv[k] = bi; }
-            }
-            __syncthreads();
-            p = redi[32];
-            if (p != k) {
-                for (int j = tid; j < n; j += blockDim.x) {
-                    const double a = A[(ll)k * ld + j];
-                    A[(ll)k * ld + j] = A[(ll)p * ld + j];
-                    A[(ll)p * ld + j] = a;
-                }
-                __syncthreads();
-            }
-        }
-        const double d = A[(ll)k * ld + k];
-        if (!(fabs(d) > 0.0) || (!kPivot && !(d > 0.0))) { fail = 1; break; }   // uniform across the CTA
-        const double dinv = 1.0 / d;
-        __syncthreads();
-        for (int j = tid; j < n; j += blockDim.x) {
-            rowv[j] = A[(ll)k * ld + j] * dinv;
-            colv[j] = A[(ll)j * ld + k];
-        }
-        __syncthreads();
-        for (int j = mycol; j < n && myrg < rgroups; j += ncol_threads) {
-            const double r = rowv[j];
-            if (j == k) {
-                for (int i = myrg; i < n; i += rgroups) A[(ll)i * ld + j] = (i == k) ? dinv : -colv[i] * dinv;
-            } else {
-                for (int i = myrg; i < n; i += rgroups) {
-                    if (i == k) A[(ll)i * ld + j] = r;
-                    else A[(ll)i * ld + j] = fma(-colv[i], r, A[(ll)i * ld + j]);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (kPivot && !fail) {
-        // (P M)^-1 = M^-1 P^T: undo the row exchanges as column exchanges, last first
-        for (int k = n - 1; k >= 0; --k) {
-            const int p = piv[k];
-            if (p != k) {
-                for (int i = tid; i < n; i += blockDim.x) {
-                    const double a = A[(ll)i * ld + k];
-                    A[(ll)i * ld + k] = A[(ll)i * ld + p];
-                    A[(ll)i * ld + p] = a;
-                }
-                __syncthreads();
-            }
-        }
-    }
-    return fail;
-}
-
-template <bool kPivot, bool kShared>
-__global__ void __launch_bounds__(1024)
-ssc_invert_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll count, int *__restrict__ fail_flags)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int ld = kShared ? (n | 1) : ldg;
-    double *rowv = reinterpret_cast<double *>(smem_raw);
-    double *colv = rowv + n;
-    double *redv = colv + n;
-    int *redi = reinterpret_cast<int *>(redv + 32);
-    int *piv = redi + 34;
-    double *As = reinterpret_cast<double *>(smem_raw) + 2 * n + 32 + ((34 + n + 1) / 2 + 1);
-    const int tid = threadIdx.x;
-    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
-        double *B = blocks + p * stride;
-        double *A = kShared ? As : B;
-        if (kShared) {
-            for (int e = tid; e < n * n; e += blockDim.x) { const int i = e / n, j = e - i * n; As[(ll)j * ld + i] = B[(ll)i * ldg + j]; }
-        }
-        __syncthreads();
-        const int fail = gauss_jordan<kPivot>(A, n, ld, rowv, colv, piv, redv, redi);
-        __syncthreads();
-        if (tid == 0) fail_flags[p] = fail;
-        if (kShared) {
-            for (int e = tid; e < n * n; e += blockDim.x) { const int i = e / n, j = e - i * n; B[(ll)i * ldg + j] = As[(ll)i * ld + j]; }
-        } else {
-            // in-place transpose of the n x n block
-            for (ll e = tid; e < (ll)n * n; e += blockDim.x) {
-                const int i = (int)(e / n), j = (int)(e - (ll)i * n);
-                if (i < j) { const double a = B[(ll)i * ldg + j]; B[(ll)i * ldg + j] = B[(ll)j * ldg + i]; B[(ll)j * ldg + i] = a; }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// Register-resident Gauss-Jordan for n <= 128: the whole block lives in registers, thread (tr, tc) owns the
-// 8 x 4 tile of rows 8tr.. and columns 4tc..; per elimination step a thread reads only its 8 multipliers and its 4
-// pivot-row entries from shared memory (32 FMAs per 12 loads, against 1 FMA per 3 shared accesses in the
-// shared-memory kernel above).  Pivoting is implicit: rows are never moved, every warp finds the pivot row of the
-// step redundantly (same deterministic arg-max), and the permutation is applied once when the result is stored.
-// Two barriers per step; the two broadcast vectors are double-buffered so no third barrier is needed.
-__device__ __forceinline__ double sel4(const double (&v)[4], int c)
-{
-    return c == 0 ? v[0] : (c == 1 ? v[1] : (c == 2 ? v[2] : v[3]));
-}
-
-template <bool kPivot>
-__global__ void __launch_bounds__(512, 1)
-ssc_invert_reg_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll count, int *__restrict__ fail_flags, int TC)
-{
-    __shared__ __align__(16) double colv[2][128];
-    __shared__ __align__(16) double rowv[2][128];
-    __shared__ int perm[128], qinv[128];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int tr = tid / TC, tc = tid - tr * TC;
-    const bool owner = tr < (n + 7) / 8;
-    // non-owner threads (padding of the thread grid) read row/column slots 0.. harmlessly
-    const int r0 = owner ? 8 * tr : 0, c0 = 4 * tc;
-    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
-        double *B = blocks + p * stride;
-        double a[8][4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int j = c0 + c;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int i = r0 + r;
-                a[r][c] = (owner && i < n && j < n) ? B[(ll)j * ldg + i] : 0.0;      // transposed load: A = B^T
-            }
-        }
-        unsigned usedmask = 0;      // bit s of lane l <-> row l + 32 s has been a pivot row
-        int fail = 0;
-        for (int k = 0; k < n; ++k) {
-            const int buf = k & 1;
-            // (1) the owners of column k publish it and clear it in their registers (k & 3 is uniform: no divergence
-            //     on the switch, static register indices inside)
-            if (owner && tc == (k >> 2)) {
-#define PUBLISH_COL(C)                                                                  \
-    _Pragma("unroll") for (int r = 0; r < 8; ++r) { colv[buf][r0 + r] = a[r][C]; a[r][C] = 0.0; }
-                switch (k & 3) {
-                case 0: PUBLISH_COL(0) break;
-                case 1: PUBLISH_COL(1) break;
-                case 2: PUBLISH_COL(2) break;
-                default: PUBLISH_COL(3) break;
-                }
-#undef PUBLISH_COL
-            }
-            __syncthreads();
-            int prow = k;
-            if (kPivot) {
-                double best = -1.0;
-                int bi = 1 << 30;
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const int i = lane + 32 * s;
-                    if (i < n && !((usedmask >> s) & 1u)) {
-                        const double v = fabs(colv[buf][i]);
-                        if (v > best) { best = v; bi = i; }
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-                }
-                prow = bi;
-                if (prow >= n) { fail = 1; break; }                  // no candidate (NaNs)
-                if ((prow & 31) == lane) usedmask |= 1u << (prow >> 5);
-                if (tid == 0) perm[k] = prow;
-            }
-            const double d = colv[buf][prow];
-            if (!(fabs(d) > 0.0) || (!kPivot && !(d > 0.0))) { fail = 1; break; }     // uniform across the CTA
-            const double dinv = 1.0 / d;
-            // (2) the owners of the pivot row publish it scaled (slot k carries 1/d) and clear it
-            if (owner && tr == (prow >> 3)) {
-#define PUBLISH_ROW(R)                                                                                          \
-    _Pragma("unroll") for (int c = 0; c < 4; ++c) { rowv[buf][c0 + c] = (c0 + c == k) ? dinv : a[R][c] * dinv; a[R][c] = 0.0; }
-                switch (prow & 7) {
-                case 0: PUBLISH_ROW(0) break;
-                case 1: PUBLISH_ROW(1) break;
-                case 2: PUBLISH_ROW(2) break;
-                case 3: PUBLISH_ROW(3) break;
-                case 4: PUBLISH_ROW(4) break;
-                case 5: PUBLISH_ROW(5) break;
-                case 6: PUBLISH_ROW(6) break;
-                default: PUBLISH_ROW(7) break;
-                }
-#undef PUBLISH_ROW
-            }
-            __syncthreads();
-            // (3) rank-1 update of the whole tile.  Column k and row p were cleared above, the multiplier of row p is
-            //     -1 and slot k of the pivot row is 1/d, so the same FMA yields the Gauss-Jordan special cases:
-            //     a[p][j] = rowv[j],  a[i][k] = -colv[i]/d,  a[p][k] = 1/d.
-            const double2 *cp = reinterpret_cast<const double2 *>(&colv[buf][r0]);
-            const double2 *rp2 = reinterpret_cast<const double2 *>(&rowv[buf][c0]);
-            double cv[8], rv[4];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) { const double2 t = cp[h]; cv[2 * h] = t.x; cv[2 * h + 1] = t.y; }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) { const double2 t = rp2[h]; rv[2 * h] = t.x; rv[2 * h + 1] = t.y; }
-            const int rp = prow - r0;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const double m = (r == rp) ? 1.0 : -cv[r];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) a[r][c] = fma(m, rv[c], a[r][c]);
-            }
-        }
-        __syncthreads();
-        if (tid < n) { if (!kPivot) perm[tid] = tid; }
-        __syncthreads();
-        if (tid < n) qinv[perm[tid]] = tid;
-        __syncthreads();
-        if (tid == 0) fail_flags[p] = fail;
-        if (!fail && owner) {
-            // A^-1[kk][cc] = W[perm[kk]][qinv[cc]]  <=>  W[i][j] goes to row qinv[i], column perm[j]
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int i = r0 + r;
-                if (i < n) {
-                    const ll row = (ll)qinv[i] * ldg;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int j = c0 + c;
-                        if (j < n) B[row + perm[j]] = a[r][c];
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// Look-ahead form of the register-resident Gauss-Jordan above.  ncu showed the kernel above issue- and latency-bound:
-// 295 warp instructions per warp and elimination step for 32 FMAs, because every warp repeats the pivot search and
-// the division, and the whole CTA waits for them twice per step.  Here an extra warp (the "searcher") owns the pivot
-// search and the reciprocal.  While the 16 worker warps apply step k to their tiles, the owners of column k+1 update
-// that column first, publish it and signal the searcher, which finds the pivot of step k+1 and its reciprocal in
-// parallel with the bulk of the update.  Named barriers: 1 = column published (workers arrive, searcher waits),
-// 2 = pivot ready (searcher arrives, workers wait), 3 = pivot row published (workers only).
-// Tiles are 8 x 5 here (16 x 25 workers + the searcher = 448 threads: the register file holds 128 per thread).
-// Same arithmetic, same pivot choice (largest magnitude, lowest row on ties), same stored layout as above.
-__device__ __forceinline__ void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void nbar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
-template <bool kPivot>
-__global__ void __launch_bounds__(448, 1)
-ssc_invert_la_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll count, int *__restrict__ fail_flags, int TC, int W)
-{
-    __shared__ __align__(16) double colv[2][136];
-    __shared__ __align__(16) double rowv[2][136];      // 26 column tiles of 5 reach slot 129
-    __shared__ double s_dinv[2];
-    __shared__ int s_prow[2];
-    __shared__ int s_fail;
-    __shared__ int perm[128], qinv[128];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int all = W + 32;
-    const bool searcher = tid >= W;
-    const int tr = tid / TC, tc = tid - tr * TC;
-    const bool owner = !searcher && tr < (n + 7) / 8;
-    const int r0 = owner ? 8 * tr : 0, c0 = owner ? 5 * tc : 0;
-    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
-        double *B = blocks + p * stride;
-        double a[8][5];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const int j = c0 + c;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int i = r0 + r;
-                a[r][c] = (owner && i < n && j < n) ? B[(ll)j * ldg + i] : 0.0;      // transposed load: A = B^T
-            }
-        }
-        if (tid == 0) s_fail = 0;
-        if (owner && tc == 0) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) { colv[0][r0 + r] = a[r][0]; a[r][0] = 0.0; }
-        }
-        __syncthreads();
-        if (searcher) {
-            unsigned usedmask = 0;      // bit s of lane l <-> row l + 32 s has been a pivot row
-            for (int k = 0; k < n; ++k) {
-                const int buf = k & 1;
-                if (k > 0) nbar_sync(1, all);                        // column k is in colv[buf]
-                int prow = k;
-                if (kPivot) {
-                    unsigned long long bestk = 0ull;
-                    int bi = 1 << 30;
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        const int i = lane + 32 * s;
-                        if (i < n && !((usedmask >> s) & 1u)) {
-                            const double v = fabs(colv[buf][i]);
-                            const unsigned long long key = (v == v) ? (unsigned long long)__double_as_longlong(v) : 0ull;   // |v| orders like its bits
-                            if (bi == (1 << 30) || key > bestk) { bestk = key; bi = i; }
-                        }
-                    }
-                    const bool have = bi < (1 << 30);
-                    const unsigned hi = (unsigned)(bestk >> 32), lo = (unsigned)bestk;
-                    const unsigned mh = __reduce_max_sync(0xffffffffu, have ? hi : 0u);
-                    const bool in1 = have && hi == mh;
-                    const unsigned ml = __reduce_max_sync(0xffffffffu, in1 ? lo : 0u);
-                    prow = (int)__reduce_min_sync(0xffffffffu, (in1 && lo == ml) ? (unsigned)bi : 0x7fffffffu);
-                }
-                bool bad = prow >= n;
-                double dinv = 0.0;
-                if (!bad) {
-                    const double d = colv[buf][prow];
-                    bad = !(fabs(d) > 0.0) || (!kPivot && !(d > 0.0));
-                    dinv = 1.0 / d;
-                    if ((prow & 31) == lane) usedmask |= 1u << (prow >> 5);
-                }
-                if (lane == 0) {
-                    s_prow[buf] = bad ? -1 : prow; s_dinv[buf] = dinv; perm[k] = bad ? k : prow;
-                    if (bad) s_fail = 1;
-                }
-                nbar_arrive(2, all);                                  // orders the stores above for the waiting workers
-                if (bad) break;
-            }
-        } else {
-            for (int k = 0; k < n; ++k) {
-                const int buf = k & 1;
-                nbar_sync(2, all);                                    // the pivot of step k is known
-                const int prow = s_prow[buf];
-                if (prow < 0) break;                                  // no usable pivot: uniform across the CTA
-                const double dinv = s_dinv[buf];
-                // the owners of the pivot row publish it scaled (slot k carries 1/d) and clear it; the multiplier of the
-                // pivot row becomes -1 so that the update below writes the scaled row back without a special case
-                if (owner && tr == (prow >> 3)) {
-                    if (tc == 0) colv[buf][prow] = -1.0;
-#define PUBLISH_ROW(R)                                                                                          \
-    _Pragma("unroll") for (int c = 0; c < 5; ++c) { rowv[buf][c0 + c] = (c0 + c == k) ? dinv : a[R][c] * dinv; a[R][c] = 0.0; }
-                    switch (prow & 7) {
-                    case 0: PUBLISH_ROW(0) break;
-                    case 1: PUBLISH_ROW(1) break;
-                    case 2: PUBLISH_ROW(2) break;
-                    case 3: PUBLISH_ROW(3) break;
-                    case 4: PUBLISH_ROW(4) break;
-                    case 5: PUBLISH_ROW(5) break;
-                    case 6: PUBLISH_ROW(6) break;
-                    default: PUBLISH_ROW(7) break;
-                    }
-#undef PUBLISH_ROW
-                }
-                nbar_sync(3, W);
-                const double2 *cp = reinterpret_cast<const double2 *>(&colv[buf][r0]);
-                double cv[8], rv[5];
-#pragma unroll
-                for (int h = 0; h < 4; ++h) { const double2 t = cp[h]; cv[2 * h] = t.x; cv[2 * h + 1] = t.y; }
-#pragma unroll
-                for (int c = 0; c < 5; ++c) rv[c] = rowv[buf][c0 + c];
-                // look-ahead: column k+1 first, published for the searcher and cleared like column k was
-                const int k1 = k + 1;
-                const int t1 = k1 / 5, w1 = k1 - 5 * t1;
-                const bool early = owner && k1 < n && tc == t1;
-                if (early) {
-#define EARLY_COL(C)                                                                                            \
-    _Pragma("unroll") for (int r = 0; r < 8; ++r) { colv[buf ^ 1][r0 + r] = fma(-cv[r], rv[C], a[r][C]); a[r][C] = 0.0; }
-                    switch (w1) {
-                    case 0: EARLY_COL(0) break;
-                    case 1: EARLY_COL(1) break;
-                    case 2: EARLY_COL(2) break;
-                    case 3: EARLY_COL(3) break;
-                    default: EARLY_COL(4) break;
-                    }
-#undef EARLY_COL
-                }
-                if (k1 < n) nbar_arrive(1, all);
-                const int skip = early ? w1 : -1;
-#pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    if (c != skip) {
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) a[r][c] = fma(-cv[r], rv[c], a[r][c]);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        const int fail = s_fail;
-        if (tid < n) qinv[perm[tid]] = tid;
-        __syncthreads();
-        if (tid == 0) fail_flags[p] = fail;
-        if (!fail && owner) {
-            // A^-1[kk][cc] = W[perm[kk]][qinv[cc]]  <=>  W[i][j] goes to row qinv[i], column perm[j]
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int i = r0 + r;
-                if (i < n) {
-                    const ll row = (ll)qinv[i] * ldg;
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) {
-                        const int j = c0 + c;
-                        if (j < n) B[row + perm[j]] = a[r][c];
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// Blocked form of the look-ahead kernel: panels of 5 columns.  Applying the 5 Gauss-Jordan steps of a panel to the
-// whole matrix is  A <- T A  with  T = T_5 ... T_1, and T differs from the identity only in the columns of the 5 pivot
-// rows.  So every other column gets the rank-5 update  A[:, j] += (T - I)[:, P] A_old[P, j]  (P = the pivot rows, raw
-// values from before the panel), and the panel's own slots receive T[:, P] -- which is exactly what the same in-place
-// Gauss-Jordan steps leave behind when they are run on the n x 5 panel alone.  The searcher warp does that small
-// factorisation (pivot searches, reciprocals) for the next panel while the worker warps apply the current one:
-// 200 FMAs per worker thread between barriers instead of 40, and the serial pivot chain runs beside them.
-// A panel is NOT five neighbouring columns: it takes the same local column w of five neighbouring column tiles
-// (columns 5 (5 g + q) + w, q = 0..4), so its columns belong to 80 threads instead of 16 and the look-ahead update of
-// the next panel -- which sits on the critical path between two panel factorisations -- is 40 FMAs per owner, not 200.
-// Columns are therefore eliminated in a different order than in the kernels above (any order is a valid partial-pivot
-// elimination; perm[] is indexed by column); the inverse agrees to rounding.
-// The searcher keeps its working panel row-major in shared memory (S) and re-reads its rows every step, so the row
-// that just served as pivot row can be replaced by one lane without dynamic register indexing (a register-only
-// version with selects measured 6 % slower).
-// position of matrix row i inside a panel column in shared memory: the 16-byte chunks (row pairs) that the 16 row
-// tiles of a warp read together are neighbours, so those reads are conflict-free (a plain row order puts them 64
-// bytes apart: 8-way bank conflicts, which also starved the searcher's own shared-memory traffic)
-__device__ __forceinline__ int ppos(int i) { return ((((i >> 1) & 3) * 16 + (i >> 3)) << 1) | (i & 1); }
-
-template <bool kPivot>
-__global__ void __launch_bounds__(512, 1)
-ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll count, int *__restrict__ fail_flags, int TR, int TC, int W, int remap)
-{
-    constexpr int PB = 5, LDP = 136, SR = 6;
-    __shared__ __align__(16) double Pcol[2][PB][LDP];      // panel columns: raw from their owners, then (T - I)[:, P] from the searcher
-    __shared__ __align__(16) double Rrow[2][PB][LDP];      // the raw pivot rows of a panel
-    __shared__ __align__(16) double S[128][SR];            // the searcher's working panel, one row per matrix row
-    __shared__ int s_prow[2][8];
-    __shared__ int s_pj[32], s_pbw[32], s_np;
-    __shared__ int perm[128], qinv[128];
-    // remap (13 worker warps, 512 threads): warp 13 is the searcher and warps 5 and 9 -- the other two warps of its SM
-    // sub-partition besides worker warp 1 -- stay idle, so the serial pivot chain shares its scheduler and fp64 pipe
-    // with one worker warp instead of three; the other sub-partitions run four worker warps each
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // the non-empty panels in elimination order: panel j = (g, w) holds the columns 5 (5 g + q) + w < n of the tiles
-    // 5 g + q < TC, a prefix in q; the list is the same for every block of the class
-    if (threadIdx.x == 0) {
-        int cntp = 0;
-        for (int j = 0; j < PB * ((TC + PB - 1) / PB); ++j) {
-            const int g = j / PB, w = j - PB * g;
-            int bw = 0;
-            for (int q = 0; q < PB; ++q) bw += (PB * g + q < TC && PB * (PB * g + q) + w < n) ? 1 : 0;
-            if (bw) { s_pj[cntp] = j; s_pbw[cntp] = bw; ++cntp; }
-        }
-        s_np = cntp;
-    }
-    __syncthreads();
-    const int NPE = s_np;
-    if (remap && (wid == 5 || wid == 9)) {
-        for (ll p = blockIdx.x; p < count; p += gridDim.x) __syncthreads();
-        return;
-    }
-    const bool searcher = remap ? wid == 13 : (int)threadIdx.x >= W;
-    const int tid = remap ? ((wid - (wid > 5) - (wid > 9) - (wid > 13)) << 5) + lane : (int)threadIdx.x;   // logical thread: tiles, permutation arrays
-    const int all = W + 32;
-    const int tc = tid / TR, tr = tid - tc * TR;
-    const bool owner = !searcher && tc < TC;
-    const int r0 = owner ? 8 * tr : 0, c0 = owner ? PB * tc : 0;
-    const int gt = tc / PB, qt = tc - PB * gt;               // column-tile group of this thread, its panel column there
-    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
-        double *B = blocks + p * stride;
-        if (searcher) {
-            unsigned usedmask = 0;      // bit s of lane l <-> row l + 32 s has been a pivot row (rows >= n count as used)
-#pragma unroll
-            for (int s = 0; s < 4; ++s) if (lane + 32 * s >= n) usedmask |= 1u << s;
-            for (int it = 0; it < NPE; ++it) {
-                const int j = s_pj[it], bw = s_pbw[it];
-                const int buf = it & 1, g = j / PB, w = j - PB * g;
-                nbar_sync(1, all);                                    // panel j is in Pcol[buf]
-                double x[4][PB];
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const int i = lane + 32 * s;
-#pragma unroll
-                    for (int c = 0; c < PB; ++c) x[s][c] = (i < n && c < bw) ? Pcol[buf][c][ppos(i)] : 0.0;
-                    double2 *row = reinterpret_cast<double2 *>(&S[i][0]);
-                    row[0] = make_double2(x[s][0], x[s][1]); row[1] = make_double2(x[s][2], x[s][3]); S[i][4] = x[s][4];
-                }
-                __syncwarp();
-                int pl[PB];
-                bool bad = false;
-#pragma unroll
-                for (int t = 0; t < PB; ++t) {
-                    pl[t] = 0;
-                    if (t < bw && !bad) {
-                        int prow = PB * (PB * g + t) + w;            // unpivoted: the diagonal entry of this column
-                        if (kPivot) {
-                            // largest |x|, lowest row on ties; integer compares on the bit pattern (|v| orders like its
-                            // bits); exact zeros are no candidates, so a zero column ends with prow >= n (singular)
-                            unsigned bh = 0u, bl = 0u;
-                            int bi = 1 << 30;
-#pragma unroll
-                            for (int s = 0; s < 4; ++s) {
-                                const unsigned kh = (unsigned)__double2hiint(x[s][t]) & 0x7fffffffu, kl = (unsigned)__double2loint(x[s][t]);
-                                const bool better = !((usedmask >> s) & 1u) && (kh > bh || (kh == bh && kl > bl));
-                                if (better) { bh = kh; bl = kl; bi = lane + 32 * s; }
-                            }
-                            const bool have = bi < (1 << 30);
-                            const unsigned mh = __reduce_max_sync(0xffffffffu, have ? bh : 0u);
-                            const bool in1 = have && bh == mh;
-                            const unsigned ml = __reduce_max_sync(0xffffffffu, in1 ? bl : 0u);
-                            prow = (int)__reduce_min_sync(0xffffffffu, (in1 && bl == ml) ? (unsigned)bi : 0x7fffffffu);
-                        }
-                        if (prow >= n) bad = true;
-                        else {
-                            const double2 *prw = reinterpret_cast<const double2 *>(&S[prow][0]);
-                            const double2 p01 = prw[0], p23 = prw[1];
-                            const double pr[PB] = {p01.x, p01.y, p23.x, p23.y, S[prow][4]};
-                            const double d = pr[t];
-                            if (!(fabs(d) > 0.0) || (!kPivot && !(d > 0.0))) bad = true;
-                            const double dinv = __drcp_rn(d);        // correctly rounded, = 1.0 / d
-                            double rr[PB];
-#pragma unroll
-                            for (int c = 0; c < PB; ++c) rr[c] = (c == t) ? dinv : pr[c] * dinv;
-                            __syncwarp();                            // everybody has read the pivot row
-#pragma unroll
-                            for (int s = 0; s < 4; ++s) {
-                                const int i = lane + 32 * s;
-                                const double mlt = -x[s][t];
-#pragma unroll
-                                for (int c = 0; c < PB; ++c) x[s][c] = (c == t) ? mlt * dinv : fma(mlt, rr[c], x[s][c]);
-                                double2 *row = reinterpret_cast<double2 *>(&S[i][0]);
-                                row[0] = make_double2(x[s][0], x[s][1]); row[1] = make_double2(x[s][2], x[s][3]); S[i][4] = x[s][4];
-                            }
-                            // the pivot row itself becomes the scaled row, slot t carries 1/d (its lane stored it above:
-                            // the same lane overwrites it here, in program order)
-                            if ((prow & 31) == lane) {
-                                double2 *row = reinterpret_cast<double2 *>(&S[prow][0]);
-                                row[0] = make_double2(rr[0], rr[1]); row[1] = make_double2(rr[2], rr[3]); S[prow][4] = rr[4];
-                                usedmask |= 1u << (prow >> 5);
-                            }
-                            __syncwarp();
-                            // re-read the own rows: only the pivot row changed under its owner's feet
-#pragma unroll
-                            for (int s = 0; s < 4; ++s) {
-                                const double2 *row = reinterpret_cast<const double2 *>(&S[lane + 32 * s][0]);
-                                const double2 a01 = row[0], a23 = row[1];
-                                x[s][0] = a01.x; x[s][1] = a01.y; x[s][2] = a23.x; x[s][3] = a23.y; x[s][4] = S[lane + 32 * s][4];
-                            }
-                            pl[t] = prow;
-                        }
-                    }
-                }
-                // (T - I)[:, P]: take the unit entries of the pivot rows out again
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const int i = lane + 32 * s;
-#pragma unroll
-                    for (int c = 0; c < PB; ++c)
-                        if (i < n && c < bw) Pcol[buf][c][ppos(i)] = x[s][c] - ((i == pl[c]) ? 1.0 : 0.0);
-                }
-                if (lane == 0) {
-#pragma unroll
-                    for (int t = 0; t < PB; ++t) { s_prow[buf][t] = bad ? -1 : pl[t]; if (t < bw) perm[PB * (PB * g + t) + w] = bad ? PB * (PB * g + t) + w : pl[t]; }
-                }
-                nbar_arrive(2, all);                                  // orders the stores above for the waiting workers
-                if (bad) break;
-            }
-        } else {
-            // the tile lives only in the workers' registers (the searcher's registers hold its panel)
-            double a[8][PB];
-#pragma unroll
-            for (int c = 0; c < PB; ++c) {
-                const int j = c0 + c;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int i = r0 + r;
-                    a[r][c] = (owner && i < n && j < n) ? B[(ll)j * ldg + i] : 0.0;      // transposed load: A = B^T
-                }
-            }
-            if (owner && gt == 0) {
-#pragma unroll
-                for (int r = 0; r < 8; ++r) Pcol[0][qt][ppos(r0 + r)] = a[r][0];
-            }
-            nbar_arrive(1, all);
-            int fail = 0;
-            for (int it = 0; it < NPE; ++it) {
-                const int j = s_pj[it], bw = s_pbw[it], buf = it & 1, g = j / PB, w = j - PB * g;
-                const bool more = it + 1 < NPE;                        // the next non-empty panel
-                const int jn = more ? s_pj[it + 1] : 0, bwn = more ? s_pbw[it + 1] : 0;
-                const int gn = jn / PB, wn = jn - PB * gn;
-                nbar_sync(2, all);                                    // the pivots of panel j are known
-                int pl[PB];
-#pragma unroll
-                for (int t = 0; t < PB; ++t) pl[t] = s_prow[buf][t];
-                if (pl[0] < 0) { fail = 1; break; }                   // no usable pivot: uniform across the CTA
-                // the owners of the pivot rows publish them as they are
-#pragma unroll
-                for (int t = 0; t < PB; ++t) {
-                    if (t < bw && owner && tr == (pl[t] >> 3)) {
-#define PUBLISH_ROW(R) _Pragma("unroll") for (int c = 0; c < PB; ++c) Rrow[buf][t][c0 + c] = a[R][c];
-                        switch (pl[t] & 7) {
-                        case 0: PUBLISH_ROW(0) break;
-                        case 1: PUBLISH_ROW(1) break;
-                        case 2: PUBLISH_ROW(2) break;
-                        case 3: PUBLISH_ROW(3) break;
-                        case 4: PUBLISH_ROW(4) break;
-                        case 5: PUBLISH_ROW(5) break;
-                        case 6: PUBLISH_ROW(6) break;
-                        default: PUBLISH_ROW(7) break;
-                        }
-#undef PUBLISH_ROW
-                    }
-                }
-                nbar_sync(3, W);
-                const bool in_panel = owner && gt == g && qt < bw;
-                const bool in_next = owner && more && gt == gn && qt < bwn;
-                // look-ahead: the next panel's columns first, then they go to the searcher
-                if (in_next) {
-#define EARLY_COL(C)                                                                                                    \
-    _Pragma("unroll") for (int t = 0; t < PB; ++t) {                                                                   \
-        if (t < bw) {                                                                                                   \
-            const double rvc = Rrow[buf][t][c0 + C];                                                                    \
-            _Pragma("unroll") for (int h = 0; h < 4; ++h) {                                                             \
-                const double2 q2 = *reinterpret_cast<const double2 *>(&Pcol[buf][t][ppos(r0 + 2 * h)]);                 \
-                a[2 * h][C] = fma(q2.x, rvc, a[2 * h][C]); a[2 * h + 1][C] = fma(q2.y, rvc, a[2 * h + 1][C]);           \
-            }                                                                                                           \
-        }                                                                                                               \
-    }                                                                                                                   \
-    _Pragma("unroll") for (int r = 0; r < 8; ++r) Pcol[buf ^ 1][qt][ppos(r0 + r)] = a[r][C];
-                    switch (wn) {
-                    case 0: EARLY_COL(0) break;
-                    case 1: EARLY_COL(1) break;
-                    case 2: EARLY_COL(2) break;
-                    case 3: EARLY_COL(3) break;
-                    default: EARLY_COL(4) break;
-                    }
-#undef EARLY_COL
-                }
-                if (more) nbar_arrive(1, all);
-                const int skip1 = in_panel ? w : -1, skip2 = in_next ? wn : -1;
-                if (owner) {
-#pragma unroll
-                    for (int t = 0; t < PB; ++t) {
-                        if (t < bw) {
-                            double cv[8], rv[PB];
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) { const double2 q = *reinterpret_cast<const double2 *>(&Pcol[buf][t][ppos(r0 + 2 * h)]); cv[2 * h] = q.x; cv[2 * h + 1] = q.y; }
-#pragma unroll
-                            for (int c = 0; c < PB; ++c) rv[c] = Rrow[buf][t][c0 + c];
-#pragma unroll
-                            for (int c = 0; c < PB; ++c) {
-                                if (c != skip1 && c != skip2) {
-#pragma unroll
-                                    for (int r = 0; r < 8; ++r) a[r][c] = fma(cv[r], rv[c], a[r][c]);
-                                }
-                            }
-                        }
-                    }
-                }
-                if (in_panel) {
-                    // this thread's column w is column qt of the panel: it receives T[:, P] = (T - I)[:, P] + unit entry
-                    const int prow = s_prow[buf][qt];
-#define TAKE_COL(C) _Pragma("unroll") for (int r = 0; r < 8; ++r) a[r][C] = Pcol[buf][qt][ppos(r0 + r)] + ((r0 + r == prow) ? 1.0 : 0.0);
-                    switch (w) {
-                    case 0: TAKE_COL(0) break;
-                    case 1: TAKE_COL(1) break;
-                    case 2: TAKE_COL(2) break;
-                    case 3: TAKE_COL(3) break;
-                    default: TAKE_COL(4) break;
-                    }
-#undef TAKE_COL
-                }
-            }
-            // all pivots are known (the last pivot barrier has been passed): invert the permutation and store
-            if (!fail && tid < n) qinv[perm[tid]] = tid;       // perm is incomplete after a failure
-            nbar_sync(3, W);
-            if (tid == 0) fail_flags[p] = fail;
-            if (!fail && owner) {
-                // A^-1[kk][cc] = W[perm[kk]][qinv[cc]]  <=>  W[i][j] goes to row qinv[i], column perm[j]
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int i = r0 + r;
-                    if (i < n) {
-                        const ll row = (ll)qinv[i] * ldg;
-#pragma unroll
-                        for (int c = 0; c < PB; ++c) {
-                            const int j2 = c0 + c;
-                            if (j2 < n) B[row + perm[j2]] = a[r][c];
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// Same algorithm with 8 x 8 tiles: (n/8)^2 threads, 64 FMAs per thread and step against 16 shared-memory loads and
-// half as many warps repeating the pivot search -- the 8 x 4 form above is issue-bound on exactly that overhead.
-template <bool kPivot>
-__global__ void __launch_bounds__(256, 1)
-ssc_invert_reg8_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll count, int *__restrict__ fail_flags, int TC)
-{
-    __shared__ __align__(16) double colv[2][128];
-    __shared__ __align__(16) double rowv[2][128];
-    __shared__ int perm[128], qinv[128];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int tr = tid / TC, tc = tid - tr * TC;
-    const bool owner = tr < TC;                              // TC = ceil(n / 8) tiles in both directions
-    const int r0 = owner ? 8 * tr : 0, c0 = 8 * tc;
-    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
-        double *B = blocks + p * stride;
-        double a[8][8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int j = c0 + c;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int i = r0 + r;
-                a[r][c] = (owner && i < n && j < n) ? B[(ll)j * ldg + i] : 0.0;      // transposed load: A = B^T
-            }
-        }
-        unsigned usedmask = 0;
-        int fail = 0;
-        for (int k = 0; k < n; ++k) {
-            const int buf = k & 1;
-            if (owner && tc == (k >> 3)) {
-#define PUBLISH_COL(C)                                                                  \
-    _Pragma("unroll") for (int r = 0; r < 8; ++r) { colv[buf][r0 + r] = a[r][C]; a[r][C] = 0.0; }
-                switch (k & 7) {
-                case 0: PUBLISH_COL(0) break;
-                case 1: PUBLISH_COL(1) break;
-                case 2: PUBLISH_COL(2) break;
-                case 3: PUBLISH_COL(3) break;
-                case 4: PUBLISH_COL(4) break;
-                case 5: PUBLISH_COL(5) break;
-                case 6: PUBLISH_COL(6) break;
-                default: PUBLISH_COL(7) break;
-                }
-#undef PUBLISH_COL
-            }
-            __syncthreads();
-            int prow = k;
-            if (kPivot) {
-                double best = -1.0;
-                int bi = 1 << 30;
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const int i = lane + 32 * s;
-                    if (i < n && !((usedmask >> s) & 1u)) {
-                        const double v = fabs(colv[buf][i]);
-                        if (v > best) { best = v; bi = i; }
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-                }
-                prow = bi;
-                if (prow >= n) { fail = 1; break; }
-                if ((prow & 31) == lane) usedmask |= 1u << (prow >> 5);
-                if (tid == 0) perm[k] = prow;
-            }
-            const double d = colv[buf][prow];
-            if (!(fabs(d) > 0.0) || (!kPivot && !(d > 0.0))) { fail = 1; break; }     // uniform across the CTA
-            const double dinv = 1.0 / d;
-            if (owner && tr == (prow >> 3)) {
-#define PUBLISH_ROW(R)                                                                                          \
-    _Pragma("unroll") for (int c = 0; c < 8; ++c) { rowv[buf][c0 + c] = (c0 + c == k) ? dinv : a[R][c] * dinv; a[R][c] = 0.0; }
-                switch (prow & 7) {
-                case 0: PUBLISH_ROW(0) break;
-                case 1: PUBLISH_ROW(1) break;
-                case 2: PUBLISH_ROW(2) break;
-                case 3: PUBLISH_ROW(3) break;
-                case 4: PUBLISH_ROW(4) break;
-                case 5: PUBLISH_ROW(5) break;
-                case 6: PUBLISH_ROW(6) break;
-                default: PUBLISH_ROW(7) break;
-                }
-#undef PUBLISH_ROW
-            }
-            __syncthreads();
-            const double2 *cp = reinterpret_cast<const double2 *>(&colv[buf][r0]);
-            const double2 *rp2 = reinterpret_cast<const double2 *>(&rowv[buf][c0]);
-            double cv[8], rv[8];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) { const double2 t = cp[h]; cv[2 * h] = t.x; cv[2 * h + 1] = t.y; }
-#pragma unroll
-            for (int h = 0; h < 4; ++h) { const double2 t = rp2[h]; rv[2 * h] = t.x; rv[2 * h + 1] = t.y; }
-            const int rp = prow - r0;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const double m = (r == rp) ? 1.0 : -cv[r];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) a[r][c] = fma(m, rv[c], a[r][c]);
-            }
-        }
-        __syncthreads();
-        if (tid < n) { if (!kPivot) perm[tid] = tid; }
-        __syncthreads();
-        if (tid < n) qinv[perm[tid]] = tid;
-        __syncthreads();
-        if (tid == 0) fail_flags[p] = fail;
-        if (!fail && owner) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int i = r0 + r;
-                if (i < n) {
-                    const ll row = (ll)qinv[i] * ldg;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const int j = c0 + c;
-                        if (j < n) B[row + perm[j]] = a[r][c];
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// Blocked Gauss-Jordan for n > 128: the block stays in global memory (L2), 16 columns at a time are brought into
-// shared memory and eliminated there (with partial pivoting, rows exchanged across the whole block), and the
-// transformation they define is applied to all other columns as one (n x 16) x (16 x n) product on the fp64 tensor
-// cores (mma.sync.m8n8k4.f64, DMMA): every element of the block is read and written once per 16 pivots instead of once
-// per pivot, which is what bounds the unblocked global-memory kernel above.
-//   panel P (n x 16) after its own elimination holds T's non-trivial columns:  rest <- rest + (P - E) * rest[mid rows]
-__device__ __forceinline__ void dmma8x8x4(double &d0, double &d1, double a, double b, double c0, double c1)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
-                 : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
-}
-
-template <bool kPivot, int NB>
-__global__ void __launch_bounds__(512, NB == 16 ? 2 : 1)
-ssc_invert_blocked_kernel(double *__restrict__ blocks, int n, int ld, ll stride, ll count, int *__restrict__ fail_flags)
-{
-    constexpr int PP = NB + 1;                            // odd panel row stride: a thread per row walks it without bank conflicts
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int npad = (n + 7) & ~7;
-    const int WP = ((npad + 15) & ~15) + 4;               // row stride of W, = 4 mod 16: conflict-free B fragments per half-warp
-    double *P = reinterpret_cast<double *>(smem_raw);     // npad x PP
-    double *W = P + (size_t)npad * PP;                    // NB x WP
-    double *rowv = W + (size_t)NB * WP;                   // NB
-    double *redv = rowv + NB;                             // 32
-    int *redi = reinterpret_cast<int *>(redv + 32);       // 34
-    int *piv = redi + 34;                                 // n
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
-        double *A = blocks + p * stride;
-        int fail = 0;
-        for (int kb = 0; kb < n && !fail; kb += NB) {
-            const int bw = min(NB, n - kb);
-            // (a) panel -> shared memory
-            for (int e = tid; e < npad * NB; e += blockDim.x) {
-                const int i = e / NB, j = e - i * NB;
-                P[i * PP + j] = (i < n && j < bw) ? A[(ll)i * ld + kb + j] : 0.0;
-            }
-            __syncthreads();
-            // (b) unblocked Gauss-Jordan on the panel columns, two barriers per pivot: the scaled pivot row is staged in
-            //     rowv, then every thread updates its rows; the row exchange is implicit (the thread that owns position
-            //     prow writes both exchanged rows) and the arg-max partials for the next column are collected on the fly.
-            auto warp_argmax = [&](double &best, int &bi) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-                }
-            };
-            if (kPivot) {
-                double best = -1.0; int bi = n;
-                for (int i = kb + tid; i < n; i += blockDim.x) { const double v = fabs(P[i * PP]); if (v > best) { best = v; bi = i; } }
-                warp_argmax(best, bi);
-                if (lane == 0) { redv[warp] = best; redi[warp] = bi; }
-                __syncthreads();
-            }
-            for (int j = 0; j < bw; ++j) {
-                const int c = kb + j;
-                int prow = c;
-                if (kPivot) {
-                    double best = -1.0; int bi = n;
-                    for (int w = 0; w < nwarps; ++w) { const double ov = redv[w]; const int oi = redi[w]; if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; } }
-                    prow = bi;
-                    if (prow >= n) { fail = 1; break; }
-                }
-                const double d = P[prow * PP + j];
-                if (!(fabs(d) > 0.0) || (!kPivot && !(d > 0.0))) { fail = 1; break; }     // uniform
-                const double dinv = 1.0 / d;
-                if (tid < NB) rowv[tid] = (tid == j) ? dinv : P[prow * PP + tid] * dinv;
-                if (tid == 0) piv[c] = prow;
-                __syncthreads();
-                double best = -1.0; int bi = n;
-                for (int i = tid; i < n; i += blockDim.x) {
-                    if (i == c && prow != c) continue;             // written by the owner of position prow
-                    if (i == prow) {
-                        double old[NB];
-                        if (prow != c) {
-#pragma unroll
-                            for (int jj = 0; jj < NB; ++jj) old[jj] = P[c * PP + jj];
-                        }
-#pragma unroll
-                        for (int jj = 0; jj < NB; ++jj) P[c * PP + jj] = rowv[jj];
-                        if (prow != c) {
-                            const double f = old[j];
-                            double *r = P + prow * PP;
-#pragma unroll
-                            for (int jj = 0; jj < NB; ++jj) {
-                                const double v = (jj == j) ? -f * dinv : fma(-f, rowv[jj], old[jj]);
-                                r[jj] = v;
-                                if (jj == j + 1) { const double av = fabs(v); if (av > best) { best = av; bi = prow; } }
-                            }
-                        }
-                    } else {
-                        double *r = P + i * PP;
-                        const double f = r[j];
-#pragma unroll
-                        for (int jj = 0; jj < NB; ++jj) {
-                            const double v = (jj == j) ? -f * dinv : fma(-f, rowv[jj], r[jj]);
-                            r[jj] = v;
-                            if (jj == j + 1 && i > c) { const double av = fabs(v); if (av > best || (av == best && i < bi)) { best = av; bi = i; } }
-                        }
-                    }
-                }
-                if (kPivot) {
-                    warp_argmax(best, bi);
-                    if (lane == 0) { redv[warp] = best; redi[warp] = bi; }
-                }
-                __syncthreads();
-            }
-            if (fail) break;
-            // (c) the panel's row exchanges on all other columns: a thread owns a column and replays the exchanges in
-            //     order for it, so no barrier is needed between them
-            if (kPivot) {
-                bool any = false;
-                for (int j = 0; j < bw; ++j) any |= (piv[kb + j] != kb + j);
-                if (any) {
-                    for (int col = tid; col < n; col += blockDim.x) {
-                        if (col >= kb && col < kb + bw) continue;
-                        for (int j = 0; j < bw; ++j) {
-                            const int c = kb + j, pr = piv[c];
-                            if (pr != c) { const double t = A[(ll)c * ld + col]; A[(ll)c * ld + col] = A[(ll)pr * ld + col]; A[(ll)pr * ld + col] = t; }
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-            // (d) the pivot rows of all other columns -> shared memory
-            for (int e = tid; e < NB * npad; e += blockDim.x) {
-                const int r = e / npad, col = e - r * npad;
-                W[r * WP + col] = (r < bw && col < n) ? A[(ll)(kb + r) * ld + col] : 0.0;
-            }
-            __syncthreads();
-            // (e) rest <- rest + (P - E) W on the tensor cores.  A warp owns a strip of kCT consecutive 8 x 8 tiles of one
-            //     tile row: the kCT accumulator fragments are fetched first (2*kCT independent loads in flight per lane),
-            //     then 4 DMMAs per tile with the A fragments shared along the strip.
-            constexpr int kCT = 8;
-            const int tr_n = npad >> 3;
-            const int nstrips = (tr_n + kCT - 1) / kCT;
-            for (int t = warp; t < tr_n * nstrips; t += nwarps) {
-                const int ti = t / nstrips, ts = t - ti * nstrips;
-                const int i0 = ti << 3;
-                const bool midrow = (i0 >= kb && i0 < kb + NB);
-                const int ri = i0 + (lane >> 2);
-                double c0[kCT], c1[kCT];
-#pragma unroll
-                for (int u = 0; u < kCT; ++u) {
-                    const int j0 = (ts * kCT + u) << 3, cj = j0 + 2 * (lane & 3);
-                    const bool skip = (j0 >= kb && j0 < kb + NB) || j0 >= npad;
-                    c0[u] = 0.0; c1[u] = 0.0;
-                    if (!skip && !midrow && ri < n) {
-                        if (cj < n) c0[u] = A[(ll)ri * ld + cj];
-                        if (cj + 1 < n) c1[u] = A[(ll)ri * ld + cj + 1];
-                    }
-                }
-                double af[NB / 4];
-#pragma unroll
-                for (int q = 0; q < NB / 4; ++q) af[q] = P[(i0 + (lane >> 2)) * PP + 4 * q + (lane & 3)];
-#pragma unroll
-                for (int u = 0; u < kCT; ++u) {
-                    const int j0 = (ts * kCT + u) << 3;
-                    if (j0 >= npad) continue;
-#pragma unroll
-                    for (int q = 0; q < NB / 4; ++q) {
-                        const double bfr = W[(4 * q + (lane & 3)) * WP + j0 + (lane >> 2)];
-                        dmma8x8x4(c0[u], c1[u], af[q], bfr, c0[u], c1[u]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kCT; ++u) {
-                    const int j0 = (ts * kCT + u) << 3, cj = j0 + 2 * (lane & 3);
-                    const bool skip = (j0 >= kb && j0 < kb + NB) || j0 >= npad;
-                    if (!skip && ri < n) {
-                        if (cj < n) A[(ll)ri * ld + cj] = c0[u];
-                        if (cj + 1 < n) A[(ll)ri * ld + cj + 1] = c1[u];
-                    }
-                }
-            }
-            // (f) panel back
-            for (int e = tid; e < n * bw; e += blockDim.x) {
-                const int i = e / bw, j = e - i * bw;
-                A[(ll)i * ld + kb + j] = P[i * PP + j];
-            }
-            __syncthreads();
-        }
-        __syncthreads();
-        if (tid == 0) fail_flags[p] = fail;
-        // The array now holds M' = (Pi A)^-1 = A^-1 Pi^T with (Pi A)[k] = A[pi(k)].  Wanted: S = (A^-1)^T, whose row pi(k)
-        // is column k of M'.  So: transpose in place, then permute rows; a thread owns a column during the row
-        // permutation and follows the cycles of pi, so neither step needs barriers inside.
-        for (ll e = tid; e < (ll)n * n; e += blockDim.x) {
-            const int i = (int)(e / n), j = (int)(e - (ll)i * n);
-            if (i < j) { const double a = A[(ll)i * ld + j]; A[(ll)i * ld + j] = A[(ll)j * ld + i]; A[(ll)j * ld + i] = a; }
-        }
-        if (kPivot && !fail) {
-            int *pi = redi + 34 + n;                      // second int array behind piv
-            if (tid == 0) {
-                for (int i = 0; i < n; ++i) pi[i] = i;
-                for (int c = 0; c < n; ++c) { const int pr = piv[c]; const int t = pi[c]; pi[c] = pi[pr]; pi[pr] = t; }
-            }
-            __syncthreads();                              // also orders the transpose before the permutation
-            for (int col = tid; col < n; col += blockDim.x) {
-                // new row pi(k) = old row k.  Walk every cycle once, starting from its smallest member.
-                for (int s = 0; s < n; ++s) {
-                    if (pi[s] == s) continue;
-                    bool smallest = true;
-                    for (int q = pi[s]; q != s; q = pi[q]) if (q < s) { smallest = false; break; }
-                    if (!smallest) continue;
-                    double carry = A[(ll)s * ld + col];
-                    int k = s;
-                    do {
-                        const int dst = pi[k];
-                        const double nxt = A[(ll)dst * ld + col];
-                        A[(ll)dst * ld + col] = carry;
-                        carry = nxt;
-                        k = dst;
-                    } while (k != s);
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K3+K4+K5 apply: gather -> stored-inverse product -> scatter-add, fused (ssc/libssc.c:1359-1386).
-// `ppb` patches per CTA, `tp` threads per patch (tp >= n except for very large patches, where a thread
-// owns several rows).  The residual entries of a patch are gathered into shared memory (one index load and
-// one x load per patch dof), then thread i streams column i of S with evict-first loads and adds its
-// result into y with one fp64 reduction (RED.E.ADD.F64 at L2).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-ssc_apply_kernel(const double *__restrict__ S, ll stride, int ld, const int *__restrict__ gtol, int n, ll count, int tp, int ppb,
-                 const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
-                 const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
-{
-    extern __shared__ __align__(16) double xs_all[];
-    const int lp = threadIdx.x / tp, t = threadIdx.x - lp * tp;
-    const ll p = (ll)blockIdx.x * ppb + lp;
-    const bool active = lp < ppb && p < count;
-    double *xs = xs_all + (size_t)lp * n;
-    const int *g = gtol + p * n;
-    if (active) for (int i = t; i < n; i += tp) xs[i] = gather_x(x, g[i], ps);
-    __syncthreads();
-    if (!active) return;
-    const double sc = mult ? scale * mult[p] : scale;
-    for (int i = t; i < n; i += tp) {
-        const double *M = S + p * stride + i;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int j = 0;
-#pragma unroll 1
-        for (; j + 8 <= n; j += 8) {
-            const double m0 = __ldcs(M + (ll)(j + 0) * ld), m1 = __ldcs(M + (ll)(j + 1) * ld);
-            const double m2 = __ldcs(M + (ll)(j + 2) * ld), m3 = __ldcs(M + (ll)(j + 3) * ld);
-            const double m4 = __ldcs(M + (ll)(j + 4) * ld), m5 = __ldcs(M + (ll)(j + 5) * ld);
-            const double m6 = __ldcs(M + (ll)(j + 6) * ld), m7 = __ldcs(M + (ll)(j + 7) * ld);
-            a0 = fma(m0, xs[j + 0], a0); a1 = fma(m1, xs[j + 1], a1); a2 = fma(m2, xs[j + 2], a2); a3 = fma(m3, xs[j + 3], a3);
-            a0 = fma(m4, xs[j + 4], a0); a1 = fma(m5, xs[j + 5], a1); a2 = fma(m6, xs[j + 6], a2); a3 = fma(m7, xs[j + 7], a3);
-        }
-        for (; j < n; ++j) a0 = fma(__ldcs(M + (ll)j * ld), xs[j], a0);
-        emit(y, g[i], ((a0 + a1) + (a2 + a3)) * sc, ps, ypatch, p * n + i);
-    }
-}
-
-// Software-pipelined variants: the next group of kU column loads is already in flight while the current group is
-// consumed, so a thread always has kU..2*kU loads outstanding (the v0 loop drains its loads every iteration).
-// kVec = 1: thread i owns row i (LDG.64).  kVec = 2: thread t owns rows 2t and 2t+1 and loads them with one
-// 16-byte LDG.128; the row stride ld is even so every such load is aligned.
-template <int kVec> struct VecT;
-template <> struct VecT<1> { typedef double T; };
-template <> struct VecT<2> { typedef double2 T; };
-__device__ __forceinline__ void fma_vec(double m, double xv, double &a0, double &) { a0 = fma(m, xv, a0); }
-__device__ __forceinline__ void fma_vec(double2 m, double xv, double &a0, double &a1) { a0 = fma(m.x, xv, a0); a1 = fma(m.y, xv, a1); }
-
-template <int kVec, int kU>
-__global__ void __launch_bounds__(256)
-ssc_apply_pipe_kernel(const double *__restrict__ S, ll stride, int ld, const int *__restrict__ gtol, int n, ll count, int tp, int ppb,
-                      const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
-                      const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
-{
-    typedef typename VecT<kVec>::T T;
-    extern __shared__ __align__(16) double xs_all[];
-    const int lp = threadIdx.x / tp, t = threadIdx.x - lp * tp;
-    const ll p = (ll)blockIdx.x * ppb + lp;
-    const bool active = lp < ppb && p < count;
-    double *xs = xs_all + (size_t)lp * n;
-    const int *g = gtol + p * n;
-    if (active) for (int i = t; i < n; i += tp) xs[i] = gather_x(x, g[i], ps);
-    __syncthreads();
-    if (!active) return;
-    const double sc = mult ? scale * mult[p] : scale;
-    const int ngroups = n / kU;
-    const ll ldv = ld / kVec;                         // row stride in units of T
-    for (int i = t * kVec; i < n; i += tp * kVec) {
-        const T *M = reinterpret_cast<const T *>(S + p * stride + i);
-        T A[kU], B[kU];
-        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-        if (ngroups > 0) {
-#pragma unroll
-            for (int u = 0; u < kU; ++u) A[u] = __ldcs(M + (ll)u * ldv);
-        }
-        for (int gi = 0; gi < ngroups; gi += 2) {
-            const int j = gi * kU;
-            const bool hasB = gi + 1 < ngroups, hasA = gi + 2 < ngroups;
-            if (hasB) {
-#pragma unroll
-                for (int u = 0; u < kU; ++u) B[u] = __ldcs(M + (ll)(j + kU + u) * ldv);
-            }
-#pragma unroll
-            for (int u = 0; u < kU; u += 2) {
-                fma_vec(A[u], xs[j + u], a0, a1);
-                fma_vec(A[u + 1], xs[j + u + 1], b0, b1);
-            }
-            if (hasA) {
-#pragma unroll
-                for (int u = 0; u < kU; ++u) A[u] = __ldcs(M + (ll)(j + 2 * kU + u) * ldv);
-            }
-            if (hasB) {
-#pragma unroll
-                for (int u = 0; u < kU; u += 2) {
-                    fma_vec(B[u], xs[j + kU + u], a0, a1);
-                    fma_vec(B[u + 1], xs[j + kU + u + 1], b0, b1);
-                }
-            }
-        }
-        for (int j = ngroups * kU; j < n; ++j) fma_vec(__ldcs(M + (ll)j * ldv), xs[j], a0, a1);
-        emit(y, g[i], (a0 + b0) * sc, ps, ypatch, p * n + i);
-        if (kVec == 2 && i + 1 < n) emit(y, g[i + 1], (a1 + b1) * sc, ps, ypatch, p * n + i + 1);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// small vector kernels of PCApply_PATCH / PCSetUp_PATCH
-// ---------------------------------------------------------------------------------------------
-// y[idx] = x[idx] on owned Dirichlet dofs, ssc/libssc.c:1408-1413
-__global__ void ssc_bc_kernel(const int *__restrict__ bc, ll nbc, const double *__restrict__ x, double *__restrict__ y)
-{
-    const ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nbc) { const int d = bc[i]; y[d] = x[d]; }
-}
-// y *= w, ssc/libssc.c:1418-1421
-__global__ void ssc_scale_kernel(ll n, const double *__restrict__ w, double *__restrict__ y)
-{
-    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) y[i] *= w[i];
-}
-// multiplicity: scatter ones through every patch's dof list, ssc/libssc.c:1263-1273
-__global__ void ssc_count_kernel(const int *__restrict__ gtol, ll total, double *__restrict__ m)
-{
-    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (ll)gridDim.x * blockDim.x) atomicAdd(m + gtol[i], 1.0);
-}
-// VecReciprocal (:1282): zero entries stay zero
-__global__ void ssc_reciprocal_kernel(ll n, double *__restrict__ w)
-{
-    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) { const double v = w[i]; w[i] = v != 0.0 ? 1.0 / v : 0.0; }
-}
-// star-forest pieces: dst[di[i]] (=|+=) src[si[i]]
-__global__ void ssc_gather_kernel(ll n, const int *__restrict__ si, const double *__restrict__ src, double *__restrict__ dst)
-{
-    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) dst[i] = src[si[i]];
-}
-__global__ void ssc_scatter_kernel(ll n, const int *__restrict__ di, const double *__restrict__ src, double *__restrict__ dst, int add)
-{
-    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) {
-        if (add) atomicAdd(dst + di[i], src[i]); else dst[di[i]] = src[i];
-    }
-}
-__global__ void ssc_copy_indexed_kernel(ll n, const int *__restrict__ di, const int *__restrict__ si, const double *__restrict__ src,
-                                        double *__restrict__ dst, int add)
-{
-    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) {
-        if (add) atomicAdd(dst + di[i], src[si[i]]); else dst[di[i]] = src[si[i]];
-    }
-}
-__global__ void ssc_fill_kernel(ll n, double *__restrict__ a, double v)
-{
-    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) a[i] = v;
-}
-
-// y = A x for a CSR matrix, one warp per row (restriction / prolongation of the low-order PC, ssc/lo.py:187-198)
-__global__ void ssc_spmv_kernel(ll nrows, const ll *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals,
-                                const double *__restrict__ x, double *__restrict__ y)
-{
-    const ll warp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= nrows) return;
-    double s = 0.0;
-    for (ll k = rowptr[warp] + lane; k < rowptr[warp + 1]; k += 32) s = fma(vals[k], __ldg(x + colidx[k]), s);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) y[warp] = s;
-}
-
-// ---------------------------------------------------------------------------------------------
-// NVLink peer exchange (one process per GPU, buffers mapped with CUDA IPC)
-// ---------------------------------------------------------------------------------------------
-struct PeerPush { double *xl[16]; };
-// halo fill (SFBcast, ssc/libssc.c:1323-1324) as direct stores into the neighbours' ghost slots
-__global__ void ssc_peer_push_kernel(ll n, const int *__restrict__ sendRoot, const int *__restrict__ sendPeer, const int *__restrict__ remoteLeaf,
-                                     const double *__restrict__ x, PeerPush peers)
-{
-    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x)
-        peers.xl[sendPeer[i]][remoteLeaf[i]] = x[sendRoot[i]];
-}
-struct PeerFlags { unsigned long long *flags[16]; int slot[16]; };
-// Neighbour barrier: thread k tells neighbour k "everything this rank enqueued before epoch e is done" and waits for
-// the same word from it.  Each rank runs on its own GPU; a bounded spin turns a lost peer into an error flag, not a hang.
-__global__ void ssc_peer_barrier_kernel(int nneigh, PeerFlags peers, volatile unsigned long long *mine, unsigned long long epoch, int *timeout)
-{
-    const int k = threadIdx.x;
-    if (k >= nneigh) return;
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flags[k] + peers.slot[k]), "l"(epoch) : "memory");
-    const long long t0 = clock64();
-    unsigned long long v;
-    do {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + k) : "memory");
-        if (clock64() - t0 > 8000000000LL) { *timeout = 1; break; }      // ~4 s
-    } while (v < epoch);
-    __threadfence_system();
-}
-
-// The two halves of the neighbour barrier as separate launches: a rank can announce "my patches that touch other
-// ranks' dofs are done" early and collect the neighbours' announcements late (pipelined host-space apply).
-__global__ void ssc_peer_signal_kernel(int nneigh, PeerFlags peers, unsigned long long epoch)
-{
-    const int k = threadIdx.x;
-    if (k >= nneigh) return;
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flags[k] + peers.slot[k]), "l"(epoch) : "memory");
-}
-__global__ void ssc_peer_wait_kernel(int nneigh, volatile unsigned long long *mine, unsigned long long epoch, int *timeout)
-{
-    const int k = threadIdx.x;
-    if (k >= nneigh) return;
-    const long long t0 = clock64();
-    unsigned long long v;
-    do {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + k) : "memory");
-        if (clock64() - t0 > 8000000000LL) { *timeout = 1; break; }      // ~4 s
-    } while (v < epoch);
-    __threadfence_system();
-}
-
-// r = x - A y, one warp per row (residual between the colours of a multiplicative sweep)
-__global__ void ssc_residual_kernel(ll nrows, const ll *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals,
-                                    const double *__restrict__ x, const double *__restrict__ y, double *__restrict__ r)
-{
-    const ll warp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= nrows) return;
-    double s = 0.0;
-    for (ll k = rowptr[warp] + lane; k < rowptr[warp + 1]; k += 32) s = fma(vals[k], y[colidx[k]], s);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) r[warp] = x[warp] - s;
-}
-
-// deterministic mode: y[g] = sum of the slots of dof g, in ascending slot order (no atomics)
-__global__ void ssc_slot_sum_kernel(ll n, const ll *__restrict__ off, const int *__restrict__ slots, const double *__restrict__ ypatch, double *__restrict__ y)
-{
-    for (ll g = (ll)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (ll)gridDim.x * blockDim.x) {
-        double s = 0.0;
-        for (ll k = off[g]; k < off[g + 1]; ++k) s += ypatch[slots[k]];
-        y[g] = s;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Packed-symmetric storage (-ssc_symmetric_storage, SPD blocks with -sub_pc_type cholesky): the inverse of an SPD
-// block is symmetric, so only its lower triangle is kept, column by column: L[colstart(j) + (i - j)] = S[i][j], i >= j,
-// colstart(j) = j n - j (j - 1) / 2.  Half the bytes of the general layout (own roofline line: SURVEY.md 8d).
-// The apply kernel brings the whole triangle of a patch into shared memory with ONE bulk asynchronous copy (TMA,
-// cp.async.bulk + mbarrier: SASS UBLKCP), several CTAs per SM keep ~190 KB in flight, and thread i then does
-//   y_i = sum_{j <= i} L[i][j] x_j  (row pass, conflict-free)  +  sum_{k > i} L[k][i] x_k  (column pass)
-// -- n multiply-adds per thread whatever i is.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE;\n"
-        "bra LAB_WAIT;\n"
-        "LAB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-// the two halves of y_i for the packed layout, four independent loads in flight each
-__device__ __forceinline__ double sym_row_pass(const double *__restrict__ L, const double *__restrict__ xs, int n, int i)
-{
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int cs = i, j = 0;                                   // L[i][j] sits at colstart(j) + (i - j); +(n - j - 1) per column
-    for (; j + 3 <= i; j += 4) {
-        const int c1 = cs + (n - j) - 1, c2 = c1 + (n - j) - 2, c3 = c2 + (n - j) - 3;
-        const double l0 = L[cs], l1 = L[c1], l2 = L[c2], l3 = L[c3];
-        a0 = fma(l0, xs[j], a0); a1 = fma(l1, xs[j + 1], a1); a2 = fma(l2, xs[j + 2], a2); a3 = fma(l3, xs[j + 3], a3);
-        cs = c3 + (n - j) - 4;
-    }
-    for (; j <= i; ++j) { a0 = fma(L[cs], xs[j], a0); cs += (n - j) - 1; }
-    return (a0 + a1) + (a2 + a3);
-}
-__device__ __forceinline__ double sym_col_pass(const double *__restrict__ L, const double *__restrict__ xs, int n, int i)
-{
-    const double *col = L + ((ll)i * n - (ll)i * (i - 1) / 2) - i;      // L[k][i] = col[k], k > i
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int kk = i + 1;
-    for (; kk + 3 < n; kk += 4) {
-        a0 = fma(col[kk], xs[kk], a0); a1 = fma(col[kk + 1], xs[kk + 1], a1);
-        a2 = fma(col[kk + 2], xs[kk + 2], a2); a3 = fma(col[kk + 3], xs[kk + 3], a3);
-    }
-    for (; kk < n; ++kk) a0 = fma(col[kk], xs[kk], a0);
-    return (a0 + a1) + (a2 + a3);
-}
-
-// sum over m = q (mod F), mlo <= m < mhi, of L[colstart(min(i, m)) + |i - m|] * x_m  -- one thread's share of y_i when F
-// threads split a row.  Indices advance incrementally: in the row part (m <= i) the step from m to m + F is
-// F (n - m - 1) - F (F - 1) / 2 and shrinks by F^2 each time; in the column part (m > i) it is F.
-__device__ __forceinline__ double sym_terms(const double *__restrict__ L, const double *__restrict__ xs, int n, int i, int q, int F, int mlo, int mhi)
-{
-    double a0 = 0.0, a1 = 0.0;
-    int m = mlo + ((q - mlo) % F + F) % F;
-    const int rend = min(mhi, i + 1);
-    if (m < rend) {
-        int idx = m * n - ((m * (m - 1)) >> 1) + (i - m);
-        int step = F * (n - m - 1) - ((F * (F - 1)) >> 1);
-        const int dstep = F * F;
-        for (; m + F < rend; m += 2 * F) {
-            const double l0 = L[idx];
-            const int idx1 = idx + step;
-            const double l1 = L[idx1];
-            a0 = fma(l0, xs[m], a0);
-            a1 = fma(l1, xs[m + F], a1);
-            idx = idx1 + step - dstep;
-            step -= 2 * dstep;
-        }
-        if (m < rend) { a0 = fma(L[idx], xs[m], a0); m += F; }
-    }
-    // column part: first m > i (and >= mlo) in this thread's residue class
-    if (m <= i) m += ((i - m) / F + 1) * F;
-    const double *col = L + (i * n - ((i * (i - 1)) >> 1) - i);
-    for (; m + F < mhi; m += 2 * F) { a0 = fma(col[m], xs[m], a0); a1 = fma(col[m + F], xs[m + F], a1); }
-    if (m < mhi) a0 = fma(col[m], xs[m], a0);
-    return a0 + a1;
-}
-
-__global__ void ssc_pack_sym_kernel(const double *__restrict__ blocks, int n, int ld, ll stride, double *__restrict__ packed, ll pstride, ll count)
-{
-    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
-        const double *S = blocks + p * stride;
-        double *L = packed + p * pstride;
-        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-            const int j = e / n, i = e - j * n;                          // S[j*ld + i] = inverse[i][j]; consecutive threads -> consecutive i
-            if (i >= j) L[(ll)j * n - (ll)j * (j - 1) / 2 + (i - j)] = 0.5 * (S[(ll)j * ld + i] + S[(ll)i * ld + j]);
-        }
-    }
-}
-
-// kBulk = true: one TMA bulk copy per patch (UBLKCP + mbarrier), the default.  kBulk = false: every thread issues 16-byte
-// cp.async copies (LDGSTS) -- measured slower on B200 (4.46 ms against 3.24 ms at 64^3 Q3, profiles/README.md).
-template <bool kBulk>
-__global__ void __launch_bounds__(1024)
-ssc_apply_sym_kernel(const double *__restrict__ packed, ll pstride, unsigned copy_bytes, const int *__restrict__ gtol, int n, ll count,
-                     const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
-                     const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *L = reinterpret_cast<double *>(smem_raw);
-    double *xs = L + (copy_bytes >> 3);
-    __shared__ __align__(8) unsigned long long bar;
-    const ll p = blockIdx.x;
-    const int t = threadIdx.x;
-    if (kBulk) {
-        if (t == 0) {
-            mbar_init(&bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (t == 0) {
-            mbar_expect_tx(&bar, copy_bytes);
-            bulk_copy_g2s(L, packed + p * pstride, copy_bytes, &bar);
-        }
-    } else {
-        const char *src = reinterpret_cast<const char *>(packed + p * pstride);
-        const unsigned dst = smem_u32(L);
-        for (unsigned off = 16u * t; off < copy_bytes; off += 16u * blockDim.x)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    const int *g = gtol + p * n;
-    for (int i = t; i < n; i += blockDim.x) xs[i] = gather_x(x, g[i], ps);
-    if (!kBulk) asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    if (kBulk) mbar_wait(&bar, 0);
-    const double sc = mult ? scale * mult[p] : scale;
-    for (int i = t; i < n; i += blockDim.x)
-        emit(y, g[i], (sym_row_pass(L, xs, n, i) + sym_col_pass(L, xs, n, i)) * sc, ps, ypatch, p * n + i);
-}
-
-// Two-chunk, two-threads-per-row form of the packed apply (the default): the triangle arrives as two bulk copies split
-// at a column boundary j1 (about half the bytes each); everything that only needs columns < j1 is computed while the
-// second copy is still in flight, and the n terms of a row are shared by two threads.  With
-//   y_i = sum_m L[colstart(min(i, m)) + |i - m|] x_m
-// the terms available after the first chunk are exactly those with min(i, m) < j1.
-__global__ void __launch_bounds__(1024)
-ssc_apply_sym2_kernel(const double *__restrict__ packed, ll pstride, unsigned copy_bytes, int j1, unsigned bytes0, const int *__restrict__ gtol, int n,
-                      ll count, const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
-                      const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *L = reinterpret_cast<double *>(smem_raw);
-    double *xs = L + (copy_bytes >> 3);
-    double *ypart = xs + n;
-    __shared__ __align__(8) unsigned long long bar[2];
-    const ll p = blockIdx.x;
-    const int t = threadIdx.x;
-    const int rp = blockDim.x >> 1;                              // row slots; thread (i, q) = (t % rp, t / rp)
-    const unsigned bytes1 = copy_bytes - bytes0;
-    if (t == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (t == 0) {
-        const double *src = packed + p * pstride;
-        mbar_expect_tx(&bar[0], bytes0);
-        bulk_copy_g2s(L, src, bytes0, &bar[0]);
-        if (bytes1) {
-            mbar_expect_tx(&bar[1], bytes1);
-            bulk_copy_g2s(L + (bytes0 >> 3), src + (bytes0 >> 3), bytes1, &bar[1]);
-        }
-    }
-    const int *g = gtol + p * n;
-    for (int i = t; i < n; i += blockDim.x) xs[i] = gather_x(x, g[i], ps);
-    __syncthreads();
-    const int i = t < rp ? t : t - rp, q = t < rp ? 0 : 1;
-    const bool valid = i < n;
-    double a0 = 0.0, a1 = 0.0;
-    mbar_wait(&bar[0], 0);
-    if (valid) a0 = sym_terms(L, xs, n, i, q, 2, 0, i < j1 ? n : j1);          // everything with min(i, m) < j1
-    if (bytes1) {
-        mbar_wait(&bar[1], 0);
-        if (valid && i >= j1) a1 = sym_terms(L, xs, n, i, q, 2, j1, n);
-    }
-    if (q == 1 && valid) ypart[i] = a0 + a1;
-    __syncthreads();
-    if (q == 0 && valid) {
-        const double sc = mult ? scale * mult[p] : scale;
-        emit(y, g[i], (a0 + a1 + ypart[i]) * sc, ps, ypatch, p * n + i);
-    }
-}
-
-// Persistent form of the packed-symmetric apply: one CTA per SM walks its share of the patches with a ring of kStages
-// shared-memory buffers.  Thread 0 keeps kStages - 1 bulk copies (one whole packed triangle each) in flight while the
-// CTA multiplies the patch that has landed; the residual entries of the next patch are gathered into registers before
-// the current patch is computed, so neither the gather nor the scatter latency stalls the stream.
-__global__ void __launch_bounds__(1024, 1)
-ssc_apply_sym_persistent_kernel(const double *__restrict__ packed, ll pstride, unsigned copy_bytes, int stages, const int *__restrict__ gtol, int n, ll count,
-                                const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
-                                const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bar[8];
-    const size_t stage_doubles = copy_bytes >> 3;
-    double *ring = reinterpret_cast<double *>(smem_raw);
-    double *xsbuf = ring + stage_doubles * stages;            // 2 x n
-    double *ypart = xsbuf + 2 * n;                             // (F - 1) x rp partial sums
-    const int rp = (n + 31) & ~31;                             // row slots per part
-    const int F = max(1, (int)blockDim.x / rp);                // threads per row
-    const int t = threadIdx.x;
-    const ll first = blockIdx.x, step = gridDim.x;
-    const ll mine = first < count ? (count - first + step - 1) / step : 0;
-    if (t == 0) {
-        for (int s = 0; s < stages; ++s) mbar_init(&bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (t == 0) {
-        for (int s = 0; s < stages - 1 && s < mine; ++s) {
-            mbar_expect_tx(&bar[s], copy_bytes);
-            bulk_copy_g2s(ring + stage_doubles * s, packed + (first + s * step) * pstride, copy_bytes, &bar[s]);
-        }
-    }
-    // residual of the first patch
-    if (mine > 0) for (int i = t; i < n; i += blockDim.x) xsbuf[i] = gather_x(x, gtol[first * n + i], ps);
-    __syncthreads();
-    for (ll k = 0; k < mine; ++k) {
-        const ll p = first + k * step;
-        const int s = (int)(k % stages);
-        const unsigned parity = (unsigned)((k / stages) & 1);
-        // keep the ring full: the stage freed at the end of the previous iteration takes patch k + stages - 1
-        if (t == 0 && k + stages - 1 < mine) {
-            const int sn = (int)((k + stages - 1) % stages);
-            mbar_expect_tx(&bar[sn], copy_bytes);
-            bulk_copy_g2s(ring + stage_doubles * sn, packed + (p + (stages - 1) * step) * pstride, copy_bytes, &bar[sn]);
-        }
-        const double *xs = xsbuf + (k & 1) * n;
-        double *xn = xsbuf + ((k + 1) & 1) * n;
-        // gather for the next patch into a register (rows beyond blockDim are fetched after the compute, rare)
-        const int *gn = gtol + (p + step) * n;
-        double xnext = 0.0;
-        const bool have_next = k + 1 < mine;
-        if (have_next && t < n) xnext = gather_x(x, gn[t], ps);
-        const int *g = gtol + p * n;
-        const double *L = ring + stage_doubles * s;
-        mbar_wait(&bar[s], parity);
-        const double sc = mult ? scale * mult[p] : scale;
-        {
-            // F threads per row; thread (i, q) adds the terms m = q, q + F, ... of
-            //   y_i = sum_m L[colstart(min(i, m)) + |i - m|] x_m        (the symmetric product on the packed triangle)
-            const int i = t % rp, q = t / rp;
-            double a0 = 0.0, a1 = 0.0;
-            if (i < n && q < F) {
-                a0 = sym_terms(L, xs, n, i, q, F, 0, n);
-                if (q > 0) ypart[(q - 1) * rp + i] = a0;
-            }
-            __syncthreads();
-            if (i < n && q == 0) {
-                double s = a0 + a1;
-                for (int qq = 1; qq < F; ++qq) s += ypart[(qq - 1) * rp + i];
-                emit(y, g[i], s * sc, ps, ypatch, p * n + i);
-            }
-        }
-        if (have_next) {
-            if (t < n) xn[t] = xnext;
-            for (int i = t + blockDim.x; i < n; i += blockDim.x) xn[i] = gather_x(x, gn[i], ps);
-        }
-        __syncthreads();          // stage s and xs are free again
-    }
-}
-
-// after the second neighbour barrier: fold what the neighbours added for this rank's interface dofs into y and clear it
-__global__ void ssc_peer_fold_kernel(ll n, const int *__restrict__ iface, double *__restrict__ yin, double *__restrict__ y)
-{
-    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) {
-        const int d = iface[i];
-        y[d] += yin[d];
-        yin[d] = 0.0;
-    }
-}
-
-// calibration: plain streaming read (sum) of a buffer, the read-only counterpart of the driver's copy-measured HBM peak
-__global__ void __launch_bounds__(256)
-ssc_stream_read_kernel(const double2 *__restrict__ a, ll n2, double *__restrict__ sink)
-{
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    const ll stride = (ll)gridDim.x * blockDim.x;
-    ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n2; i += 4 * stride) {
-        const double2 v0 = __ldcs(a + i), v1 = __ldcs(a + i + stride), v2 = __ldcs(a + i + 2 * stride), v3 = __ldcs(a + i + 3 * stride);
-        s0 += v0.x + v0.y; s1 += v1.x + v1.y; s2 += v2.x + v2.y; s3 += v3.x + v3.y;
-    }
-    for (; i < n2; i += stride) { const double2 v = __ldcs(a + i); s0 += v.x + v.y; }
-    const double s = (s0 + s1) + (s2 + s3);
-    if (s == 1.2345678e300) sink[0] = s;          // keeps the loads alive without a store per thread
-}
+#include "kernels_common.cuh"
+#include "kernels_operators.cuh"   // K1 extract, K1e assemble
+#include "kernels_factor.cuh"      // K2 Gauss-Jordan family
+#include "kernels_apply.cuh"       // K3+K4+K5 fused apply
+#include "kernels_vector.cuh"      // BC rows, weights, slot sum, SpMV, calibration read
+#include "kernels_peer.cuh"        // NVLink peer exchange
+#include "kernels_packed.cuh"      // packed-symmetric storage

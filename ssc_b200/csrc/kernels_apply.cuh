@@ -1,0 +1,110 @@
+// The fused apply kernels (K3+K4+K5), general storage.
+#pragma once
+#include "kernels_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// K3+K4+K5 apply: gather -> stored-inverse product -> scatter-add, fused (ssc/libssc.c:1359-1386).
+// `ppb` patches per CTA, `tp` threads per patch (tp >= n except for very large patches, where a thread
+// owns several rows).  The residual entries of a patch are gathered into shared memory (one index load and
+// one x load per patch dof), then thread i streams column i of S with evict-first loads and adds its
+// result into y with one fp64 reduction (RED.E.ADD.F64 at L2).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+ssc_apply_kernel(const double *__restrict__ S, ll stride, int ld, const int *__restrict__ gtol, int n, ll count, int tp, int ppb,
+                 const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
+                 const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
+{
+    extern __shared__ __align__(16) double xs_all[];
+    const int lp = threadIdx.x / tp, t = threadIdx.x - lp * tp;
+    const ll p = (ll)blockIdx.x * ppb + lp;
+    const bool active = lp < ppb && p < count;
+    double *xs = xs_all + (size_t)lp * n;
+    const int *g = gtol + p * n;
+    if (active) for (int i = t; i < n; i += tp) xs[i] = gather_x(x, g[i], ps);
+    __syncthreads();
+    if (!active) return;
+    const double sc = mult ? scale * mult[p] : scale;
+    for (int i = t; i < n; i += tp) {
+        const double *M = S + p * stride + i;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int j = 0;
+#pragma unroll 1
+        for (; j + 8 <= n; j += 8) {
+            const double m0 = __ldcs(M + (ll)(j + 0) * ld), m1 = __ldcs(M + (ll)(j + 1) * ld);
+            const double m2 = __ldcs(M + (ll)(j + 2) * ld), m3 = __ldcs(M + (ll)(j + 3) * ld);
+            const double m4 = __ldcs(M + (ll)(j + 4) * ld), m5 = __ldcs(M + (ll)(j + 5) * ld);
+            const double m6 = __ldcs(M + (ll)(j + 6) * ld), m7 = __ldcs(M + (ll)(j + 7) * ld);
+            a0 = fma(m0, xs[j + 0], a0); a1 = fma(m1, xs[j + 1], a1); a2 = fma(m2, xs[j + 2], a2); a3 = fma(m3, xs[j + 3], a3);
+            a0 = fma(m4, xs[j + 4], a0); a1 = fma(m5, xs[j + 5], a1); a2 = fma(m6, xs[j + 6], a2); a3 = fma(m7, xs[j + 7], a3);
+        }
+        for (; j < n; ++j) a0 = fma(__ldcs(M + (ll)j * ld), xs[j], a0);
+        emit(y, g[i], ((a0 + a1) + (a2 + a3)) * sc, ps, ypatch, p * n + i);
+    }
+}
+
+// Software-pipelined variants: the next group of kU column loads is already in flight while the current group is
+// consumed, so a thread always has kU..2*kU loads outstanding (the v0 loop drains its loads every iteration).
+// kVec = 1: thread i owns row i (LDG.64).  kVec = 2: thread t owns rows 2t and 2t+1 and loads them with one
+// 16-byte LDG.128; the row stride ld is even so every such load is aligned.
+template <int kVec> struct VecT;
+template <> struct VecT<1> { typedef double T; };
+template <> struct VecT<2> { typedef double2 T; };
+__device__ __forceinline__ void fma_vec(double m, double xv, double &a0, double &) { a0 = fma(m, xv, a0); }
+__device__ __forceinline__ void fma_vec(double2 m, double xv, double &a0, double &a1) { a0 = fma(m.x, xv, a0); a1 = fma(m.y, xv, a1); }
+
+template <int kVec, int kU>
+__global__ void __launch_bounds__(256)
+ssc_apply_pipe_kernel(const double *__restrict__ S, ll stride, int ld, const int *__restrict__ gtol, int n, ll count, int tp, int ppb,
+                      const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
+                      const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
+{
+    typedef typename VecT<kVec>::T T;
+    extern __shared__ __align__(16) double xs_all[];
+    const int lp = threadIdx.x / tp, t = threadIdx.x - lp * tp;
+    const ll p = (ll)blockIdx.x * ppb + lp;
+    const bool active = lp < ppb && p < count;
+    double *xs = xs_all + (size_t)lp * n;
+    const int *g = gtol + p * n;
+    if (active) for (int i = t; i < n; i += tp) xs[i] = gather_x(x, g[i], ps);
+    __syncthreads();
+    if (!active) return;
+    const double sc = mult ? scale * mult[p] : scale;
+    const int ngroups = n / kU;
+    const ll ldv = ld / kVec;                         // row stride in units of T
+    for (int i = t * kVec; i < n; i += tp * kVec) {
+        const T *M = reinterpret_cast<const T *>(S + p * stride + i);
+        T A[kU], B[kU];
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        if (ngroups > 0) {
+#pragma unroll
+            for (int u = 0; u < kU; ++u) A[u] = __ldcs(M + (ll)u * ldv);
+        }
+        for (int gi = 0; gi < ngroups; gi += 2) {
+            const int j = gi * kU;
+            const bool hasB = gi + 1 < ngroups, hasA = gi + 2 < ngroups;
+            if (hasB) {
+#pragma unroll
+                for (int u = 0; u < kU; ++u) B[u] = __ldcs(M + (ll)(j + kU + u) * ldv);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; u += 2) {
+                fma_vec(A[u], xs[j + u], a0, a1);
+                fma_vec(A[u + 1], xs[j + u + 1], b0, b1);
+            }
+            if (hasA) {
+#pragma unroll
+                for (int u = 0; u < kU; ++u) A[u] = __ldcs(M + (ll)(j + 2 * kU + u) * ldv);
+            }
+            if (hasB) {
+#pragma unroll
+                for (int u = 0; u < kU; u += 2) {
+                    fma_vec(B[u], xs[j + kU + u], a0, a1);
+                    fma_vec(B[u + 1], xs[j + kU + u + 1], b0, b1);
+                }
+            }
+        }
+        for (int j = ngroups * kU; j < n; ++j) fma_vec(__ldcs(M + (ll)j * ldv), xs[j], a0, a1);
+        emit(y, g[i], (a0 + b0) * sc, ps, ypatch, p * n + i);
+        if (kVec == 2 && i + 1 < n) emit(y, g[i + 1], (a1 + b1) * sc, ps, ypatch, p * n + i + 1);
+    }
+}

@@ -1,0 +1,309 @@
+// Packed-symmetric storage: pack kernel and the TMA bulk-copy apply kernels.
+#pragma once
+#include "kernels_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// Packed-symmetric storage (-ssc_symmetric_storage, SPD blocks with -sub_pc_type cholesky): the inverse of an SPD
+// block is symmetric, so only its lower triangle is kept, column by column: L[colstart(j) + (i - j)] = S[i][j], i >= j,
+// colstart(j) = j n - j (j - 1) / 2.  Half the bytes of the general layout (own roofline line: SURVEY.md 8d).
+// The apply kernel brings the whole triangle of a patch into shared memory with ONE bulk asynchronous copy (TMA,
+// cp.async.bulk + mbarrier: SASS UBLKCP), several CTAs per SM keep ~190 KB in flight, and thread i then does
+//   y_i = sum_{j <= i} L[i][j] x_j  (row pass, conflict-free)  +  sum_{k > i} L[k][i] x_k  (column pass)
+// -- n multiply-adds per thread whatever i is.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// the two halves of y_i for the packed layout, four independent loads in flight each
+__device__ __forceinline__ double sym_row_pass(const double *__restrict__ L, const double *__restrict__ xs, int n, int i)
+{
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int cs = i, j = 0;                                   // L[i][j] sits at colstart(j) + (i - j); +(n - j - 1) per column
+    for (; j + 3 <= i; j += 4) {
+        const int c1 = cs + (n - j) - 1, c2 = c1 + (n - j) - 2, c3 = c2 + (n - j) - 3;
+        const double l0 = L[cs], l1 = L[c1], l2 = L[c2], l3 = L[c3];
+        a0 = fma(l0, xs[j], a0); a1 = fma(l1, xs[j + 1], a1); a2 = fma(l2, xs[j + 2], a2); a3 = fma(l3, xs[j + 3], a3);
+        cs = c3 + (n - j) - 4;
+    }
+    for (; j <= i; ++j) { a0 = fma(L[cs], xs[j], a0); cs += (n - j) - 1; }
+    return (a0 + a1) + (a2 + a3);
+}
+__device__ __forceinline__ double sym_col_pass(const double *__restrict__ L, const double *__restrict__ xs, int n, int i)
+{
+    const double *col = L + ((ll)i * n - (ll)i * (i - 1) / 2) - i;      // L[k][i] = col[k], k > i
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int kk = i + 1;
+    for (; kk + 3 < n; kk += 4) {
+        a0 = fma(col[kk], xs[kk], a0); a1 = fma(col[kk + 1], xs[kk + 1], a1);
+        a2 = fma(col[kk + 2], xs[kk + 2], a2); a3 = fma(col[kk + 3], xs[kk + 3], a3);
+    }
+    for (; kk < n; ++kk) a0 = fma(col[kk], xs[kk], a0);
+    return (a0 + a1) + (a2 + a3);
+}
+
+// sum over m = q (mod F), mlo <= m < mhi, of L[colstart(min(i, m)) + |i - m|] * x_m  -- one thread's share of y_i when F
+// threads split a row.  Indices advance incrementally: in the row part (m <= i) the step from m to m + F is
+// F (n - m - 1) - F (F - 1) / 2 and shrinks by F^2 each time; in the column part (m > i) it is F.
+__device__ __forceinline__ double sym_terms(const double *__restrict__ L, const double *__restrict__ xs, int n, int i, int q, int F, int mlo, int mhi)
+{
+    double a0 = 0.0, a1 = 0.0;
+    int m = mlo + ((q - mlo) % F + F) % F;
+    const int rend = min(mhi, i + 1);
+    if (m < rend) {
+        int idx = m * n - ((m * (m - 1)) >> 1) + (i - m);
+        int step = F * (n - m - 1) - ((F * (F - 1)) >> 1);
+        const int dstep = F * F;
+        for (; m + F < rend; m += 2 * F) {
+            const double l0 = L[idx];
+            const int idx1 = idx + step;
+            const double l1 = L[idx1];
+            a0 = fma(l0, xs[m], a0);
+            a1 = fma(l1, xs[m + F], a1);
+            idx = idx1 + step - dstep;
+            step -= 2 * dstep;
+        }
+        if (m < rend) { a0 = fma(L[idx], xs[m], a0); m += F; }
+    }
+    // column part: first m > i (and >= mlo) in this thread's residue class
+    if (m <= i) m += ((i - m) / F + 1) * F;
+    const double *col = L + (i * n - ((i * (i - 1)) >> 1) - i);
+    for (; m + F < mhi; m += 2 * F) { a0 = fma(col[m], xs[m], a0); a1 = fma(col[m + F], xs[m + F], a1); }
+    if (m < mhi) a0 = fma(col[m], xs[m], a0);
+    return a0 + a1;
+}
+
+__global__ void ssc_pack_sym_kernel(const double *__restrict__ blocks, int n, int ld, ll stride, double *__restrict__ packed, ll pstride, ll count)
+{
+    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
+        const double *S = blocks + p * stride;
+        double *L = packed + p * pstride;
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+            const int j = e / n, i = e - j * n;                          // S[j*ld + i] = inverse[i][j]; consecutive threads -> consecutive i
+            if (i >= j) L[(ll)j * n - (ll)j * (j - 1) / 2 + (i - j)] = 0.5 * (S[(ll)j * ld + i] + S[(ll)i * ld + j]);
+        }
+    }
+}
+
+// kBulk = true: one TMA bulk copy per patch (UBLKCP + mbarrier), the default.  kBulk = false: every thread issues 16-byte
+// cp.async copies (LDGSTS) -- measured slower on B200 (4.46 ms against 3.24 ms at 64^3 Q3, profiles/README.md).
+template <bool kBulk>
+__global__ void __launch_bounds__(1024)
+ssc_apply_sym_kernel(const double *__restrict__ packed, ll pstride, unsigned copy_bytes, const int *__restrict__ gtol, int n, ll count,
+                     const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
+                     const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *L = reinterpret_cast<double *>(smem_raw);
+    double *xs = L + (copy_bytes >> 3);
+    __shared__ __align__(8) unsigned long long bar;
+    const ll p = blockIdx.x;
+    const int t = threadIdx.x;
+    if (kBulk) {
+        if (t == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (t == 0) {
+            mbar_expect_tx(&bar, copy_bytes);
+            bulk_copy_g2s(L, packed + p * pstride, copy_bytes, &bar);
+        }
+    } else {
+        const char *src = reinterpret_cast<const char *>(packed + p * pstride);
+        const unsigned dst = smem_u32(L);
+        for (unsigned off = 16u * t; off < copy_bytes; off += 16u * blockDim.x)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const int *g = gtol + p * n;
+    for (int i = t; i < n; i += blockDim.x) xs[i] = gather_x(x, g[i], ps);
+    if (!kBulk) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (kBulk) mbar_wait(&bar, 0);
+    const double sc = mult ? scale * mult[p] : scale;
+    for (int i = t; i < n; i += blockDim.x)
+        emit(y, g[i], (sym_row_pass(L, xs, n, i) + sym_col_pass(L, xs, n, i)) * sc, ps, ypatch, p * n + i);
+}
+
+// Two-chunk, two-threads-per-row form of the packed apply (the default): the triangle arrives as two bulk copies split
+// at a column boundary j1 (about half the bytes each); everything that only needs columns < j1 is computed while the
+// second copy is still in flight, and the n terms of a row are shared by two threads.  With
+//   y_i = sum_m L[colstart(min(i, m)) + |i - m|] x_m
+// the terms available after the first chunk are exactly those with min(i, m) < j1.
+__global__ void __launch_bounds__(1024)
+ssc_apply_sym2_kernel(const double *__restrict__ packed, ll pstride, unsigned copy_bytes, int j1, unsigned bytes0, const int *__restrict__ gtol, int n,
+                      ll count, const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
+                      const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *L = reinterpret_cast<double *>(smem_raw);
+    double *xs = L + (copy_bytes >> 3);
+    double *ypart = xs + n;
+    __shared__ __align__(8) unsigned long long bar[2];
+    const ll p = blockIdx.x;
+    const int t = threadIdx.x;
+    const int rp = blockDim.x >> 1;                              // row slots; thread (i, q) = (t % rp, t / rp)
+    const unsigned bytes1 = copy_bytes - bytes0;
+    if (t == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0) {
+        const double *src = packed + p * pstride;
+        mbar_expect_tx(&bar[0], bytes0);
+        bulk_copy_g2s(L, src, bytes0, &bar[0]);
+        if (bytes1) {
+            mbar_expect_tx(&bar[1], bytes1);
+            bulk_copy_g2s(L + (bytes0 >> 3), src + (bytes0 >> 3), bytes1, &bar[1]);
+        }
+    }
+    const int *g = gtol + p * n;
+    for (int i = t; i < n; i += blockDim.x) xs[i] = gather_x(x, g[i], ps);
+    __syncthreads();
+    const int i = t < rp ? t : t - rp, q = t < rp ? 0 : 1;
+    const bool valid = i < n;
+    double a0 = 0.0, a1 = 0.0;
+    mbar_wait(&bar[0], 0);
+    if (valid) a0 = sym_terms(L, xs, n, i, q, 2, 0, i < j1 ? n : j1);          // everything with min(i, m) < j1
+    if (bytes1) {
+        mbar_wait(&bar[1], 0);
+        if (valid && i >= j1) a1 = sym_terms(L, xs, n, i, q, 2, j1, n);
+    }
+    if (q == 1 && valid) ypart[i] = a0 + a1;
+    __syncthreads();
+    if (q == 0 && valid) {
+        const double sc = mult ? scale * mult[p] : scale;
+        emit(y, g[i], (a0 + a1 + ypart[i]) * sc, ps, ypatch, p * n + i);
+    }
+}
+
+// Persistent form of the packed-symmetric apply: one CTA per SM walks its share of the patches with a ring of kStages
+// shared-memory buffers.  Thread 0 keeps kStages - 1 bulk copies (one whole packed triangle each) in flight while the
+// CTA multiplies the patch that has landed; the residual entries of the next patch are gathered into registers before
+// the current patch is computed, so neither the gather nor the scatter latency stalls the stream.
+__global__ void __launch_bounds__(1024, 1)
+ssc_apply_sym_persistent_kernel(const double *__restrict__ packed, ll pstride, unsigned copy_bytes, int stages, const int *__restrict__ gtol, int n, ll count,
+                                const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
+                                const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar[8];
+    const size_t stage_doubles = copy_bytes >> 3;
+    double *ring = reinterpret_cast<double *>(smem_raw);
+    double *xsbuf = ring + stage_doubles * stages;            // 2 x n
+    double *ypart = xsbuf + 2 * n;                             // (F - 1) x rp partial sums
+    const int rp = (n + 31) & ~31;                             // row slots per part
+    const int F = max(1, (int)blockDim.x / rp);                // threads per row
+    const int t = threadIdx.x;
+    const ll first = blockIdx.x, step = gridDim.x;
+    const ll mine = first < count ? (count - first + step - 1) / step : 0;
+    if (t == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0) {
+        for (int s = 0; s < stages - 1 && s < mine; ++s) {
+            mbar_expect_tx(&bar[s], copy_bytes);
+            bulk_copy_g2s(ring + stage_doubles * s, packed + (first + s * step) * pstride, copy_bytes, &bar[s]);
+        }
+    }
+    // residual of the first patch
+    if (mine > 0) for (int i = t; i < n; i += blockDim.x) xsbuf[i] = gather_x(x, gtol[first * n + i], ps);
+    __syncthreads();
+    for (ll k = 0; k < mine; ++k) {
+        const ll p = first + k * step;
+        const int s = (int)(k % stages);
+        const unsigned parity = (unsigned)((k / stages) & 1);
+        // keep the ring full: the stage freed at the end of the previous iteration takes patch k + stages - 1
+        if (t == 0 && k + stages - 1 < mine) {
+            const int sn = (int)((k + stages - 1) % stages);
+            mbar_expect_tx(&bar[sn], copy_bytes);
+            bulk_copy_g2s(ring + stage_doubles * sn, packed + (p + (stages - 1) * step) * pstride, copy_bytes, &bar[sn]);
+        }
+        const double *xs = xsbuf + (k & 1) * n;
+        double *xn = xsbuf + ((k + 1) & 1) * n;
+        // gather for the next patch into a register (rows beyond blockDim are fetched after the compute, rare)
+        const int *gn = gtol + (p + step) * n;
+        double xnext = 0.0;
+        const bool have_next = k + 1 < mine;
+        if (have_next && t < n) xnext = gather_x(x, gn[t], ps);
+        const int *g = gtol + p * n;
+        const double *L = ring + stage_doubles * s;
+        mbar_wait(&bar[s], parity);
+        const double sc = mult ? scale * mult[p] : scale;
+        {
+            // F threads per row; thread (i, q) adds the terms m = q, q + F, ... of
+            //   y_i = sum_m L[colstart(min(i, m)) + |i - m|] x_m        (the symmetric product on the packed triangle)
+            const int i = t % rp, q = t / rp;
+            double a0 = 0.0, a1 = 0.0;
+            if (i < n && q < F) {
+                a0 = sym_terms(L, xs, n, i, q, F, 0, n);
+                if (q > 0) ypart[(q - 1) * rp + i] = a0;
+            }
+            __syncthreads();
+            if (i < n && q == 0) {
+                double s = a0 + a1;
+                for (int qq = 1; qq < F; ++qq) s += ypart[(qq - 1) * rp + i];
+                emit(y, g[i], s * sc, ps, ypatch, p * n + i);
+            }
+        }
+        if (have_next) {
+            if (t < n) xn[t] = xnext;
+            for (int i = t + blockDim.x; i < n; i += blockDim.x) xn[i] = gather_x(x, gn[i], ps);
+        }
+        __syncthreads();          // stage s and xs are free again
+    }
+}
+
+// after the second neighbour barrier: fold what the neighbours added for this rank's interface dofs into y and clear it
+__global__ void ssc_peer_fold_kernel(ll n, const int *__restrict__ iface, double *__restrict__ yin, double *__restrict__ y)
+{
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) {
+        const int d = iface[i];
+        y[d] += yin[d];
+        yin[d] = 0.0;
+    }
+}
+
+// calibration: plain streaming read (sum) of a buffer, the read-only counterpart of the driver's copy-measured HBM peak
+__global__ void __launch_bounds__(256)
+ssc_stream_read_kernel(const double2 *__restrict__ a, ll n2, double *__restrict__ sink)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const ll stride = (ll)gridDim.x * blockDim.x;
+    ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n2; i += 4 * stride) {
+        const double2 v0 = __ldcs(a + i), v1 = __ldcs(a + i + stride), v2 = __ldcs(a + i + 2 * stride), v3 = __ldcs(a + i + 3 * stride);
+        s0 += v0.x + v0.y; s1 += v1.x + v1.y; s2 += v2.x + v2.y; s3 += v3.x + v3.y;
+    }
+    for (; i < n2; i += stride) { const double2 v = __ldcs(a + i); s0 += v.x + v.y; }
+    const double s = (s0 + s1) + (s2 + s3);
+    if (s == 1.2345678e300) sink[0] = s;          // keeps the loads alive without a store per thread
+}
