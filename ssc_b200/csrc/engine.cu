@@ -115,6 +115,7 @@ struct SSCPatchPC_s {
     int factor_tile = 4;          // register tiles of the n <= 128 factor kernel: 4 (8x4, default) or 8 (8x8, measured slower)
     int factor_ctas = 0;          // concurrent CTAs of the blocked factor kernel (0 = fill the SMs)
     int factor_panel = 16;        // panel width of the blocked factor kernel (16 or 32)
+    int factor_searchers = 1;     // blocked look-ahead kernel: searcher warps (1 or 2)
     bool factor_remap = true;     // blocked look-ahead kernel: keep the searcher's SM sub-partition nearly free of worker warps
     int factor_variant = -1;      // n <= 128: 0 shared-memory Gauss-Jordan, 1 register-resident, 2 + look-ahead pivot search, 3 blocked look-ahead;
                                   // -1 (default): 3 for 100 <= n <= 128 (one CTA per SM anyway), 1 below (many small CTAs per SM hide the latency)
@@ -481,6 +482,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
         return 0;
     }
     if (name == "ssc_factor_remap") return parse_bool(v, &pc->factor_remap);
+    if (name == "ssc_factor_searchers") { pc->factor_searchers = atoi(v); return 0; }
     if (name == "ssc_overlap_classes") return parse_bool(v, &pc->overlap_classes);
     if (name == "ssc_factor_panel") { pc->factor_panel = atoi(v); return 0; }
     if (name == "ssc_factor_ctas") { pc->factor_ctas = atoi(v); return 0; }
@@ -1222,10 +1224,16 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
         // blocked look-ahead Gauss-Jordan: panels of 5 columns, (n/8) x (n/5) worker threads + one searcher warp
         const int TC = (n + 4) / 5, TR = (n + 7) / 8;
         const int W = (TR * TC + 31) / 32 * 32;
-        const int remap = (W == 416 && pc->factor_remap) ? 1 : 0;
-        const int threads = remap ? 512 : W + 32;
-        if (pivot) ssc_invert_panel_kernel<true><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W, remap);
-        else ssc_invert_panel_kernel<false><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W, remap);
+        const int NS = pc->factor_searchers == 2 ? 2 : 1;
+        const int remap = (NS == 1 && W == 416 && pc->factor_remap) ? 1 : 0;
+        const int threads = remap ? 512 : W + 32 * NS;
+        if (NS == 2) {
+            if (pivot) ssc_invert_panel_kernel<true, 2><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W, 0);
+            else ssc_invert_panel_kernel<false, 2><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W, 0);
+        } else {
+            if (pivot) ssc_invert_panel_kernel<true, 1><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W, remap);
+            else ssc_invert_panel_kernel<false, 1><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W, remap);
+        }
     }
     else if (n <= 128 && fvar == 2) {
         // register-resident tiles with a look-ahead pivot search: (n/8) x (n/5) worker threads + one searcher warp

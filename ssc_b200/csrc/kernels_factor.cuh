@@ -458,7 +458,7 @@ ssc_invert_la_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll 
 // bytes apart: 8-way bank conflicts, which also starved the searcher's own shared-memory traffic)
 __device__ __forceinline__ int ppos(int i) { return ((((i >> 1) & 3) * 16 + (i >> 3)) << 1) | (i & 1); }
 
-template <bool kPivot>
+template <bool kPivot, int NS>
 __global__ void __launch_bounds__(512, 1)
 ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll count, int *__restrict__ fail_flags, int TR, int TC, int W, int remap)
 {
@@ -467,6 +467,8 @@ ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, 
     __shared__ __align__(16) double Rrow[2][PB][LDP];      // the raw pivot rows of a panel
     __shared__ __align__(16) double S[128][SR];            // the searcher's working panel, one row per matrix row
     __shared__ int s_prow[2][8];
+    __shared__ unsigned s_best[2][2][4];                   // two searcher warps: each warp's best candidate of a step (hi, lo, row)
+    __shared__ __align__(16) double s_prv[2][SR];          // ... and the pivot row handed over by its lane
     __shared__ int s_pj[32], s_pbw[32], s_np;
     __shared__ int perm[128], qinv[128];
     // remap (13 worker warps, 512 threads): warp 13 is the searcher and warps 5 and 9 -- the other two warps of its SM
@@ -493,14 +495,106 @@ ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, 
     }
     const bool searcher = remap ? wid == 13 : (int)threadIdx.x >= W;
     const int tid = remap ? ((wid - (wid > 5) - (wid > 9) - (wid > 13)) << 5) + lane : (int)threadIdx.x;   // logical thread: tiles, permutation arrays
-    const int all = W + 32;
+    const int all = W + 32 * NS;
     const int tc = tid / TR, tr = tid - tc * TR;
     const bool owner = !searcher && tc < TC;
     const int r0 = owner ? 8 * tr : 0, c0 = owner ? PB * tc : 0;
     const int gt = tc / PB, qt = tc - PB * gt;               // column-tile group of this thread, its panel column there
     for (ll p = blockIdx.x; p < count; p += gridDim.x) {
         double *B = blocks + p * stride;
-        if (searcher) {
+        if (searcher && NS == 2) {
+            // Two searcher warps: lane l of warp sw holds rows l + 32 sw and l + 32 sw + 64 of the panel (2 x 5
+            // values), so a step costs each warp half the instructions; the warps agree on the pivot through shared
+            // memory (s_best) and the lane that holds the pivot row hands it over (s_prv), one 64-thread barrier each.
+            const int sw = ((int)threadIdx.x - W) >> 5;
+            const int i0 = lane + 32 * sw, i1 = i0 + 64;
+            unsigned usedmask = (i0 >= n ? 1u : 0u) | (i1 >= n ? 2u : 0u);
+            for (int it = 0; it < NPE; ++it) {
+                const int j = s_pj[it], bw = s_pbw[it];
+                const int buf = it & 1, g = j / PB, w = j - PB * g;
+                nbar_sync(1, all);                                    // panel j is in Pcol[buf]
+                double x[2][PB];
+#pragma unroll
+                for (int c = 0; c < PB; ++c) {
+                    x[0][c] = (i0 < n && c < bw) ? Pcol[buf][c][ppos(i0)] : 0.0;
+                    x[1][c] = (i1 < n && c < bw) ? Pcol[buf][c][ppos(i1)] : 0.0;
+                }
+                int pl[PB];
+                bool bad = false;
+#pragma unroll
+                for (int t = 0; t < PB; ++t) {
+                    pl[t] = 0;
+                    if (t < bw && !bad) {
+                        int prow = PB * (PB * g + t) + w;            // unpivoted: the diagonal entry of this column
+                        if (kPivot) {
+                            const unsigned h0 = (unsigned)__double2hiint(x[0][t]) & 0x7fffffffu, l0 = (unsigned)__double2loint(x[0][t]);
+                            const unsigned h1 = (unsigned)__double2hiint(x[1][t]) & 0x7fffffffu, l1 = (unsigned)__double2loint(x[1][t]);
+                            const bool ok0 = !(usedmask & 1u) && (h0 | l0) != 0u, ok1 = !(usedmask & 2u) && (h1 | l1) != 0u;
+                            const bool take1 = ok1 && (!ok0 || h1 > h0 || (h1 == h0 && l1 > l0));      // ties keep the lower row
+                            const bool have = ok0 || ok1;
+                            const unsigned bh = take1 ? h1 : h0, bl = take1 ? l1 : l0;
+                            const unsigned bi = take1 ? (unsigned)i1 : (unsigned)i0;
+                            const unsigned mh = __reduce_max_sync(0xffffffffu, have ? bh : 0u);
+                            const bool in1 = have && bh == mh;
+                            const unsigned ml = __reduce_max_sync(0xffffffffu, in1 ? bl : 0u);
+                            const unsigned mr = __reduce_min_sync(0xffffffffu, (in1 && bl == ml) ? bi : 0x7fffffffu);
+                            if (lane == 0) { s_best[t & 1][sw][0] = mh; s_best[t & 1][sw][1] = ml; s_best[t & 1][sw][2] = mr; }
+                            nbar_sync(4, 64);
+                            const unsigned ah = s_best[t & 1][0][0], al = s_best[t & 1][0][1], ar = s_best[t & 1][0][2];
+                            const unsigned bh2 = s_best[t & 1][1][0], bl2 = s_best[t & 1][1][1], br = s_best[t & 1][1][2];
+                            const bool av = ar < 0x7fffffffu, bv = br < 0x7fffffffu;
+                            const bool takeb = bv && (!av || bh2 > ah || (bh2 == ah && (bl2 > al || (bl2 == al && br < ar))));
+                            prow = (int)(takeb ? br : ar);
+                        }
+                        if (prow >= n) bad = true;
+                        else {
+                            const bool mine = (prow & 63) == i0;     // rows i0 and i0 + 64 live in this lane
+                            const int slot = prow >> 6;
+                            if (mine) {
+                                double2 *row = reinterpret_cast<double2 *>(&s_prv[t & 1][0]);
+                                row[0] = make_double2(slot ? x[1][0] : x[0][0], slot ? x[1][1] : x[0][1]);
+                                row[1] = make_double2(slot ? x[1][2] : x[0][2], slot ? x[1][3] : x[0][3]);
+                                s_prv[t & 1][4] = slot ? x[1][4] : x[0][4];
+                                usedmask |= 1u << slot;
+                            }
+                            nbar_sync(4, 64);
+                            const double2 *prw = reinterpret_cast<const double2 *>(&s_prv[t & 1][0]);
+                            const double2 p01 = prw[0], p23 = prw[1];
+                            const double pr[PB] = {p01.x, p01.y, p23.x, p23.y, s_prv[t & 1][4]};
+                            const double d = pr[t];
+                            if (!(fabs(d) > 0.0) || (!kPivot && !(d > 0.0))) bad = true;
+                            const double dinv = __drcp_rn(d);        // correctly rounded, = 1.0 / d
+                            double rr[PB];
+#pragma unroll
+                            for (int c = 0; c < PB; ++c) rr[c] = (c == t) ? dinv : pr[c] * dinv;
+#pragma unroll
+                            for (int s = 0; s < 2; ++s) {
+                                const bool isp = mine && slot == s;
+                                const double mlt = -x[s][t];
+#pragma unroll
+                                for (int c = 0; c < PB; ++c) {
+                                    const double u = (c == t) ? mlt * dinv : fma(mlt, rr[c], x[s][c]);
+                                    x[s][c] = isp ? rr[c] : u;
+                                }
+                            }
+                            pl[t] = prow;
+                        }
+                    }
+                }
+                // (T - I)[:, P]: take the unit entries of the pivot rows out again
+#pragma unroll
+                for (int c = 0; c < PB; ++c) {
+                    if (i0 < n && c < bw) Pcol[buf][c][ppos(i0)] = x[0][c] - ((i0 == pl[c]) ? 1.0 : 0.0);
+                    if (i1 < n && c < bw) Pcol[buf][c][ppos(i1)] = x[1][c] - ((i1 == pl[c]) ? 1.0 : 0.0);
+                }
+                if (sw == 0 && lane == 0) {
+#pragma unroll
+                    for (int t = 0; t < PB; ++t) { s_prow[buf][t] = bad ? -1 : pl[t]; if (t < bw) perm[PB * (PB * g + t) + w] = bad ? PB * (PB * g + t) + w : pl[t]; }
+                }
+                nbar_arrive(2, all);                                  // orders the stores above for the waiting workers
+                if (bad) break;
+            }
+        } else if (searcher) {
             unsigned usedmask = 0;      // bit s of lane l <-> row l + 32 s has been a pivot row (rows >= n count as used)
 #pragma unroll
             for (int s = 0; s < 4; ++s) if (lane + 32 * s >= n) usedmask |= 1u << s;
