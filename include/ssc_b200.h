@@ -127,6 +127,12 @@ int SSCPatchSetOperatorCSR(SSCPatchPC pc, SSCInt nrows, const SSCInt *rowptr, co
  * SSCPatchSetPatches); multiplicative sweeps need the assembled operator instead. */
 int SSCPatchSetElementMatrices(SSCPatchPC pc, SSCInt ncells, SSCInt dofs_per_cell, const double *Ke, SSCInt cell_stride, int memspace);
 
+/* The arrays handed to SSCPatchSetOperatorCSR / SSCPatchSetElementMatrices are borrowed, like the data behind the
+ * reference's compute-operator callback (ssc/PatchPC.pyx:158-163 keeps the Python objects alive, nothing is copied).
+ * This call tells the library they are gone: device copies of the last SSCPatchSetUp stay usable, a further
+ * SSCPatchSetUp fails with a wrong-state error until an operator is set again. */
+int SSCPatchReleaseOperator(SSCPatchPC pc);
+
 /* ---- setup and apply ----------------------------------------------------------------------- */
 int SSCPatchSetUp(SSCPatchPC pc);                         /* PCSetUp_PATCH ssc/libssc.c:1201-1299 (+ the lazy factorisation inside :1374) */
 /* PCApply_PATCH ssc/libssc.c:1301-1426: y = sum_p R_p^T B_p^{-1} R_p x on free dofs, y = x on owned Dirichlet dofs,

@@ -48,6 +48,7 @@ _sigs = {
     "SSCPatchPeerConnect": [_H, C.c_char_p, i32p, i64p, i64p],
     "SSCPatchSetOperatorCSR": [_H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
     "SSCPatchSetElementMatrices": [_H, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int],
+    "SSCPatchReleaseOperator": [_H],
     "SSCPatchSetUp": [_H],
     "SSCPatchApply": [_H, C.c_void_p, C.c_void_p, C.c_int],
     "SSCPatchApplyTranspose": [_H, C.c_void_p, C.c_void_p, C.c_int],

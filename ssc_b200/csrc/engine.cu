@@ -155,6 +155,7 @@ struct SSCPatchPC_s {
     const double *csr_vals = nullptr;
     int csr_space = SSC_MEM_HOST;
     bool csr_set = false;
+    bool op_released = false;        // the caller took the borrowed operator arrays back (SSCPatchReleaseOperator)
     // device state
     bool device_ready = false, setup_done = false;
     std::vector<SizeClass> classes;
@@ -652,7 +653,7 @@ extern "C" int SSCPatchSetOperatorCSR(SSCPatchPC pc, SSCInt nrows, const SSCInt 
     if (!rowptr || !colidx || !vals) return ssc_set_error(SSC_ERR_ARG_NULL, "null CSR array");
     pc->csr_nrows = nrows; pc->csr_rowptr = rowptr; pc->csr_colidx = colidx; pc->csr_vals = vals;
     pc->csr_space = memspace; pc->csr_set = true;
-    pc->elem_set = false;
+    pc->elem_set = false; pc->op_released = false;
     return 0;
 }
 
@@ -666,7 +667,17 @@ extern "C" int SSCPatchSetElementMatrices(SSCPatchPC pc, SSCInt ncells, SSCInt d
     if (cell_stride != 0 && cell_stride < dofs_per_cell * dofs_per_cell) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "cell stride %lld is smaller than one %lld x %lld matrix (0 = one matrix shared by all cells)", (long long)cell_stride, (long long)dofs_per_cell, (long long)dofs_per_cell);
     pc->elem_K = Ke; pc->elem_ncells = ncells; pc->elem_t = dofs_per_cell; pc->elem_stride = cell_stride; pc->elem_space = memspace;
     pc->elem_set = true;
-    pc->csr_set = false;
+    pc->csr_set = false; pc->op_released = false;
+    return 0;
+}
+
+// The operator arrays are only borrowed (ssc/libssc.c never owns the callback's data either): the caller announces that they
+// are gone.  Device copies made by the last SSCPatchSetUp stay; a further SSCPatchSetUp needs a new operator first.
+extern "C" int SSCPatchReleaseOperator(SSCPatchPC pc)
+{
+    if (!pc) return ssc_set_error(SSC_ERR_ARG_NULL, "null PC");
+    pc->op_released = true;
+    pc->csr_rowptr = nullptr; pc->csr_colidx = nullptr; pc->csr_vals = nullptr; pc->elem_K = nullptr;
     return 0;
 }
 
@@ -1087,7 +1098,11 @@ static int upload_elements(PC *pc)
     return 0;
 }
 
-static int upload_operator(PC *pc) { return pc->elem_set ? upload_elements(pc) : upload_csr(pc); }
+static int upload_operator(PC *pc)
+{
+    if (pc->op_released) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "the operator arrays were released (SSCPatchReleaseOperator): set the operator again before SSCPatchSetUp()");
+    return pc->elem_set ? upload_elements(pc) : upload_csr(pc);
+}
 
 // cells of every patch in size-sorted order + the cell-node maps: what the assemble kernel turns into the `dofs` table on the fly
 static int upload_element_lists(PC *pc)

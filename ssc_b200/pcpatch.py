@@ -261,6 +261,7 @@ class PC(object):
         """Drop the host CSR arrays kept alive for the library (they are only borrowed until setUp returns)."""
         self._csr_keep = None
         self._core.releaseOperator()
+        CHKERR(lib.SSCPatchReleaseOperator(self.handle))
 
     # ---- setup / apply ---------------------------------------------------------------------
     def setUp(self):

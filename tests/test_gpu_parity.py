@@ -443,3 +443,30 @@ def test_p_sweep_on_triangles(p):
     pc.apply(x, y)
     # equispaced Lagrange bases get ill-conditioned with p: the bound is the tolerance of north_star up to p = 6
     assert relerr(y, o.apply(x)) < (1e-12 if p <= 6 else 1e-10)
+
+
+def test_released_operator_cannot_be_set_up_again():
+    """The operator arrays are borrowed; after releaseOperator a further setUp must fail cleanly (wrong state), and
+    work again once an operator is set."""
+    from ssc_b200 import SSCError
+    form, bcs, disc, A = _problem(plex.TensorPlex((3, 3, 3)), 2, "scalar")
+    pc = make_gpu(form, bcs)
+    pc._compute_op = None
+    pc.setOperatorCSR(A.indptr, A.indices, A.data)
+    pc.setUp()
+    x = rhs_vector(disc.total_dofs)
+    y = np.zeros_like(x)
+    pc.apply(x, y)
+    pc.P = None
+    pc.releaseOperator()
+    y2 = np.zeros_like(x)
+    pc.apply(x, y2)                           # the factors stay resident
+    assert np.array_equal(y, y2)
+    with pytest.raises(SSCError) as e:
+        pc.setUp()
+    assert e.value.ierr == 73
+    pc.setOperatorCSR(A.indptr, A.indices, 2.0 * A.data)
+    pc.setUp()
+    pc.apply(x, y2)
+    free = np.setdiff1d(np.arange(x.size), disc.global_bc_nodes)
+    assert relerr(2.0 * y2[free], y[free]) < 1e-13
