@@ -42,3 +42,13 @@ def problem_type(request):
 def rhs_vector(n, seed=20260101):
     """i.i.d. uniform(-1, 1), numpy default_rng(20260101)."""
     return np.random.default_rng(seed).uniform(-1.0, 1.0, n)
+
+
+def delaunay_mesh(dim, npts, seed=3):
+    """Unstructured simplicial mesh (scipy Delaunay of random points): vertex valences vary, so the vertex-star patches
+    come in many sizes (the ragged case of SURVEY.md 8(d) C4)."""
+    from scipy.spatial import Delaunay
+    from ssc_b200 import plex
+    pts = np.random.default_rng(seed).uniform(0, 1, (npts, dim))
+    tri = Delaunay(pts)
+    return plex.simplex_plex(dim, tri.simplices.astype(np.int64), pts)

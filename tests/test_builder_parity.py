@@ -3,7 +3,7 @@ oracle's restatement of ssc/libssc.c:452-900: cells, gtol and the per-cell dofs 
 import numpy as np
 import pytest
 
-from conftest import meshes
+from conftest import delaunay_mesh, meshes
 from helpers import OPT_NAMES, make_oracle
 from ssc_b200 import PC, fem, plex
 from ssc_b200.patch import setup_patch_pc
@@ -118,3 +118,18 @@ def test_print_patches(capfd):
         art = set(map(int, lines[7].split())) if len(lines) > 7 and lines[7].strip() else set()
         assert art == seen - owned and gbc == seen & set(disc.ghost_bc_nodes.tolist())
         assert set(gtol[off[i]:off[i + 1]].tolist()) == owned - gbc
+
+
+@pytest.mark.parametrize("dim,npts,p,kind", [(2, 150, 3, "scalar"), (2, 90, 2, "mixed"), (3, 120, 2, "vector"), (3, 60, 3, "scalar")])
+def test_unstructured_delaunay_meshes(dim, npts, p, kind):
+    """Ragged patches: on a Delaunay mesh the vertex valence varies, so do the patch sizes (10-20 distinct ones)."""
+    o, pc = both(delaunay_mesh(dim, npts), p, kind)
+    assert_same(o, pc)
+    sizes = np.diff(pc.getPatches()[0])
+    assert np.unique(sizes[sizes > 0]).size >= 6
+
+
+def test_unstructured_vanka_and_edge_patches():
+    mesh = delaunay_mesh(2, 80, seed=5)
+    for opts in (dict(construct_type=1), dict(dim=1), dict(codim=0)):
+        assert_same(*both(mesh, 2, "mixed", **opts))
