@@ -461,7 +461,7 @@ def test_released_operator_cannot_be_set_up_again():
     pc.releaseOperator()
     y2 = np.zeros_like(x)
     pc.apply(x, y2)                           # the factors stay resident
-    assert np.array_equal(y, y2)
+    assert relerr(y2, y) < 1e-14               # (not bit-equal: the order of the fp64 atomics varies run to run)
     with pytest.raises(SSCError) as e:
         pc.setUp()
     assert e.value.ierr == 73
