@@ -461,7 +461,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_keep_dofs_table") return parse_bool(v, &pc->bopt.keep_dofs);
     if (name == "ssc_keep_patch_operators") return parse_bool(v, &pc->keep_operators);
     if (name == "ssc_builder_threads") { pc->bopt.nthreads = atoi(v); return 0; }
-    if (name == "ssc_factor_variant") { pc->factor_variant = atoi(v); if (pc->factor_variant < -1 || pc->factor_variant > 3) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "ssc_factor_variant must be -1 (automatic), 0, 1, 2 or 3"); return 0; }
+    if (name == "ssc_factor_variant") { pc->factor_variant = atoi(v); if (pc->factor_variant < -1 || pc->factor_variant > 4) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "ssc_factor_variant must be -1 (automatic) or 0..4"); return 0; }
     if (name == "ssc_symmetric_storage") {
         bool f = false;
         CHK(parse_bool(v, &f));
@@ -1234,6 +1234,15 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
         const int threads = std::max((TC * TC + 31) / 32 * 32, (n + 31) / 32 * 32);
         if (pivot) ssc_invert_reg8_kernel<true><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC);
         else ssc_invert_reg8_kernel<false><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TC);
+    }
+    else if (n <= 128 && fvar == 4) {
+        // blocked look-ahead Gauss-Jordan, searcher decoupled by two panels
+        const int TC = (n + 4) / 5, TR = (n + 7) / 8;
+        const int W = (TR * TC + 31) / 32 * 32;
+        const int remap = (W == 416 && pc->factor_remap) ? 1 : 0;
+        const int threads = remap ? 512 : W + 32;
+        if (pivot) ssc_invert_panel2_kernel<true><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W, remap);
+        else ssc_invert_panel2_kernel<false><<<grid_f, threads, 0, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail, TR, TC, W, remap);
     }
     else if (n <= 128 && fvar == 3) {
         // blocked look-ahead Gauss-Jordan: panels of 5 columns, (n/8) x (n/5) worker threads + one searcher warp

@@ -821,6 +821,322 @@ ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, 
     }
 }
 
+// The blocked look-ahead kernel with the searcher decoupled by one more panel.  Above, the searcher can only start
+// panel j + 1 after the workers have passed the pivot barrier of panel j, published the pivot rows and updated the
+// look-ahead columns: that front (~1/3 of the panel cycle) sits between two panel factorisations.  Here the workers
+// publish the columns of panel j + 2 as they are after panel j, and the searcher applies panel j + 1 to them ITSELF
+// (it holds (T - I)[:, P] of panel j + 1 in registers and finds the pivot rows' entries in the published columns:
+// 100 FMAs per lane) before it factors them.  It therefore never waits for the workers' front, only for columns that
+// were published a whole panel earlier; barriers alternate between two ids by panel parity so that a barrier is never
+// arrived at twice within one phase.  Three panel buffers: M of panel j (workers reading), panel j + 1 (searcher),
+// panel j + 2 (being published).  Same elimination order, pivots and arithmetic per step as the kernel above.
+template <bool kPivot>
+__global__ void __launch_bounds__(512, 1)
+ssc_invert_panel2_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, ll count, int *__restrict__ fail_flags, int TR, int TC, int W, int remap)
+{
+    constexpr int PB = 5, LDP = 136, SR = 6;
+    __shared__ __align__(16) double Pcol[3][PB][LDP];      // panel columns: published by their owners, then (T - I)[:, P] from the searcher
+    __shared__ __align__(16) double Rrow[2][PB][LDP];      // the raw pivot rows of a panel
+    __shared__ __align__(16) double S[128][SR];            // the searcher's working panel, one row per matrix row
+    __shared__ int s_prow[2][8];
+    __shared__ int s_pg[32], s_pw[32], s_pbw[32], s_np;
+    __shared__ int perm[128], qinv[128];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        int cntp = 0;
+        for (int j = 0; j < PB * ((TC + PB - 1) / PB); ++j) {
+            const int g = j / PB, w = j - PB * g;
+            int bw = 0;
+            for (int q = 0; q < PB; ++q) bw += (PB * g + q < TC && PB * (PB * g + q) + w < n) ? 1 : 0;
+            if (bw) { s_pg[cntp] = g; s_pw[cntp] = w; s_pbw[cntp] = bw; ++cntp; }
+        }
+        s_np = cntp;
+    }
+    __syncthreads();
+    const int NPE = s_np;
+    if (remap && (wid == 5 || wid == 9)) {                   // see ssc_invert_panel_kernel
+        for (ll p = blockIdx.x; p < count; p += gridDim.x) __syncthreads();
+        return;
+    }
+    const bool searcher = remap ? wid == 13 : (int)threadIdx.x >= W;
+    const int tid = remap ? ((wid - (wid > 5) - (wid > 9) - (wid > 13)) << 5) + lane : (int)threadIdx.x;
+    const int all = W + 32;
+    const int tc = tid / TR, tr = tid - tc * TR;
+    const bool owner = !searcher && tc < TC;
+    const int r0 = owner ? 8 * tr : 0, c0 = owner ? PB * tc : 0;
+    const int gt = tc / PB, qt = tc - PB * gt;
+    const int rb = owner ? 2 * tr : 0;                       // ppos(8 tr + 2 h + e) = 2 tr + 32 h + e: this thread's row pairs inside a panel column
+    // barrier ids: 1 / 6 columns published (by parity of the panel they belong to), 2 / 5 pivots ready (parity of the panel), 3 pivot rows published
+    for (ll p = blockIdx.x; p < count; p += gridDim.x) {
+        double *B = blocks + p * stride;
+        if (searcher) {
+            unsigned usedmask = 0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) if (lane + 32 * s >= n) usedmask |= 1u << s;
+            double mprev[4][PB];                               // (T - I)[:, P] of the previous panel, this lane's rows
+            int plprev[PB], bwprev = 0;
+#pragma unroll
+            for (int t = 0; t < PB; ++t) plprev[t] = 0;
+            nbar_sync(1, all);                                    // the columns of the first two panels are there
+            for (int it = 0; it < NPE; ++it) {
+                const int bw = s_pbw[it], g = s_pg[it], w = s_pw[it];
+                const int b3 = it % 3;
+                if (it >= 2) nbar_sync((it & 1) ? 6 : 1, all);    // panel `it` was published (as of panel it - 2)
+                double x[4][PB];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int i = lane + 32 * s;
+#pragma unroll
+                    for (int c = 0; c < PB; ++c) x[s][c] = (i < n && c < bw) ? Pcol[b3][c][ppos(i)] : 0.0;
+                }
+                if (it >= 1) {
+                    // the previous panel applied to these columns: x += (T - I)[:, P_prev] * (rows P_prev of the published columns)
+#pragma unroll
+                    for (int t = 0; t < PB; ++t) {
+                        if (t < bwprev) {
+                            const int pp = ppos(plprev[t]);
+#pragma unroll
+                            for (int c = 0; c < PB; ++c) {
+                                const double rv = c < bw ? Pcol[b3][c][pp] : 0.0;
+#pragma unroll
+                                for (int s = 0; s < 4; ++s) x[s][c] = fma(mprev[s][t], rv, x[s][c]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    double2 *row = reinterpret_cast<double2 *>(&S[lane + 32 * s][0]);
+                    row[0] = make_double2(x[s][0], x[s][1]); row[1] = make_double2(x[s][2], x[s][3]); S[lane + 32 * s][4] = x[s][4];
+                }
+                __syncwarp();
+                int pl[PB];
+                bool bad = false;
+#pragma unroll
+                for (int t = 0; t < PB; ++t) {
+                    pl[t] = 0;
+                    if (t < bw && !bad) {
+                        int prow = PB * (PB * g + t) + w;            // unpivoted: the diagonal entry of this column
+                        if (kPivot) {
+                            unsigned bh = 0u, bl = 0u;
+                            int bi = 1 << 30;
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) {
+                                const unsigned kh = (unsigned)__double2hiint(x[s][t]) & 0x7fffffffu, kl = (unsigned)__double2loint(x[s][t]);
+                                const bool better = !((usedmask >> s) & 1u) && (kh > bh || (kh == bh && kl > bl));
+                                if (better) { bh = kh; bl = kl; bi = lane + 32 * s; }
+                            }
+                            const bool have = bi < (1 << 30);
+                            const unsigned mh = __reduce_max_sync(0xffffffffu, have ? bh : 0u);
+                            const bool in1 = have && bh == mh;
+                            const unsigned ml = __reduce_max_sync(0xffffffffu, in1 ? bl : 0u);
+                            prow = (int)__reduce_min_sync(0xffffffffu, (in1 && bl == ml) ? (unsigned)bi : 0x7fffffffu);
+                        }
+                        if (prow >= n) bad = true;
+                        else {
+                            const double2 *prw = reinterpret_cast<const double2 *>(&S[prow][0]);
+                            const double2 p01 = prw[0], p23 = prw[1];
+                            const double pr[PB] = {p01.x, p01.y, p23.x, p23.y, S[prow][4]};
+                            const double d = pr[t];
+                            if (!(fabs(d) > 0.0) || (!kPivot && !(d > 0.0))) bad = true;
+                            const double dinv = __drcp_rn(d);        // correctly rounded, = 1.0 / d
+                            double rr[PB];
+#pragma unroll
+                            for (int c = 0; c < PB; ++c) rr[c] = (c == t) ? dinv : pr[c] * dinv;
+                            __syncwarp();                            // everybody has read the pivot row
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) {
+                                const int i = lane + 32 * s;
+                                const double mlt = -x[s][t];
+#pragma unroll
+                                for (int c = 0; c < PB; ++c) x[s][c] = (c == t) ? mlt * dinv : fma(mlt, rr[c], x[s][c]);
+                                double2 *row = reinterpret_cast<double2 *>(&S[i][0]);
+                                row[0] = make_double2(x[s][0], x[s][1]); row[1] = make_double2(x[s][2], x[s][3]); S[i][4] = x[s][4];
+                            }
+                            if ((prow & 31) == lane) {
+                                double2 *row = reinterpret_cast<double2 *>(&S[prow][0]);
+                                row[0] = make_double2(rr[0], rr[1]); row[1] = make_double2(rr[2], rr[3]); S[prow][4] = rr[4];
+                                usedmask |= 1u << (prow >> 5);
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) {
+                                const double2 *row = reinterpret_cast<const double2 *>(&S[lane + 32 * s][0]);
+                                const double2 a01 = row[0], a23 = row[1];
+                                x[s][0] = a01.x; x[s][1] = a01.y; x[s][2] = a23.x; x[s][3] = a23.y; x[s][4] = S[lane + 32 * s][4];
+                            }
+                            pl[t] = prow;
+                        }
+                    }
+                }
+                // (T - I)[:, P]: take the unit entries of the pivot rows out again; keep it for the next panel's columns
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int i = lane + 32 * s;
+#pragma unroll
+                    for (int c = 0; c < PB; ++c) {
+                        mprev[s][c] = (c < bw) ? x[s][c] - ((i == pl[c]) ? 1.0 : 0.0) : 0.0;
+                        if (i < n && c < bw) Pcol[b3][c][ppos(i)] = mprev[s][c];
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < PB; ++t) plprev[t] = pl[t];
+                bwprev = bw;
+                if (lane == 0) {
+#pragma unroll
+                    for (int t = 0; t < PB; ++t) { s_prow[it & 1][t] = bad ? -1 : pl[t]; if (t < bw) perm[PB * (PB * g + t) + w] = bad ? PB * (PB * g + t) + w : pl[t]; }
+                }
+                nbar_arrive((it & 1) ? 5 : 2, all);                // orders the stores above for the waiting workers
+                if (bad) {
+                    // the workers have already announced the columns of panel it + 1 (during panel it - 1): consume that
+                    // arrival so the barrier starts clean for the next block
+                    if (it >= 1 && it + 1 < NPE) nbar_sync(((it + 1) & 1) ? 6 : 1, all);
+                    break;
+                }
+            }
+        } else {
+            double a[8][PB];
+#pragma unroll
+            for (int c = 0; c < PB; ++c) {
+                const int j = c0 + c;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i = r0 + r;
+                    a[r][c] = (owner && i < n && j < n) ? B[(ll)j * ldg + i] : 0.0;      // transposed load: A = B^T
+                }
+            }
+            // the first two panels as they are
+#pragma unroll 1
+            for (int it = 0; it < 2 && it < NPE; ++it) {
+                const int g = s_pg[it], w = s_pw[it];
+                if (owner && gt == g) {
+#define PUT_COL(C) _Pragma("unroll") for (int h = 0; h < 4; ++h) *reinterpret_cast<double2 *>(&Pcol[it][qt][rb + 32 * h]) = make_double2(a[2 * h][C], a[2 * h + 1][C]);
+                    switch (w) {
+                    case 0: PUT_COL(0) break;
+                    case 1: PUT_COL(1) break;
+                    case 2: PUT_COL(2) break;
+                    case 3: PUT_COL(3) break;
+                    default: PUT_COL(4) break;
+                    }
+#undef PUT_COL
+                }
+            }
+            nbar_arrive(1, all);
+            int fail = 0;
+            for (int it = 0; it < NPE; ++it) {
+                const int bw = s_pbw[it], b3 = it % 3, b2 = it & 1, g = s_pg[it], w = s_pw[it];
+                const bool more = it + 2 < NPE;                        // the panel two ahead
+                const int bwn = more ? s_pbw[it + 2] : 0, gn = more ? s_pg[it + 2] : -1, wn = more ? s_pw[it + 2] : 0, bn3 = (it + 2) % 3;
+                nbar_sync(b2 ? 5 : 2, all);                           // the pivots of this panel are known
+                int pl[PB];
+#pragma unroll
+                for (int t = 0; t < PB; ++t) pl[t] = s_prow[b2][t];
+                if (pl[0] < 0) { fail = 1; break; }                   // no usable pivot: uniform across the CTA
+                const bool in_panel = owner && gt == g && qt < bw;
+                const int myprow = in_panel ? s_prow[b2][qt] : -1;    // read now: the searcher may reuse the slot two panels on
+#pragma unroll
+                for (int t = 0; t < PB; ++t) {
+                    if (t < bw && owner && tr == (pl[t] >> 3)) {
+#define PUBLISH_ROW(R) _Pragma("unroll") for (int c = 0; c < PB; ++c) Rrow[b2][t][c0 + c] = a[R][c];
+                        switch (pl[t] & 7) {
+                        case 0: PUBLISH_ROW(0) break;
+                        case 1: PUBLISH_ROW(1) break;
+                        case 2: PUBLISH_ROW(2) break;
+                        case 3: PUBLISH_ROW(3) break;
+                        case 4: PUBLISH_ROW(4) break;
+                        case 5: PUBLISH_ROW(5) break;
+                        case 6: PUBLISH_ROW(6) break;
+                        default: PUBLISH_ROW(7) break;
+                        }
+#undef PUBLISH_ROW
+                    }
+                }
+                nbar_sync(3, W);
+                const bool in_next = owner && more && gt == gn && qt < bwn;
+                // look-ahead: the columns of the panel two ahead first, then they go to the searcher
+                if (in_next) {
+#define EARLY_COL(C)                                                                                                    \
+    _Pragma("unroll") for (int t = 0; t < PB; ++t) {                                                                   \
+        if (t < bw) {                                                                                                   \
+            const double rvc = Rrow[b2][t][c0 + C];                                                                     \
+            _Pragma("unroll") for (int h = 0; h < 4; ++h) {                                                             \
+                const double2 q2 = *reinterpret_cast<const double2 *>(&Pcol[b3][t][rb + 32 * h]);                       \
+                a[2 * h][C] = fma(q2.x, rvc, a[2 * h][C]); a[2 * h + 1][C] = fma(q2.y, rvc, a[2 * h + 1][C]);           \
+            }                                                                                                           \
+        }                                                                                                               \
+    }                                                                                                                   \
+    _Pragma("unroll") for (int h = 0; h < 4; ++h) *reinterpret_cast<double2 *>(&Pcol[bn3][qt][rb + 32 * h]) = make_double2(a[2 * h][C], a[2 * h + 1][C]);
+                    switch (wn) {
+                    case 0: EARLY_COL(0) break;
+                    case 1: EARLY_COL(1) break;
+                    case 2: EARLY_COL(2) break;
+                    case 3: EARLY_COL(3) break;
+                    default: EARLY_COL(4) break;
+                    }
+#undef EARLY_COL
+                }
+                if (more) nbar_arrive(((it + 2) & 1) ? 6 : 1, all);
+                // branch-free: a column that must not be touched (this panel's own column: replaced below; the
+                // look-ahead column: done above) gets the multiplier 0, so all nine loads of a rank are issued
+                // together and the 40 FMAs follow back to back
+                const int skip1 = in_panel ? w : -1, skip2 = in_next ? wn : -1;
+                bool keep[PB];
+#pragma unroll
+                for (int c = 0; c < PB; ++c) keep[c] = c != skip1 && c != skip2;
+                if (owner) {
+#pragma unroll
+                    for (int t = 0; t < PB; ++t) {
+                        if (t < bw) {
+                            double cv[8], rv[PB];
+                            const double *pc_t = &Pcol[b3][t][rb];
+                            const double *rr_t = &Rrow[b2][t][c0];
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) { const double2 q = *reinterpret_cast<const double2 *>(pc_t + 32 * h); cv[2 * h] = q.x; cv[2 * h + 1] = q.y; }
+#pragma unroll
+                            for (int c = 0; c < PB; ++c) rv[c] = rr_t[c];
+#pragma unroll
+                            for (int c = 0; c < PB; ++c) {
+                                const double m = keep[c] ? rv[c] : 0.0;
+#pragma unroll
+                                for (int r = 0; r < 8; ++r) a[r][c] = fma(cv[r], m, a[r][c]);
+                            }
+                        }
+                    }
+                }
+                if (in_panel) {
+#define TAKE_COL(C) _Pragma("unroll") for (int r = 0; r < 8; ++r) a[r][C] = Pcol[b3][qt][rb + 32 * (r >> 1) + (r & 1)] + ((r0 + r == myprow) ? 1.0 : 0.0);
+                    switch (w) {
+                    case 0: TAKE_COL(0) break;
+                    case 1: TAKE_COL(1) break;
+                    case 2: TAKE_COL(2) break;
+                    case 3: TAKE_COL(3) break;
+                    default: TAKE_COL(4) break;
+                    }
+#undef TAKE_COL
+                }
+            }
+            if (!fail && tid < n) qinv[perm[tid]] = tid;       // perm is incomplete after a failure
+            nbar_sync(3, W);
+            if (tid == 0) fail_flags[p] = fail;
+            if (!fail && owner) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i = r0 + r;
+                    if (i < n) {
+                        const ll row = (ll)qinv[i] * ldg;
+#pragma unroll
+                        for (int c = 0; c < PB; ++c) {
+                            const int j2 = c0 + c;
+                            if (j2 < n) B[row + perm[j2]] = a[r][c];
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Same algorithm with 8 x 8 tiles: (n/8)^2 threads, 64 FMAs per thread and step against 16 shared-memory loads and
 // half as many warps repeating the pivot search -- the 8 x 4 form above is issue-bound on exactly that overhead.
 template <bool kPivot>

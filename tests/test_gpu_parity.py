@@ -159,7 +159,7 @@ def test_apply_kernel_variants(variant, shape, p, kind):
     assert np.array_equal(pc.getPatchMatrix(i), o.patchMatrix(i))
 
 
-@pytest.mark.parametrize("factor_variant", [0, 1, 2, 3, 14, 32])
+@pytest.mark.parametrize("factor_variant", [0, 1, 2, 3, 4, 14, 32])
 @pytest.mark.parametrize("n", [5, 33, 64, 100, 128, 150])
 def test_general_blocks_need_pivoting(n, factor_variant):
     """Non-symmetric operator with zero diagonal entries: -sub_pc_type lu must pivot.  Patches are arbitrary dof sets
@@ -207,7 +207,7 @@ def test_general_blocks_need_pivoting(n, factor_variant):
         assert np.abs(pc.getPatchMatrix(i, inverse=True) @ B - np.eye(l.size)).max() < 1e-8
 
 
-@pytest.mark.parametrize("factor_variant", [0, 1, 2, 3, 32])
+@pytest.mark.parametrize("factor_variant", [0, 1, 2, 3, 4, 32])
 def test_singular_block_is_reported(factor_variant):
     import scipy.sparse as sp
     from ssc_b200 import PC, SSCError
@@ -230,8 +230,8 @@ def test_factor_variants_agree(shape, p, sub_pc):
     the same pivots and do the same elimination steps: their inverses agree to rounding."""
     form, bcs, disc, A = _problem(plex.TensorPlex(shape), p, "scalar")
     inv = []
-    for variant in (0, 1, 2, 3, 32):
-        pc = make_gpu(form, bcs, ssc_factor_variant=min(variant, 3), ssc_factor_searchers=2 if variant == 32 else 1, sub_pc_type=sub_pc)
+    for variant in (0, 1, 2, 3, 4, 32):
+        pc = make_gpu(form, bcs, ssc_factor_variant=3 if variant == 32 else variant, ssc_factor_searchers=2 if variant == 32 else 1, sub_pc_type=sub_pc)
         pc.setUp()
         sizes = np.diff(pc.getPatches()[0])
         inv.append([pc.getPatchMatrix(int(i), inverse=True) for i in (np.argmax(sizes), np.argmin(np.where(sizes > 0, sizes, 1 << 30)), sizes.size // 2)])
