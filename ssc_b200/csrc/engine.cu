@@ -118,7 +118,8 @@ struct SSCPatchPC_s {
     int factor_searchers = 1;     // blocked look-ahead kernel: searcher warps (1 or 2)
     bool factor_remap = true;     // blocked look-ahead kernel: keep the searcher's SM sub-partition nearly free of worker warps
     int factor_variant = -1;      // n <= 128: 0 shared-memory Gauss-Jordan, 1 register-resident, 2 + look-ahead pivot search, 3 blocked look-ahead;
-                                  // -1 (default): 3 for 100 <= n <= 128 (one CTA per SM anyway), 1 below (many small CTAs per SM hide the latency)
+                                  // 4 blocked look-ahead with the searcher two panels ahead;
+                                  // -1 (default): for 100 <= n <= 128 (one CTA per SM anyway) 4 with pivoting (lu), 3 without (cholesky); 1 below (many small CTAs per SM hide the latency)
     int apply_variant = 1;        // 0: simple loop, 1: pipelined LDG.64, 2: pipelined LDG.128 (even row stride)
     std::string sub_mat_type, sub_ksp_type = "preonly";
     BuildOptions bopt;
@@ -1150,6 +1151,8 @@ static int upload_element_lists(PC *pc)
     return 0;
 }
 
+static inline bool pivot_wanted(const PC *pc) { return pc->sub_pc == SSC_SUB_LU; }
+
 static size_t invert_smem_bytes(int n, bool shared)
 {
     const size_t ld = (size_t)(n | 1);
@@ -1207,7 +1210,7 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
         if (smem_f > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_invert_kernel<P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
         ssc_invert_kernel<P, S><<<grid_f, bdf, smem_f, pc->stream>>>(blocks, n, c.ld, c.stride, cnt, fail);             \
     } while (0)
-    const int fvar = pc->factor_variant >= 0 ? pc->factor_variant : ((n >= 100 && n <= 128) ? 3 : 1);
+    const int fvar = pc->factor_variant >= 0 ? pc->factor_variant : ((n >= 100 && n <= 128) ? (pivot_wanted(pc) ? 4 : 3) : 1);
     if (n > 128 && fvar >= 1) {
         // blocked Gauss-Jordan with DMMA updates, block resident in L2
         const int npad = (n + 7) & ~7, WP = ((npad + 15) & ~15) + 4;

@@ -500,6 +500,7 @@ ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, 
     const bool owner = !searcher && tc < TC;
     const int r0 = owner ? 8 * tr : 0, c0 = owner ? PB * tc : 0;
     const int gt = tc / PB, qt = tc - PB * gt;               // column-tile group of this thread, its panel column there
+    const int rb = owner ? 2 * tr : 0;                       // ppos(8 tr + 2 h + e) = 2 tr + 32 h + e: this thread's row pairs inside a panel column
     for (ll p = blockIdx.x; p < count; p += gridDim.x) {
         double *B = blocks + p * stride;
         if (searcher && NS == 2) {
@@ -705,7 +706,7 @@ ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, 
             }
             if (owner && gt == 0) {
 #pragma unroll
-                for (int r = 0; r < 8; ++r) Pcol[0][qt][ppos(r0 + r)] = a[r][0];
+                for (int h = 0; h < 4; ++h) *reinterpret_cast<double2 *>(&Pcol[0][qt][rb + 32 * h]) = make_double2(a[2 * h][0], a[2 * h + 1][0]);
             }
             nbar_arrive(1, all);
             int fail = 0;
@@ -747,12 +748,12 @@ ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, 
         if (t < bw) {                                                                                                   \
             const double rvc = Rrow[buf][t][c0 + C];                                                                    \
             _Pragma("unroll") for (int h = 0; h < 4; ++h) {                                                             \
-                const double2 q2 = *reinterpret_cast<const double2 *>(&Pcol[buf][t][ppos(r0 + 2 * h)]);                 \
+                const double2 q2 = *reinterpret_cast<const double2 *>(&Pcol[buf][t][rb + 32 * h]);                      \
                 a[2 * h][C] = fma(q2.x, rvc, a[2 * h][C]); a[2 * h + 1][C] = fma(q2.y, rvc, a[2 * h + 1][C]);           \
             }                                                                                                           \
         }                                                                                                               \
     }                                                                                                                   \
-    _Pragma("unroll") for (int r = 0; r < 8; ++r) Pcol[buf ^ 1][qt][ppos(r0 + r)] = a[r][C];
+    _Pragma("unroll") for (int h = 0; h < 4; ++h) *reinterpret_cast<double2 *>(&Pcol[buf ^ 1][qt][rb + 32 * h]) = make_double2(a[2 * h][C], a[2 * h + 1][C]);
                     switch (wn) {
                     case 0: EARLY_COL(0) break;
                     case 1: EARLY_COL(1) break;
@@ -763,22 +764,29 @@ ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, 
 #undef EARLY_COL
                 }
                 if (more) nbar_arrive(1, all);
+                // branch-free: a column that must not be touched (this panel's own column: replaced below; the
+                // look-ahead column: done above) gets the multiplier 0, so all nine loads of a rank are issued
+                // together and the 40 FMAs follow back to back
                 const int skip1 = in_panel ? w : -1, skip2 = in_next ? wn : -1;
+                bool keep[PB];
+#pragma unroll
+                for (int c = 0; c < PB; ++c) keep[c] = c != skip1 && c != skip2;
                 if (owner) {
 #pragma unroll
                     for (int t = 0; t < PB; ++t) {
                         if (t < bw) {
                             double cv[8], rv[PB];
+                            const double *pc_t = &Pcol[buf][t][rb];
+                            const double *rr_t = &Rrow[buf][t][c0];
 #pragma unroll
-                            for (int h = 0; h < 4; ++h) { const double2 q = *reinterpret_cast<const double2 *>(&Pcol[buf][t][ppos(r0 + 2 * h)]); cv[2 * h] = q.x; cv[2 * h + 1] = q.y; }
+                            for (int h = 0; h < 4; ++h) { const double2 q = *reinterpret_cast<const double2 *>(pc_t + 32 * h); cv[2 * h] = q.x; cv[2 * h + 1] = q.y; }
 #pragma unroll
-                            for (int c = 0; c < PB; ++c) rv[c] = Rrow[buf][t][c0 + c];
+                            for (int c = 0; c < PB; ++c) rv[c] = rr_t[c];
 #pragma unroll
                             for (int c = 0; c < PB; ++c) {
-                                if (c != skip1 && c != skip2) {
+                                const double m = keep[c] ? rv[c] : 0.0;
 #pragma unroll
-                                    for (int r = 0; r < 8; ++r) a[r][c] = fma(cv[r], rv[c], a[r][c]);
-                                }
+                                for (int r = 0; r < 8; ++r) a[r][c] = fma(cv[r], m, a[r][c]);
                             }
                         }
                     }
@@ -786,7 +794,7 @@ ssc_invert_panel_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, 
                 if (in_panel) {
                     // this thread's column w is column qt of the panel: it receives T[:, P] = (T - I)[:, P] + unit entry
                     const int prow = s_prow[buf][qt];
-#define TAKE_COL(C) _Pragma("unroll") for (int r = 0; r < 8; ++r) a[r][C] = Pcol[buf][qt][ppos(r0 + r)] + ((r0 + r == prow) ? 1.0 : 0.0);
+#define TAKE_COL(C) _Pragma("unroll") for (int r = 0; r < 8; ++r) a[r][C] = Pcol[buf][qt][rb + 32 * (r >> 1) + (r & 1)] + ((r0 + r == prow) ? 1.0 : 0.0);
                     switch (w) {
                     case 0: TAKE_COL(0) break;
                     case 1: TAKE_COL(1) break;
