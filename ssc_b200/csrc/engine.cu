@@ -107,6 +107,7 @@ struct SSCPatchPC_s {
     cudaStream_t side_stream = nullptr, launch_stream = nullptr;   // the small size classes of an apply run beside the big one; launch_apply_class launches on launch_stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap_classes = true;
+    bool apply_stream_small = true;  // n <= 96: persistent apply kernel with the gathers prefetched across patches
     int sm_count = 148;
     // options (defaults: PCCreate_PATCH ssc/libssc.c:1697-1711)
     bool save_operators = true, partition_of_unity = false, multiplicative = false, print_patches = false;
@@ -486,6 +487,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_factor_remap") return parse_bool(v, &pc->factor_remap);
     if (name == "ssc_factor_searchers") { pc->factor_searchers = atoi(v); return 0; }
     if (name == "ssc_overlap_classes") return parse_bool(v, &pc->overlap_classes);
+    if (name == "ssc_apply_stream_small") return parse_bool(v, &pc->apply_stream_small);
     if (name == "ssc_factor_panel") { pc->factor_panel = atoi(v); return 0; }
     if (name == "ssc_factor_ctas") { pc->factor_ctas = atoi(v); return 0; }
     if (name == "ssc_factor_tile") { pc->factor_tile = atoi(v); return 0; }
@@ -1450,6 +1452,19 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
         K<<<(unsigned)grid, threads, smem, pc->launch_stream>>>(blocks, c.stride, c.ld, gt, c.n, cnt, c.tp, c.ppb, xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch); \
     } while (0)
+    if (pc->apply_variant == 1 && pc->apply_stream_small && c.n <= 96 && c.tp >= c.n && threads <= 256) {
+        // persistent, gathers prefetched one and two patches ahead: groups walk the list in lockstep
+        const int per_sm = std::max(1, 2048 / threads);
+        const i64 ctas = std::min<i64>(grid, (i64)pc->sm_count * per_sm);
+        if (grid >= 4 * ctas) {
+            const size_t smem2 = 2 * smem;
+            if (smem2 > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_apply_stream_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            ssc_apply_stream_kernel<8><<<(unsigned)ctas, threads, smem2, pc->launch_stream>>>(blocks, c.stride, c.ld, gt, c.n, cnt, c.tp, c.ppb, xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch);
+            pc->launches++;
+            CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+    }
     if (pc->apply_variant == 2 && threads <= 256) LAUNCH_APPLY((ssc_apply_pipe_kernel<2, 8>));
     else if (pc->apply_variant == 1 && threads <= 256) LAUNCH_APPLY((ssc_apply_pipe_kernel<1, 8>));
     else LAUNCH_APPLY(ssc_apply_kernel);

@@ -108,3 +108,73 @@ ssc_apply_pipe_kernel(const double *__restrict__ S, ll stride, int ld, const int
         if (kVec == 2 && i + 1 < n) emit(y, g[i + 1], (a1 + b1) * sc, ps, ypatch, p * n + i + 1);
     }
 }
+
+// Persistent form for small and mid-size patches (n <= 96): the groups of a CTA walk the patch list in lockstep, and
+// the two dependent gather loads of a patch (its dof index, then x at that index) are issued one and two patches ahead
+// of the patch being streamed -- index of patch it + 2 and x of patch it + 1 are in flight while patch `it` streams its
+// block -- so a group is never idle in a gather: with one patch per group and CTA (the kernels above) a 27-dof patch
+// spends about as long fetching its 27 indices and residual entries as streaming its 5.8 KB block
+// (0.67 of the measured HBM bandwidth at Q2 112^3, tools/gpu_apply_sizes.py).  tp >= n: thread t of a group owns row t.
+template <int kU>
+__global__ void __launch_bounds__(256)
+ssc_apply_stream_kernel(const double *__restrict__ S, ll stride, int ld, const int *__restrict__ gtol, int n, ll count, int tp, int ppb,
+                        const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
+                        const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
+{
+    extern __shared__ __align__(16) double xs_all[];          // [2][ppb][n]
+    const int lp = threadIdx.x / tp, t = threadIdx.x - lp * tp;
+    const ll ngr = (ll)gridDim.x * ppb;                        // groups in the grid
+    const ll first = (ll)blockIdx.x * ppb + lp;
+    const ll iters = (count + ngr - 1) / ngr;                  // the same for every group: the CTA stays in lockstep
+    const bool lane_ok = lp < ppb && t < n;
+    double *xs0 = xs_all + (size_t)lp * n, *xs1 = xs_all + (size_t)(ppb + lp) * n;
+    int g0 = -1, g1 = -1;
+    if (lane_ok && first < count) g0 = gtol[first * n + t];
+    if (lane_ok && first + ngr < count) g1 = gtol[(first + ngr) * n + t];
+    if (lane_ok) xs0[t] = g0 >= 0 ? gather_x(x, g0, ps) : 0.0;
+    __syncthreads();
+    const int ngroups = n / kU;
+    for (ll it = 0; it < iters; ++it) {
+        const ll p = first + it * ngr;
+        const double *xs = (it & 1) ? xs1 : xs0;
+        double *xn = (it & 1) ? xs0 : xs1;
+        // in flight while this patch streams: the index two patches ahead, the residual entry one patch ahead
+        int g2 = -1;
+        if (lane_ok && p + 2 * ngr < count) g2 = gtol[(p + 2 * ngr) * n + t];
+        double x1 = 0.0;
+        if (g1 >= 0) x1 = gather_x(x, g1, ps);
+        if (g0 >= 0) {
+            const double *M = S + p * stride + t;
+            double A[kU], B[kU];
+            double a0 = 0.0, b0 = 0.0;
+            if (ngroups > 0) {
+#pragma unroll
+                for (int u = 0; u < kU; ++u) A[u] = __ldcs(M + (ll)u * ld);
+            }
+            for (int gi = 0; gi < ngroups; gi += 2) {
+                const int j = gi * kU;
+                const bool hasB = gi + 1 < ngroups, hasA = gi + 2 < ngroups;
+                if (hasB) {
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) B[u] = __ldcs(M + (ll)(j + kU + u) * ld);
+                }
+#pragma unroll
+                for (int u = 0; u < kU; u += 2) { a0 = fma(A[u], xs[j + u], a0); b0 = fma(A[u + 1], xs[j + u + 1], b0); }
+                if (hasA) {
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) A[u] = __ldcs(M + (ll)(j + 2 * kU + u) * ld);
+                }
+                if (hasB) {
+#pragma unroll
+                    for (int u = 0; u < kU; u += 2) { a0 = fma(B[u], xs[j + kU + u], a0); b0 = fma(B[u + 1], xs[j + kU + u + 1], b0); }
+                }
+            }
+            for (int j = ngroups * kU; j < n; ++j) a0 = fma(__ldcs(M + (ll)j * ld), xs[j], a0);
+            const double sc = mult ? scale * mult[p] : scale;
+            emit(y, g0, (a0 + b0) * sc, ps, ypatch, p * n + t);
+        }
+        if (lane_ok) xn[t] = x1;
+        g0 = g1; g1 = g2;
+        __syncthreads();
+    }
+}
