@@ -107,6 +107,7 @@ struct SSCPatchPC_s {
     cudaStream_t side_stream = nullptr, launch_stream = nullptr;   // the small size classes of an apply run beside the big one; launch_apply_class launches on launch_stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap_classes = true;
+    int apply_group_threads = 128;   // threads of a CTA that carries several small patches (n <= 96): 96 / 128 / 192 / 256 measured, tools/gpu_apply_sizes.py
     bool apply_stream_small = true;  // n <= 96: persistent apply kernel with the gathers prefetched across patches
     int sm_count = 148;
     // options (defaults: PCCreate_PATCH ssc/libssc.c:1697-1711)
@@ -488,6 +489,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_factor_searchers") { pc->factor_searchers = atoi(v); return 0; }
     if (name == "ssc_overlap_classes") return parse_bool(v, &pc->overlap_classes);
     if (name == "ssc_apply_stream_small") return parse_bool(v, &pc->apply_stream_small);
+    if (name == "ssc_apply_group_threads") { pc->apply_group_threads = atoi(v); if (pc->apply_group_threads < 32 || pc->apply_group_threads > 256) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "ssc_apply_group_threads must be in [32, 256]"); return 0; }
     if (name == "ssc_factor_panel") { pc->factor_panel = atoi(v); return 0; }
     if (name == "ssc_factor_ctas") { pc->factor_ctas = atoi(v); return 0; }
     if (name == "ssc_factor_tile") { pc->factor_tile = atoi(v); return 0; }
@@ -687,14 +689,14 @@ extern "C" int SSCPatchReleaseOperator(SSCPatchPC pc)
 // ---------------------------------------------------------------------------------------------
 // setup
 // ---------------------------------------------------------------------------------------------
-static void choose_launch_shape(SizeClass &c, int variant)
+static void choose_launch_shape(SizeClass &c, int variant, int group_threads = 128)
 {
     int n = c.n;
     if (variant == 2) n = (c.n + 1) / 2;            // one thread per pair of rows
     if (n >= 1024) { c.tp = 1024; c.ppb = 1; return; }
     if (n > 96) { c.tp = (n + 31) / 32 * 32; c.ppb = 1; return; }
     c.tp = n <= 8 ? 8 : (n + 7) / 8 * 8;       // sub-warp groups for small patches
-    c.ppb = std::max(1, 192 / c.tp);
+    c.ppb = std::max(1, group_threads / c.tp);
 }
 
 static int need_lists(PC *pc);
@@ -757,7 +759,7 @@ static int build_device_lists(PC *pc)
             c.n = (int)n; c.first = q; c.goff = goff; c.moff = moff;
             c.ld = pc->apply_variant == 2 ? (int)((n + 1) / 2 * 2) : (int)n;
             c.stride = (n * c.ld + 15) / 16 * 16;
-            choose_launch_shape(c, pc->apply_variant);
+            choose_launch_shape(c, pc->apply_variant, pc->apply_group_threads);
             { const i64 psz = n * (n + 1) / 2; c.pstride = (psz + 15) / 16 * 16; c.pbytes = (unsigned)(((psz + 1) / 2 * 2) * 8); }
             pc->classes.push_back(c);
         }
