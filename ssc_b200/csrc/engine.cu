@@ -107,6 +107,7 @@ struct SSCPatchPC_s {
     cudaStream_t side_stream = nullptr, launch_stream = nullptr;   // the small size classes of an apply run beside the big one; launch_apply_class launches on launch_stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap_classes = true;
+    int apply_stream_max_n = 96;     // largest patch the persistent apply kernel takes (n = 125: measured no better than the one-patch-per-CTA kernel)
     int apply_group_threads = 128;   // threads of a CTA that carries several small patches (n <= 96): 96 / 128 / 192 / 256 measured, tools/gpu_apply_sizes.py
     bool apply_stream_small = true;  // n <= 96: persistent apply kernel with the gathers prefetched across patches
     int sm_count = 148;
@@ -489,6 +490,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_factor_searchers") { pc->factor_searchers = atoi(v); return 0; }
     if (name == "ssc_overlap_classes") return parse_bool(v, &pc->overlap_classes);
     if (name == "ssc_apply_stream_small") return parse_bool(v, &pc->apply_stream_small);
+    if (name == "ssc_apply_stream_max_n") { pc->apply_stream_max_n = atoi(v); return 0; }
     if (name == "ssc_apply_group_threads") { pc->apply_group_threads = atoi(v); if (pc->apply_group_threads < 32 || pc->apply_group_threads > 256) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "ssc_apply_group_threads must be in [32, 256]"); return 0; }
     if (name == "ssc_factor_panel") { pc->factor_panel = atoi(v); return 0; }
     if (name == "ssc_factor_ctas") { pc->factor_ctas = atoi(v); return 0; }
@@ -1454,7 +1456,7 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
         K<<<(unsigned)grid, threads, smem, pc->launch_stream>>>(blocks, c.stride, c.ld, gt, c.n, cnt, c.tp, c.ppb, xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch); \
     } while (0)
-    if (pc->apply_variant == 1 && pc->apply_stream_small && c.n <= 96 && c.tp >= c.n && threads <= 256) {
+    if (pc->apply_variant == 1 && pc->apply_stream_small && c.n <= pc->apply_stream_max_n && c.tp >= c.n && threads <= 256) {
         // persistent, gathers prefetched one and two patches ahead: groups walk the list in lockstep
         const int per_sm = std::max(1, 2048 / threads);
         const i64 ctas = std::min<i64>(grid, (i64)pc->sm_count * per_sm);
