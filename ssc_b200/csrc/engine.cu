@@ -108,6 +108,7 @@ struct SSCPatchPC_s {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap_classes = true;
     int apply_stream_max_n = 96;     // largest patch the persistent apply kernel takes (n = 125: measured no better than the one-patch-per-CTA kernel)
+    bool apply_exact_groups = true;  // n < 32: a group has exactly n threads (false: n rounded up to a multiple of 8)
     int apply_group_threads = 128;   // threads of a CTA that carries several small patches (n <= 96): 96 / 128 / 192 / 256 measured, tools/gpu_apply_sizes.py
     bool apply_stream_small = true;  // n <= 96: persistent apply kernel with the gathers prefetched across patches
     int sm_count = 148;
@@ -490,6 +491,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_factor_searchers") { pc->factor_searchers = atoi(v); return 0; }
     if (name == "ssc_overlap_classes") return parse_bool(v, &pc->overlap_classes);
     if (name == "ssc_apply_stream_small") return parse_bool(v, &pc->apply_stream_small);
+    if (name == "ssc_apply_exact_groups") return parse_bool(v, &pc->apply_exact_groups);
     if (name == "ssc_apply_stream_max_n") { pc->apply_stream_max_n = atoi(v); return 0; }
     if (name == "ssc_apply_group_threads") { pc->apply_group_threads = atoi(v); if (pc->apply_group_threads < 32 || pc->apply_group_threads > 256) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "ssc_apply_group_threads must be in [32, 256]"); return 0; }
     if (name == "ssc_factor_panel") { pc->factor_panel = atoi(v); return 0; }
@@ -691,13 +693,13 @@ extern "C" int SSCPatchReleaseOperator(SSCPatchPC pc)
 // ---------------------------------------------------------------------------------------------
 // setup
 // ---------------------------------------------------------------------------------------------
-static void choose_launch_shape(SizeClass &c, int variant, int group_threads = 128)
+static void choose_launch_shape(SizeClass &c, int variant, int group_threads = 128, bool exact_groups = true)
 {
     int n = c.n;
     if (variant == 2) n = (c.n + 1) / 2;            // one thread per pair of rows
     if (n >= 1024) { c.tp = 1024; c.ppb = 1; return; }
     if (n > 96) { c.tp = (n + 31) / 32 * 32; c.ppb = 1; return; }
-    c.tp = n <= 8 ? 8 : (n + 7) / 8 * 8;       // sub-warp groups for small patches
+    c.tp = (n < 32 && exact_groups) ? std::max(n, 1) : (n + 7) / 8 * 8;       // sub-warp groups for small patches: exactly n threads (a thread per patch at degree 1)
     c.ppb = std::max(1, group_threads / c.tp);
 }
 
@@ -758,10 +760,12 @@ static int build_device_lists(PC *pc)
         pc->orig2sorted[p] = q;
         if (pc->classes.empty() || pc->classes.back().n != (int)n) {
             SizeClass c;
+            moff = (moff + 15) / 16 * 16;                 // every class starts on a 128-byte line (a class of tiny blocks is unpadded inside)
             c.n = (int)n; c.first = q; c.goff = goff; c.moff = moff;
             c.ld = pc->apply_variant == 2 ? (int)((n + 1) / 2 * 2) : (int)n;
             c.stride = (n * c.ld + 15) / 16 * 16;
-            choose_launch_shape(c, pc->apply_variant, pc->apply_group_threads);
+            if (n * c.ld <= 4 && pc->apply_variant != 2) c.stride = n * c.ld;      // tiny blocks (degree 1: one entry) are not padded to a 128-byte line
+            choose_launch_shape(c, pc->apply_variant, pc->apply_group_threads, pc->apply_exact_groups);
             { const i64 psz = n * (n + 1) / 2; c.pstride = (psz + 15) / 16 * 16; c.pbytes = (unsigned)(((psz + 1) / 2 * 2) * 8); }
             pc->classes.push_back(c);
         }
