@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--deterministic", action="store_true", help="ssc_deterministic: slot-and-sum instead of fp64 atomics")
     ap.add_argument("--factor-ctas", type=int, default=None)
     ap.add_argument("--host-pipeline", type=int, default=None, help="ssc_host_pipeline (slabs of the overlapped host-space apply)")
+    ap.add_argument("--pipeline-taper", type=int, default=None, help="ssc_host_pipeline_taper (0: equal slabs, 1: slabs growing from both ends)")
     return ap.parse_args()
 
 
@@ -294,6 +295,8 @@ def main():
         pc.setOption("ssc_factor_panel", args.factor_panel)
     if args.host_pipeline is not None:
         pc.setOption("ssc_host_pipeline", args.host_pipeline)
+    if args.pipeline_taper is not None:
+        pc.setOption("ssc_host_pipeline_taper", bool(args.pipeline_taper))
     if nranks > 1:
         sf = partition.star_forest(slab.global_ids, slab.nowned, rank, nranks,
                                    lambda obj: _allgather(dist, obj, nranks))

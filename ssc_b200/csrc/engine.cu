@@ -219,6 +219,7 @@ struct SSCPatchPC_s {
     // pipelined host-space apply: H2D of x, patch kernels and D2H of y overlap slab by slab
     int pipe_slabs = 12;
     bool pipe_force = false;
+    bool pipe_taper = true;      // slabs grow geometrically from both ends of the patch list
     bool pipe_ready = false, pipe_tried = false;
     std::vector<std::vector<std::pair<i64, i64>>> pipe_ranges;   // [slab][class] -> sorted positions [q0, q1)
     std::vector<i64> pipe_in, pipe_out, pipe_bc;                 // x piece bounds, y piece bounds, bc list offsets per y piece
@@ -497,6 +498,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_factor_panel") { pc->factor_panel = atoi(v); return 0; }
     if (name == "ssc_factor_ctas") { pc->factor_ctas = atoi(v); return 0; }
     if (name == "ssc_factor_tile") { pc->factor_tile = atoi(v); return 0; }
+    if (name == "ssc_host_pipeline_taper") { pc->pipe_ready = false; pc->pipe_tried = false; return parse_bool(v, &pc->pipe_taper); }
     if (name == "ssc_host_pipeline") { const int s = atoi(v); pc->pipe_force = s < 0; pc->pipe_slabs = s < 0 ? -s : s; pc->pipe_ready = false; return 0; }   // negative: use it whatever the problem size
     if (name == "ssc_apply_variant") {
         const int a = atoi(v);
@@ -1601,6 +1603,18 @@ static int apply_device(PC *pc, const double *x, double *y)
     return 0;
 }
 
+// Patch-number bounds of the slabs of a pipelined host-space apply.  Tapered (default): slab sizes grow geometrically
+// from both ends (1, 2, 4, ... , 4, 2, 1), so the first kernels start after a sliver of x has arrived and only a sliver
+// of y is left to copy back when the last kernel ends, while the middle of the mesh runs in a few large launches.
+static i64 slab_bound(const PC *pc, int s, int S, i64 np)
+{
+    if (!pc->pipe_taper || S < 4) return np * s / S;
+    double tot = 0, acc = 0;
+    for (int k = 0; k < S; ++k) tot += (double)(1u << std::min(std::min(k, S - 1 - k), 5));
+    for (int k = 0; k < s; ++k) acc += (double)(1u << std::min(std::min(k, S - 1 - k), 5));
+    return s >= S ? np : (i64)((double)np * acc / tot);
+}
+
 // Slab schedule for host-space applies when neighbour ranks take part (peer exchange).  Same slabs by patch number as
 // below, but (i) the pieces of x that hold interface values travel first, so the halo push and the first neighbour
 // barrier happen a fraction of a millisecond into the apply, (ii) the slabs that touch ghost dofs run first and the
@@ -1617,7 +1631,7 @@ static int build_peer_pipeline(PC *pc)
     P.slab_ghost.assign(S, 0);
     pc->pipe_ranges.assign(S, std::vector<std::pair<i64, i64>>(pc->classes.size()));
     for (int s = 0; s < S; ++s) {
-        const i64 p0 = np * s / S, p1 = np * (s + 1) / S;
+        const i64 p0 = slab_bound(pc, s, S, np), p1 = slab_bound(pc, s + 1, S, np);
         for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
             const SizeClass &c = pc->classes[ci];
             auto first = pc->sorted2orig.begin() + c.first, last = first + c.count;
@@ -1792,7 +1806,7 @@ static int build_host_pipeline(PC *pc)
     std::vector<i64> lo(S, N), hi(S, -1);
     pc->pipe_ranges.assign(S, std::vector<std::pair<i64, i64>>(pc->classes.size()));
     for (int s = 0; s < S; ++s) {
-        const i64 p0 = np * s / S, p1 = np * (s + 1) / S;
+        const i64 p0 = slab_bound(pc, s, S, np), p1 = slab_bound(pc, s + 1, S, np);
         for (size_t ci = 0; ci < pc->classes.size(); ++ci) {
             const SizeClass &c = pc->classes[ci];
             auto first = pc->sorted2orig.begin() + c.first, last = first + c.count;
