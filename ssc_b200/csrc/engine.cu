@@ -107,6 +107,8 @@ struct SSCPatchPC_s {
     cudaStream_t side_stream = nullptr, launch_stream = nullptr;   // the small size classes of an apply run beside the big one; launch_apply_class launches on launch_stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap_classes = true;
+    int apply_stream_min_waves = 4;  // ... and only when every CTA gets at least this many rounds of patches (tests: 0)
+    int apply_stream_ctas = 0;       // CTAs of the persistent kernel (0: fill the GPU; tests use a few to get many rounds on small cases)
     int apply_stream_max_n = 96;     // largest patch the persistent apply kernel takes (n = 125: measured no better than the one-patch-per-CTA kernel)
     bool apply_exact_groups = true;  // n < 32: a group has exactly n threads (false: n rounded up to a multiple of 8)
     int apply_group_threads = 128;   // threads of a CTA that carries several small patches (n <= 96): 96 / 128 / 192 / 256 measured, tools/gpu_apply_sizes.py
@@ -493,6 +495,8 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_overlap_classes") return parse_bool(v, &pc->overlap_classes);
     if (name == "ssc_apply_stream_small") return parse_bool(v, &pc->apply_stream_small);
     if (name == "ssc_apply_exact_groups") return parse_bool(v, &pc->apply_exact_groups);
+    if (name == "ssc_apply_stream_min_waves") { pc->apply_stream_min_waves = atoi(v); return 0; }
+    if (name == "ssc_apply_stream_ctas") { pc->apply_stream_ctas = atoi(v); return 0; }
     if (name == "ssc_apply_stream_max_n") { pc->apply_stream_max_n = atoi(v); return 0; }
     if (name == "ssc_apply_group_threads") { pc->apply_group_threads = atoi(v); if (pc->apply_group_threads < 32 || pc->apply_group_threads > 256) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "ssc_apply_group_threads must be in [32, 256]"); return 0; }
     if (name == "ssc_factor_panel") { pc->factor_panel = atoi(v); return 0; }
@@ -1465,8 +1469,8 @@ static int launch_apply_class(PC *pc, const SizeClass &c, i64 q0, i64 q1, const 
     if (pc->apply_variant == 1 && pc->apply_stream_small && c.n <= pc->apply_stream_max_n && c.tp >= c.n && threads <= 256) {
         // persistent, gathers prefetched one and two patches ahead: groups walk the list in lockstep
         const int per_sm = std::max(1, 2048 / threads);
-        const i64 ctas = std::min<i64>(grid, (i64)pc->sm_count * per_sm);
-        if (grid >= 4 * ctas) {
+        const i64 ctas = pc->apply_stream_ctas > 0 ? std::min<i64>(grid, pc->apply_stream_ctas) : std::min<i64>(grid, (i64)pc->sm_count * per_sm);
+        if (grid >= (i64)pc->apply_stream_min_waves * ctas) {
             const size_t smem2 = 2 * smem;
             if (smem2 > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_apply_stream_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
             ssc_apply_stream_kernel<8><<<(unsigned)ctas, threads, smem2, pc->launch_stream>>>(blocks, c.stride, c.ld, gt, c.n, cnt, c.tp, c.ppb, xl, yl, scale, mult, pc->p2p ? pc->d_ps : nullptr, ypatch);

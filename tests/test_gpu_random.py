@@ -146,3 +146,49 @@ def test_degenerate_inputs():
     y = np.zeros(N)
     pc.apply(x, y)
     assert y[4] == x[4] / 4.0 and np.count_nonzero(y) == 1
+
+
+@pytest.mark.parametrize("opts", [{}, {"ssc_deterministic": True}, {"pc_patch_partition_of_unity": True}, {"ssc_apply_exact_groups": False},
+                                  {"ssc_apply_group_threads": 192}], ids=["default", "deterministic", "pou", "padded-groups", "192-threads"])
+@pytest.mark.parametrize("ctas", [1, 3])
+def test_persistent_apply_kernel_many_rounds(ctas, opts):
+    """The persistent small-patch apply kernel (n <= 96) prefetches the gathers of the next two patches while one streams.
+    It is only chosen for classes with many patches per CTA, which no small test reaches: here it is forced
+    (ssc_apply_stream_min_waves 0) onto one or three CTAs, so every group walks through many rounds, including
+    partial last rounds, for every group width from a thread per patch (n = 1) to 96."""
+    from ssc_b200 import PC
+    rng = np.random.default_rng(99)
+    N = 3000
+    R = sp.random(N, N, density=6.0 / N, random_state=rng, format="csr")
+    A = (R + R.T + sp.diags(np.full(N, 25.0) + rng.uniform(0, 5, N))).tocsr()
+    A.sort_indices()
+    lists = []
+    for n, cnt in ((1, 300), (2, 150), (3, 37), (5, 37), (9, 61), (16, 37), (27, 53), (31, 37), (32, 37), (45, 41), (64, 19), (81, 11), (96, 9)):
+        lists += [np.sort(rng.choice(N, size=n, replace=False)) for _ in range(cnt)]
+    order = rng.permutation(len(lists))                   # sizes interleaved in patch order: the classes are gathered by the sort
+    lists = [lists[i] for i in order]
+    off = np.concatenate(([0], np.cumsum([l.size for l in lists])))
+    gtol = np.concatenate(lists)
+    bc = np.sort(rng.choice(N, size=30, replace=False))
+    o = OraclePatchPC()
+    o.setPatches(off, gtol, N)
+    o.setOperatorCSR(A)
+    o.setUpOperators()
+    pc = PC(device=0)
+    pc.setOption("ssc_apply_stream_min_waves", 0)
+    pc.setOption("ssc_apply_stream_ctas", ctas)
+    for k, v in opts.items():
+        pc.setOption(k, v)
+    pc.setPatches(off, gtol, N, global_bc_nodes=bc)
+    pc.setOperatorCSR(A.indptr, A.indices, A.data)
+    pc.setUp()
+    for seed in (5, 6):
+        x = rhs_vector(N, seed)
+        ref = o.applyLocal(x)
+        ref[bc] = x[bc]
+        if opts.get("pc_patch_partition_of_unity"):
+            m = np.bincount(gtol, minlength=N)
+            ref = ref * np.where(m > 0, 1.0 / np.maximum(m, 1), 0.0)
+        y = np.full(N, np.nan)
+        pc.apply(x, y)
+        assert relerr(y, ref) < 1e-12
