@@ -89,6 +89,23 @@ def test_option_errors_match_reference_messages():
     assert "Schwarz type: additive" in text and "Patch construction operator: star" in text and "KSP not yet set" in text
 
 
+def test_extension_options_are_range_checked_and_listed():
+    """Every ssc_* extension option the library parses is in PATCH_OPTIONS (so setFromOptions forwards it), and the
+    numeric ones reject values outside their range."""
+    import re
+    from ssc_b200 import PC, SSCError
+    from ssc_b200.pcpatch import PATCH_OPTIONS
+    src = open(os.path.join(ROOT, "ssc_b200", "csrc", "engine.cu")).read()
+    parsed = set(re.findall(r'name == "(ssc_[a-z_0-9]+)"', src))
+    assert parsed and parsed <= set(PATCH_OPTIONS), sorted(parsed - set(PATCH_OPTIONS))
+    pc = PC(device=-1)
+    for name, bad in (("ssc_factor_variant", 9), ("ssc_apply_group_threads", 16), ("ssc_apply_group_threads", 1024), ("ssc_assemble_threads", 100)):
+        with pytest.raises(SSCError):
+            pc.setOption(name, bad)
+    for name, ok in (("ssc_factor_variant", 4), ("ssc_apply_group_threads", 128), ("ssc_host_pipeline_taper", "false"), ("ssc_apply_exact_groups", True)):
+        pc.setOption(name, ok)
+
+
 def test_setup_without_inputs_is_an_error():
     from ssc_b200 import PC, SSCError
     pc = PC(device=-1)
