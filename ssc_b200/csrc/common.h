@@ -3,6 +3,9 @@
 #include <cstdint>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -47,11 +50,45 @@ struct UserPatches {
     bool set = false;
 };
 
+// A plain array of trivially copyable T whose resize() does not touch the new elements: the patch builder's worker
+// threads fill disjoint ranges of the big result arrays themselves (a std::vector would first zero 260 MB on one thread).
+template <class T> class RawArray {
+    T *p_ = nullptr;
+    size_t n_ = 0;
+public:
+    RawArray() {}
+    RawArray(const RawArray &o) { assign(o.begin(), o.end()); }
+    RawArray(RawArray &&o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    RawArray &operator=(const RawArray &o) { if (this != &o) assign(o.begin(), o.end()); return *this; }
+    RawArray &operator=(RawArray &&o) noexcept { if (this != &o) { std::free(p_); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; } return *this; }
+    ~RawArray() { std::free(p_); }
+    void resize(size_t n) {                                 // contents up to min(old, new) size are kept, the rest is uninitialised
+        if (n == n_) return;
+        if (n == 0) { std::free(p_); p_ = nullptr; n_ = 0; return; }
+        T *q = static_cast<T *>(std::realloc(p_, n * sizeof(T)));
+        if (!q) throw std::bad_alloc();
+        p_ = q; n_ = n;
+    }
+    template <class It> void assign(It first, It last) { resize((size_t)(last - first)); std::copy(first, last, p_); }
+    void clear() { resize(0); }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+    T *begin() { return p_; }
+    T *end() { return p_ + n_; }
+    const T *begin() const { return p_; }
+    const T *end() const { return p_ + n_; }
+    T &operator[](size_t i) { return p_[i]; }
+    const T &operator[](size_t i) const { return p_[i]; }
+};
+
 struct PatchLists {
     i64 npatch = 0, vStart = 0;
-    std::vector<i64> cellOff, cells;           // cellCounts / cells   (ssc/libssc.c:452-580, renumbered :887)
-    std::vector<i64> gtolOff, gtol;            // gtolCounts / gtol    (ssc/libssc.c:779-837)
-    std::vector<i64> dofs;                     // per-cell patch-local index table (:846-889), optional
+    std::vector<i64> cellOff, gtolOff;         // offsets of cellCounts (ssc/libssc.c:452-580) and gtolCounts (:779-837)
+    RawArray<i64> cells;                       // cells of every patch, renumbered (:887)
+    RawArray<i64> gtol;                        // patch -> local dof lists (:779-837)
+    RawArray<i64> dofs;                        // per-cell patch-local index table (:846-889), optional
     std::string printout;                      // text of -pc_patch_print_patches
 };
 

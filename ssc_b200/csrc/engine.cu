@@ -807,11 +807,12 @@ static int build_device_lists(PC *pc)
     pc->event_ms["SSCListsSort"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() - pc->event_ms["PCPATCHCreate"];
     auto t1 = std::chrono::steady_clock::now();
     // dof lists in sorted order, int32
-    std::vector<int> g32((size_t)pc->sum_n);
+    RawArray<int> g32;                                     // filled by the threads below: no serial zero-fill of 130 MB
+    g32.resize((size_t)pc->sum_n);
     {
         std::vector<i64> woff(order.size() + 1, 0);              // write offset of every sorted patch
         for (size_t q = 0; q < order.size(); ++q) woff[q + 1] = woff[q] + (L.gtolOff[(size_t)order[q] + 1] - L.gtolOff[(size_t)order[q]]);
-        const int Tn = (int)std::min<size_t>(8, std::max<size_t>(1, order.size() / 4096));
+        const int Tn = (int)std::min<size_t>(std::min<size_t>(32, std::max(1u, std::thread::hardware_concurrency())), std::max<size_t>(1, order.size() / 4096));
         auto work = [&](int t) {
             for (size_t q = order.size() * t / Tn; q < order.size() * (t + 1) / Tn; ++q) {
                 const i64 p = order[q];
