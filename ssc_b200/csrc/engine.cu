@@ -203,7 +203,8 @@ struct SSCPatchPC_s {
     double *d_vals = nullptr;
     bool csr_owned = false;
     // element matrices (the reference's own source of the patch operators, ssc/libssc.c:1120-1156): borrowed like the CSR arrays
-    bool elem_set = false, elem_owned = false, elem_lists_ready = false;
+    bool elem_set = false, elem_owned = false, elem_lists_ready = false, elem_maps_ready = false;
+    i64 elem_map_rows = 0;
     bool asm_shared = false;         // assemble kernel: accumulate in place through L2 (13.7 ms at 64^3 Q3) or in shared memory when the block fits (26 ms)
     int asm_threads = 256;
     const double *elem_K = nullptr;
@@ -341,7 +342,7 @@ static void free_device_state(PC *pc)
     pc->d_elemK = nullptr; pc->elem_owned = false;
     dev_free(pc->d_pcelloff); dev_free(pc->d_pcells);
     for (int *&q : pc->d_cnm) dev_free(q);
-    pc->d_cnm.clear(); pc->elem_lists_ready = false;
+    pc->d_cnm.clear(); pc->elem_lists_ready = false; pc->elem_maps_ready = false; pc->elem_map_rows = 0;
     pc->classes.clear(); pc->device_ready = false; pc->setup_done = false; pc->pipe_ready = false;
 }
 
@@ -1103,9 +1104,44 @@ static int upload_csr(PC *pc)
     return 0;
 }
 
+// device copies (int32) of the cell-node maps, `rows` cells each: independent of the patches, so the uploader thread
+// sends them while the host still builds the patch lists
+static int upload_cell_node_maps(PC *pc, i64 rows)
+{
+    const Discretisation &D = pc->disc;
+    if (D.nsub > 8) return ssc_set_error(SSC_ERR_SUP, "element matrices: at most 8 subspaces");
+    for (int *&q : pc->d_cnm) dev_free(q);
+    pc->d_cnm.clear();
+    ElemSpaces &E = pc->espaces;
+    memset(&E, 0, sizeof(E));
+    E.nsub = (int)D.nsub; E.t = (int)D.totalDofsPerCell;
+    RawArray<int> narrow;
+    for (i64 k = 0; k < D.nsub; ++k) {
+        const i64 len = rows * D.nodesPerCell[k];
+        narrow.resize((size_t)len);
+        for (i64 i = 0; i < len; ++i) narrow[(size_t)i] = (int)D.cellNodeMap[k][i];
+        int *d = nullptr;
+        CHK(dev_alloc(&d, len));
+        pc->d_cnm.push_back(d);
+        CUDA_OK(cudaMemcpy(d, narrow.data(), (size_t)len * sizeof(int), cudaMemcpyHostToDevice));
+        E.cnm[k] = d; E.bs[k] = (int)D.bs[k]; E.npc[k] = (int)D.nodesPerCell[k]; E.subOff[k] = (int)D.subspaceOffsets[k];
+        E.tOff[k + 1] = E.tOff[k] + E.npc[k] * E.bs[k];
+    }
+    if (E.tOff[D.nsub] != E.t) return ssc_set_error(SSC_ERR_ARG_INCOMP, "subspaces add up to %d dofs per cell, expected %d", E.tOff[D.nsub], E.t);
+    pc->elem_maps_ready = true; pc->elem_map_rows = rows;
+    return 0;
+}
+
 static int upload_elements(PC *pc)
 {
     if (pc->multiplicative) return ssc_set_error(SSC_ERR_SUP, "multiplicative sweeps update the residual with the assembled operator: use SSCPatchSetOperatorCSR()");
+    if (!pc->elem_maps_ready && pc->disc.set && pc->disc.cn_set && pc->plex.set && !pc->direct_patches) {
+        // rows of the cell-node maps = cells in the cell numbering
+        const i64 cS = pc->plex.depthStart[pc->plex.dim], cE = pc->plex.depthEnd[pc->plex.dim];
+        i64 rows = 0;
+        for (i64 c = cS; c < cE; ++c) if (pc->disc.cnDof[(size_t)c] > 0) rows = std::max(rows, pc->disc.cnOff[(size_t)c] + 1);
+        if (rows > 0) CHK(upload_cell_node_maps(pc, rows));
+    }
     if (pc->elem_owned) { dev_free(pc->d_elemK); pc->elem_owned = false; }
     if (pc->elem_space == SSC_MEM_DEVICE) { pc->d_elemK = const_cast<double *>(pc->elem_K); return 0; }
     const i64 t2 = pc->elem_t * pc->elem_t;
@@ -1147,22 +1183,7 @@ static int upload_element_lists(PC *pc)
     CHK(dev_alloc(&pc->d_pcells, std::max<i64>(1, (i64)cells.size())));
     CUDA_OK(cudaMemcpyAsync(pc->d_pcelloff, off.data(), (size_t)(ns + 1) * sizeof(i64), cudaMemcpyHostToDevice, pc->stream));
     CUDA_OK(cudaMemcpyAsync(pc->d_pcells, cells.data(), cells.size() * sizeof(int), cudaMemcpyHostToDevice, pc->stream));
-    ElemSpaces &E = pc->espaces;
-    memset(&E, 0, sizeof(E));
-    E.nsub = (int)D.nsub; E.t = (int)D.totalDofsPerCell;
-    std::vector<int> narrow;
-    for (i64 k = 0; k < D.nsub; ++k) {
-        const i64 len = (maxcell + 1) * D.nodesPerCell[k];
-        narrow.resize((size_t)len);
-        for (i64 i = 0; i < len; ++i) narrow[(size_t)i] = (int)D.cellNodeMap[k][i];
-        int *d = nullptr;
-        CHK(dev_alloc(&d, len));
-        pc->d_cnm.push_back(d);
-        CUDA_OK(cudaMemcpy(d, narrow.data(), (size_t)len * sizeof(int), cudaMemcpyHostToDevice));
-        E.cnm[k] = d; E.bs[k] = (int)D.bs[k]; E.npc[k] = (int)D.nodesPerCell[k]; E.subOff[k] = (int)D.subspaceOffsets[k];
-        E.tOff[k + 1] = E.tOff[k] + E.npc[k] * E.bs[k];
-    }
-    if (E.tOff[D.nsub] != E.t) return ssc_set_error(SSC_ERR_ARG_INCOMP, "subspaces add up to %d dofs per cell, expected %d", E.tOff[D.nsub], E.t);
+    if (!pc->elem_maps_ready || pc->elem_map_rows <= maxcell) CHK(upload_cell_node_maps(pc, maxcell + 1));
     CUDA_OK(cudaStreamSynchronize(pc->stream));
     pc->elem_lists_ready = true;
     return 0;
