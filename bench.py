@@ -327,7 +327,7 @@ def main():
         csr = None
     setup = {"note": "setup_wall_s = SSCPatchSetUp with the CSR in pageable host memory: patch construction on the host, H2D of dof lists and CSR, extract, factor" if not elements else "setup_wall_s = SSCPatchSetUp from one shared element matrix: patch construction on the host, H2D of dof lists / cell lists / cell-node maps, assemble kernel (extract_ms), factor", "create_patches_ms": pc.eventTime("PCPATCHCreate"), "extract_ms": pc.eventTime("PCPATCHComputeOp"),
              "factor_ms": pc.eventTime("PCPATCHSolve"), "lists_ms": pc.eventTime("SSCSetupLists"), "upload_operator_ms": pc.eventTime("SSCSetupUploadOperator"),
-             "alloc_blocks_ms": pc.eventTime("SSCSetupAllocBlocks"), "setup_wall_s": info["t_setup_wall"],
+             "alloc_blocks_ms": pc.eventTime("SSCSetupAllocBlocks"), "kernels_wall_ms": pc.eventTime("SSCSetupKernels"), "free_operator_ms": pc.eventTime("SSCSetupFreeOperator"), "setup_wall_s": info["t_setup_wall"],
              "assemble_wall_s": info["t_assemble"], "mesh_wall_s": info["t_mesh"]}
     if setup["extract_ms"] > 0 and not elements:
         setup["extract_gbs"] = pc.size("bytes_extract") / (setup["extract_ms"] * 1e-3) / 1e9      # algorithmic bytes of SURVEY.md 8(d)

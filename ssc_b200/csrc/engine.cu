@@ -202,9 +202,10 @@ struct SSCPatchPC_s {
     int *d_colidx = nullptr;
     double *d_vals = nullptr;
     bool csr_owned = false;
+    i64 csr_dev_rows = 0, csr_dev_nnz = 0;   // shape of the owned device copy
     // element matrices (the reference's own source of the patch operators, ssc/libssc.c:1120-1156): borrowed like the CSR arrays
     bool elem_set = false, elem_owned = false, elem_lists_ready = false, elem_maps_ready = false;
-    i64 elem_map_rows = 0;
+    i64 elem_map_rows = 0, elem_dev_len = 0;
     bool asm_shared = false;         // assemble kernel: accumulate in place through L2 (13.7 ms at 64^3 Q3) or in shared memory when the block fits (26 ms)
     int asm_threads = 256;
     const double *elem_K = nullptr;
@@ -1086,18 +1087,22 @@ static int staged_upload(PC *pc, void *dst, const void *src, size_t bytes)
 static int upload_csr(PC *pc)
 {
     if (!pc->csr_set) return ssc_set_error(SSC_ERR_ARG_WRONGSTATE, "Must call SSCPatchSetOperatorCSR() to set the operator");   // cf. ssc/libssc.c:1131-1133
-    if (pc->csr_owned) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); pc->csr_owned = false; }
     if (pc->csr_nrows < pc->nlocal) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "operator has %lld rows but the local vector has %lld dofs", (long long)pc->csr_nrows, (long long)pc->nlocal);
     if (pc->csr_space == SSC_MEM_DEVICE) {
+        if (pc->csr_owned) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); pc->csr_owned = false; }
         pc->d_rowptr = const_cast<i64 *>(pc->csr_rowptr); pc->d_colidx = const_cast<int *>(pc->csr_colidx); pc->d_vals = const_cast<double *>(pc->csr_vals);
         return 0;
     }
     const i64 nnz = pc->csr_rowptr[pc->csr_nrows];
+    // the device copy of the previous set-up is reused when the shape is the same (PCSetUp after a change of values, ssc/patch.py:269-270)
+    if (pc->csr_owned && (pc->csr_dev_rows != pc->csr_nrows || pc->csr_dev_nnz != nnz)) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); pc->csr_owned = false; }
     pc->csr_nnz = nnz;
-    CHK(dev_alloc(&pc->d_rowptr, pc->csr_nrows + 1));
-    CHK(dev_alloc(&pc->d_colidx, nnz));
-    CHK(dev_alloc(&pc->d_vals, nnz));
-    pc->csr_owned = true;
+    if (!pc->csr_owned) {
+        CHK(dev_alloc(&pc->d_rowptr, pc->csr_nrows + 1));
+        CHK(dev_alloc(&pc->d_colidx, nnz));
+        CHK(dev_alloc(&pc->d_vals, nnz));
+        pc->csr_owned = true; pc->csr_dev_rows = pc->csr_nrows; pc->csr_dev_nnz = nnz;
+    }
     CUDA_OK(cudaMemcpyAsync(pc->d_rowptr, pc->csr_rowptr, (size_t)(pc->csr_nrows + 1) * sizeof(i64), cudaMemcpyHostToDevice, pc->up_stream));
     CHK(staged_upload(pc, pc->d_colidx, pc->csr_colidx, (size_t)nnz * sizeof(int)));
     CHK(staged_upload(pc, pc->d_vals, pc->csr_vals, (size_t)nnz * sizeof(double)));
@@ -1142,12 +1147,14 @@ static int upload_elements(PC *pc)
         for (i64 c = cS; c < cE; ++c) if (pc->disc.cnDof[(size_t)c] > 0) rows = std::max(rows, pc->disc.cnOff[(size_t)c] + 1);
         if (rows > 0) CHK(upload_cell_node_maps(pc, rows));
     }
-    if (pc->elem_owned) { dev_free(pc->d_elemK); pc->elem_owned = false; }
-    if (pc->elem_space == SSC_MEM_DEVICE) { pc->d_elemK = const_cast<double *>(pc->elem_K); return 0; }
     const i64 t2 = pc->elem_t * pc->elem_t;
     const i64 len = pc->elem_stride == 0 ? t2 : (pc->elem_ncells - 1) * pc->elem_stride + t2;
-    CHK(dev_alloc(&pc->d_elemK, len));
-    pc->elem_owned = true;
+    if (pc->elem_owned && (pc->elem_space == SSC_MEM_DEVICE || pc->elem_dev_len != len)) { dev_free(pc->d_elemK); pc->elem_owned = false; }
+    if (pc->elem_space == SSC_MEM_DEVICE) { pc->d_elemK = const_cast<double *>(pc->elem_K); return 0; }
+    if (!pc->elem_owned) {                                      // else: the buffer of the previous set-up has the right size
+        CHK(dev_alloc(&pc->d_elemK, len));
+        pc->elem_owned = true; pc->elem_dev_len = len;
+    }
     CHK(staged_upload(pc, pc->d_elemK, pc->elem_K, (size_t)len * sizeof(double)));
     return 0;
 }
@@ -1406,8 +1413,16 @@ extern "C" int SSCPatchSetUp(SSCPatchPC pc)
         i64 firstbad = -1;
         pc->failed_list.clear();
         for (size_t q = 0; q < fail.size(); ++q) if (fail[q]) { if (firstbad < 0) firstbad = pc->sorted2orig[q]; pc->failed++; pc->failed_list.push_back(pc->sorted2orig[q]); }
-        if (pc->csr_owned && !pc->multiplicative) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); pc->csr_owned = false; }
-        if (pc->elem_owned) { dev_free(pc->d_elemK); pc->elem_owned = false; }
+        lap("SSCSetupKernels");                                     // extract / assemble + factor + failure flags
+        // The device copy of the operator is only dropped when memory is tight: cudaFree of the 10.65 GB CSR of the 64^3 Q3
+        // case takes 0.3 s (a third of the set-up), and the next set-up of the same shape reuses the buffers.
+        {
+            size_t free_b = 0, total_b = 0;
+            const bool tight = cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < total_b / 4;
+            if (tight && pc->csr_owned && !pc->multiplicative) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); pc->csr_owned = false; }
+            if (tight && pc->elem_owned) { dev_free(pc->d_elemK); pc->elem_owned = false; }
+        }
+        lap("SSCSetupFreeOperator");
         if (pc->failed) return ssc_set_error(SSC_ERR_MAT_LU_ZRPVT, "%lld patch operators could not be factorised (first: patch %lld)%s", (long long)pc->failed,
                                              (long long)firstbad, pc->sub_pc == SSC_SUB_CHOLESKY ? "; sub_pc_type cholesky needs SPD blocks" : "");
     } else {
