@@ -229,6 +229,7 @@ struct SSCPatchPC_s {
     std::vector<i64> pipe_in, pipe_out, pipe_bc;                 // x piece bounds, y piece bounds, bc list offsets per y piece
     cudaStream_t s_in = nullptr, s_out = nullptr;
     // the same with neighbour ranks (peer exchange): pieces of x / y over the owned dofs, slabs that touch ghosts first
+    cudaEvent_t trace_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // SSC_PIPE_TRACE timeline of the multi-rank host apply
     struct PeerPipe {
         std::vector<i64> cut, bc_off;                 // piece p = owned dofs [cut[p], cut[p+1]); Dirichlet list offsets per piece
         std::vector<int> copy_order, slab_order;      // H2D order of the pieces (those holding interface values first); launch order of the slabs
@@ -376,6 +377,7 @@ extern "C" int SSCPatchDestroy(SSCPatchPC *ppc)
     dev_free(pc->d_xg); dev_free(pc->d_yin); dev_free(pc->d_iface); dev_free(pc->d_flags); dev_free(pc->d_timeout); dev_free(pc->d_ps);
     dev_free(pc->d_ghostPeer); dev_free(pc->d_ghostRemote); dev_free(pc->d_sendPeer); dev_free(pc->d_remoteLeaf);
     if (pc->s_in) { cudaStreamDestroy(pc->s_in); cudaStreamDestroy(pc->s_out); }
+    for (auto &ev : pc->trace_ev) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     for (auto &ev : pc->ev_in) cudaEventDestroy(ev);
     for (auto &ev : pc->ev_k) cudaEventDestroy(ev);
     for (auto &e : pc->kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -1773,8 +1775,8 @@ static int apply_host_pipelined_peer(PC *pc, const double *x, double *y)
     // SSC_PIPE_TRACE=1: per-apply timeline on stderr (ms after the start: halo barrier passed, ghost slabs done, all
     // slabs done, neighbours' second barrier collected, last byte of y on the host)
     static const bool trace = getenv("SSC_PIPE_TRACE") != nullptr;
-    static cudaEvent_t tev[6];
-    if (trace && !tev[0]) for (auto &e : tev) cudaEventCreate(&e);
+    cudaEvent_t *tev = pc->trace_ev;                          // per PC: events belong to the device they were created on
+    if (trace && !tev[0]) for (int i = 0; i < 6; ++i) cudaEventCreate(&tev[i]);
     if (trace) cudaEventRecord(tev[0], pc->stream);
     CUDA_OK(cudaMemsetAsync(dy, 0, (size_t)pc->nowned * sizeof(double), pc->stream));
     CUDA_OK(cudaEventRecord(pc->ev_k[S], pc->stream));
