@@ -1794,6 +1794,7 @@ static int apply_host_pipelined_peer(PC *pc, const double *x, double *y)
     auto emit_piece = [&](int q) -> int {
         const i64 a = P.cut[q], b = P.cut[q + 1];
         const i64 nb = P.bc_off[q + 1] - P.bc_off[q];
+        CUDA_OK(cudaStreamWaitEvent(pc->stream, pc->ev_in[q], 0));      // the Dirichlet rows copy x: a piece no slab reads has not been waited for yet
         if (nb > 0) { ssc_bc_kernel<<<grid_for(nb, 256), 256, 0, pc->stream>>>(pc->d_bc + P.bc_off[q], nb, dx, dy); pc->launches++; }
         if (pc->partition_of_unity && b > a) { ssc_scale_kernel<<<grid_for(b - a, 256), 256, 0, pc->stream>>>(b - a, pc->d_w + a, dy + a); pc->launches++; }
         CUDA_OK(cudaEventRecord(pc->ev_k[q], pc->stream));
