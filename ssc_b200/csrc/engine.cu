@@ -1867,6 +1867,7 @@ static int build_host_pipeline(PC *pc)
     i64 suf = N;
     pc->pipe_out[S] = N;
     for (int s = S - 1; s >= 1; --s) { suf = std::min(suf, lo[s]); pc->pipe_out[s] = suf; }
+    for (int s = 1; s < S; ++s) pc->pipe_out[s] = std::min(pc->pipe_out[s], pc->pipe_in[s]);   // a piece of y never ends beyond the x that has arrived (Dirichlet rows copy x)
     for (int s = 1; s <= S; ++s) pc->pipe_out[s] = std::max(pc->pipe_out[s], pc->pipe_out[s - 1]);
     // Dirichlet list offsets per y piece (the list is uploaded in ascending order)
     std::vector<i64> bc;
