@@ -87,7 +87,7 @@ def _worker(rank, nranks, port, outdir, axis=2):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nranks,axis", [(2, 2), (3, 2), (2, 0), (3, 0)])
+@pytest.mark.parametrize("nranks,axis", [(2, 2), (3, 2), (2, 0), (3, 0), (2, 1)])
 def test_slabs_over_gloo_match_single_rank(nranks, axis, tmp_path):
     """Slabs cut along z (interface dofs scattered through the local numbering) and along x (contiguous at the ends:
     the layout the overlapped multi-rank host apply is built for)."""
