@@ -252,6 +252,15 @@ int ssc_build_patches(const HostPlex &plex, const Discretisation &disc, const Us
             if (ghost) { c.cellCount.push_back(0); c.gtolCount.push_back(0); continue; }
             int ierr = b.build_one(v, stamp, stamp + 1, s, c);
             if (ierr) { c.err = ierr; return; }
+            if (v - lo == 255 && hi - lo > 1024) {
+                // the first 256 patches of the range size the output arrays (20 % headroom): no regrowth copies of a
+                // dof list that ends up at tens of megabytes per thread
+                const double per = 1.2 * (double)(hi - lo) / 256.0;
+                c.gtol.reserve((size_t)(per * (double)c.gtol.size()));
+                c.cells.reserve((size_t)(per * (double)c.cells.size()));
+                c.dofs.reserve((size_t)(per * (double)c.dofs.size()));
+                c.cellCount.reserve((size_t)(hi - lo)); c.gtolCount.reserve((size_t)(hi - lo));
+            }
         }
     };
     if (T == 1) worker(0);
