@@ -114,6 +114,7 @@ struct SSCPatchPC_s {
     int apply_group_threads = 128;   // threads of a CTA that carries several small patches (n <= 96): 96 / 128 / 192 / 256 measured, tools/gpu_apply_sizes.py
     bool apply_stream_small = true;  // n <= 96: persistent apply kernel with the gathers prefetched across patches
     int sm_count = 148;
+    size_t total_mem = (size_t)180 << 30;
     // options (defaults: PCCreate_PATCH ssc/libssc.c:1697-1711)
     bool save_operators = true, partition_of_unity = false, multiplicative = false, print_patches = false;
     bool symmetrise_sweep = false, keep_operators = false, dim_set = false, codim_set = false;
@@ -322,6 +323,7 @@ extern "C" int SSCPatchCreate(int device, SSCPatchPC *out)
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     pc->sm_count = prop.multiProcessorCount;
+    pc->total_mem = (size_t)prop.totalGlobalMem;
     CUDA_OK(cudaEventCreate(&pc->ev0));
     CUDA_OK(cudaEventCreate(&pc->ev1));
     *out = pc;
@@ -1419,8 +1421,9 @@ extern "C" int SSCPatchSetUp(SSCPatchPC pc)
         // The device copy of the operator is only dropped when memory is tight: cudaFree of the 10.65 GB CSR of the 64^3 Q3
         // case takes 0.3 s (a third of the set-up), and the next set-up of the same shape reuses the buffers.
         {
-            size_t free_b = 0, total_b = 0;
-            const bool tight = cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < total_b / 4;
+            // (own bookkeeping instead of cudaMemGetInfo, which itself took up to 70 ms here)
+            const double held = 8.0 * (double)pc->block_elems * (pc->keep_operators ? 2.0 : 1.0) + 12.0 * (double)pc->csr_nnz + 8.0 * (double)pc->elem_dev_len + 4.0 * (double)pc->sum_n;
+            const bool tight = held > 0.6 * (double)pc->total_mem;
             if (tight && pc->csr_owned && !pc->multiplicative) { dev_free(pc->d_rowptr); dev_free(pc->d_colidx); dev_free(pc->d_vals); pc->csr_owned = false; }
             if (tight && pc->elem_owned) { dev_free(pc->d_elemK); pc->elem_owned = false; }
         }
