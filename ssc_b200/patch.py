@@ -10,7 +10,6 @@ Difference from the reference, by design: the inner PC does not asse
 per-patch callback into PETSc Mats (ssc/patch.py:210-213); it is given the assembled local operator in CSR and
 cuts the dense patch blocks out of it on the GPU.
 """
-import numpy as np
 
 from . import fem, petsc_lite
 from .pcpatch import PC as PatchPCCore

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import CHKERR, MEM_DEVICE, MEM_HOST, as_i64, dp, i64p, ip, lib
+from ._lib import CHKERR, MEM_DEVICE, MEM_HOST, as_i64, dp, ip, lib
 from . import PatchPC as cPatchPC      # the Cython shim (the package later rebinds this name to the python class,
                                        # exactly like ssc/patch.py:12 + ssc/__init__.py:2 in the reference)
 

@@ -2,7 +2,6 @@
 import numpy as np
 
 from oracle.oracle import OraclePatchPC
-from ssc_b200 import fem
 
 OPT_NAMES = {"dim": "pc_patch_construction_dim", "codim": "pc_patch_construction_codim",
              "construct_type": "pc_patch_construction_type", "exclude_subspace": "pc_patch_exclude_subspace",

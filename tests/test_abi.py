@@ -1,5 +1,4 @@
 """The C-ABI library loads, exports every symbol include/ssc_b200.h declares, and refuses to compute without a GPU."""
-import ctypes as C
 import os
 import re
 

@@ -9,7 +9,7 @@ import pytest
 
 from conftest import rhs_vector
 from helpers import OraclePythonPC, solve
-from ssc_b200 import fem, plex
+from ssc_b200 import fem
 from ssc_b200 import petsc_lite as pl
 
 pytestmark = pytest.mark.gpu

@@ -6,7 +6,7 @@ Krylov iteration counts; patch dof lists bit-exact.
 import numpy as np
 import pytest
 
-from conftest import meshes, rhs_vector
+from conftest import rhs_vector
 from helpers import make_gpu, make_oracle, relerr
 from ssc_b200 import fem, plex
 
