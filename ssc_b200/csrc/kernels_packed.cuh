@@ -116,8 +116,8 @@ ssc_apply_sym_kernel(const double *__restrict__ packed, ll pstride, unsigned cop
                      const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
                      const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *L = reinterpret_cast<double *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_bulk[];     // its own name: the other kernels declare the dynamic array with 16-byte alignment
+    double *L = reinterpret_cast<double *>(smem_bulk);
     double *xs = L + (copy_bytes >> 3);
     __shared__ __align__(8) unsigned long long bar;
     const ll p = blockIdx.x;
@@ -159,8 +159,8 @@ ssc_apply_sym2_kernel(const double *__restrict__ packed, ll pstride, unsigned co
                       ll count, const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
                       const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *L = reinterpret_cast<double *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_bulk[];     // its own name: the other kernels declare the dynamic array with 16-byte alignment
+    double *L = reinterpret_cast<double *>(smem_bulk);
     double *xs = L + (copy_bytes >> 3);
     double *ypart = xs + n;
     __shared__ __align__(8) unsigned long long bar[2];
@@ -212,10 +212,10 @@ ssc_apply_sym_persistent_kernel(const double *__restrict__ packed, ll pstride, u
                                 const double *__restrict__ x, double *__restrict__ y, double scale, const double *__restrict__ mult,
                                 const PeerScatter *__restrict__ ps, double *__restrict__ ypatch)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_bulk[];     // its own name: the other kernels declare the dynamic array with 16-byte alignment
     __shared__ __align__(8) unsigned long long bar[8];
     const size_t stage_doubles = copy_bytes >> 3;
-    double *ring = reinterpret_cast<double *>(smem_raw);
+    double *ring = reinterpret_cast<double *>(smem_bulk);
     double *xsbuf = ring + stage_doubles * stages;            // 2 x n
     double *ypart = xsbuf + 2 * n;                             // (F - 1) x rp partial sums
     const int rp = (n + 31) & ~31;                             // row slots per part
