@@ -48,7 +48,12 @@ int SSCPatchDestroy(SSCPatchPC *pc);                      /* PCDestroy_PATCH  ss
 /* name is the option without the prefix and leading dash, e.g. "pc_patch_save_operators", "sub_pc_type";
  * value is its string form ("true", "1", "lu", ...).  Unknown names and unsupported values return an error
  * (no silent fallback).  "pc_patch_multiplicative true": the reference raises an error (mode removed, ssc/libssc.c:1570-1572);
- * this build runs a coloured multiplicative sweep instead (BASELINE.json north_star). */
+ * this build runs a coloured multiplicative sweep instead (BASELINE.json north_star).
+ * Names of the reference (ssc/libssc.c:1551-1620): pc_patch_save_operators, pc_patch_partition_of_unity,
+ * pc_patch_multiplicative, pc_patch_construction_dim | _codim | _type, pc_patch_vanka_dim, pc_patch_exclude_subspace,
+ * pc_patch_sub_mat_type, pc_patch_print_patches, pc_patch_symmetrise_sweep, sub_ksp_type, sub_pc_type.
+ * Extensions of this build all start with "ssc_" (kernel selection, launch shapes, storage modes, host pipeline);
+ * they are listed with their defaults in DESIGN.md section 2 and never change results beyond rounding. */
 int SSCPatchSetOption(SSCPatchPC pc, const char *name, const char *value);
 int SSCPatchSetSaveOperators(SSCPatchPC pc, int flg);     /* PCPatchSetSaveOperators     ssc/libssc.c:84-91   */
 int SSCPatchSetPartitionOfUnity(SSCPatchPC pc, int flg);  /* PCPatchSetPartitionOfUnity  ssc/libssc.c:93-100  */
