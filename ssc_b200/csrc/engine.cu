@@ -209,6 +209,7 @@ struct SSCPatchPC_s {
     i64 elem_map_rows = 0, elem_dev_len = 0;
     bool asm_shared = false;         // assemble kernel: accumulate in place through L2 (13.7 ms at 64^3 Q3) or in shared memory when the block fits (26 ms)
     int asm_threads = 256;
+    int asm_ctas_per_sm = 16;        // blocks being accumulated at once per SM (their in-place working set competes for L2)
     const double *elem_K = nullptr;
     i64 elem_ncells = 0, elem_t = 0, elem_stride = 0;
     int elem_space = 0;
@@ -487,6 +488,7 @@ extern "C" int SSCPatchSetOption(SSCPatchPC pc, const char *name_, const char *v
     if (name == "ssc_symmetric_bulk_copy") return parse_bool(v, &pc->sym_bulk);
     if (name == "ssc_symmetric_two_chunk") return parse_bool(v, &pc->sym_two_chunk);
     if (name == "ssc_assemble_shared") return parse_bool(v, &pc->asm_shared);
+    if (name == "ssc_assemble_ctas_per_sm") { pc->asm_ctas_per_sm = std::max(1, atoi(v)); return 0; }
     if (name == "ssc_assemble_threads") { pc->asm_threads = atoi(v); if (pc->asm_threads != 128 && pc->asm_threads != 256 && pc->asm_threads != 512 && pc->asm_threads != 1024) return ssc_set_error(SSC_ERR_ARG_OUTOFRANGE, "ssc_assemble_threads must be 128, 256, 512 or 1024"); return 0; }
     if (name == "ssc_device_patch_construction") { CHK(parse_bool(v, &pc->device_construct)); pc->lists_valid = false; return 0; }
     if (name == "ssc_deterministic") {
@@ -1229,7 +1231,7 @@ static int extract_and_invert(PC *pc, const SizeClass &c, i64 q0, i64 q1, double
         const size_t smem_a = base + (acc_shared ? accb : 0);
         if (smem_a > 200 * 1024) return ssc_set_error(SSC_ERR_SUP, "patch with %d dofs is too large for the assemble kernel", n);
         if (smem_a > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(ssc_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-        const int grid_a = (int)std::min<i64>(cnt, (i64)pc->sm_count * 16);
+        const int grid_a = (int)std::min<i64>(cnt, (i64)pc->sm_count * pc->asm_ctas_per_sm);
         ssc_assemble_kernel<<<grid_a, pc->asm_threads, smem_a, pc->stream>>>(pc->espaces, pc->d_elemK, (ll)pc->elem_stride, (const ll *)pc->d_pcelloff + q0, pc->d_pcells,
                                                                pc->d_gtol + c.goff + (q0 - c.first) * n, blocks, n, c.ld, c.stride, cnt, H, acc_shared);
     } else {
