@@ -250,9 +250,16 @@ def main():
     args = parse()
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # `python bench.py --gpus N` without a launcher: start the N ranks ourselves, exactly as the contract's torchrun line does
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 400), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     nranks = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != nranks:
+        raise SystemExit("--gpus %d but the launcher started %d rank(s)" % (args.gpus, nranks))
     if args.impl == "reference":
         run_reference(args, rank, nranks)
         return
