@@ -30,3 +30,16 @@ def test_product_arm_fails_loudly_without_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--cells", "4", "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode != 0 and "no CPU fallback" in out.stderr
+
+
+def test_reference_arm_under_a_launcher_prints_once_and_checks_the_rank_count():
+    """--gpus N without a launcher starts N ranks itself (the contract's torchrun line); rank 0 alone prints; a launcher
+    that started a different number of ranks is an error, not a silently mislabelled line."""
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cells", "5", "--cpu-sample", "64", "--steps", "1", "--warmup", "0"]
+    env = {k: v for k, v in os.environ.items() if k not in ("WORLD_SIZE", "RANK", "LOCAL_RANK")}
+    out = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2
+    bad = subprocess.run(cmd + ["--gpus", "1"], capture_output=True, text=True, timeout=600, env=dict(env, WORLD_SIZE="2", RANK="0"))
+    assert bad.returncode != 0 and "launcher started 2" in bad.stderr
