@@ -94,7 +94,8 @@ def test_extension_options_are_range_checked_and_listed():
     import re
     from ssc_b200 import PC, SSCError
     from ssc_b200.pcpatch import PATCH_OPTIONS
-    src = open(os.path.join(ROOT, "ssc_b200", "csrc", "engine.cu")).read()
+    csrc = os.path.join(ROOT, "ssc_b200", "csrc")
+    src = "".join(open(os.path.join(csrc, f)).read() for f in sorted(os.listdir(csrc)) if f.endswith((".cu", ".inc")))
     parsed = set(re.findall(r'name == "(ssc_[a-z_0-9]+)"', src))
     assert parsed and parsed <= set(PATCH_OPTIONS), sorted(parsed - set(PATCH_OPTIONS))
     pc = PC(device=-1)
