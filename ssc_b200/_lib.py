@@ -18,7 +18,7 @@ f64p = C.POINTER(C.c_double)
 MEM_HOST, MEM_DEVICE = 0, 1
 
 if not os.path.exists(LIB_PATH):
-    raise ImportError("%s is missing: build it with `python -m ssc_b200.build` (nvcc, sm_100a). "
+    raise ImportError("%s is missing: build it with `python ssc_b200/build.py` (nvcc, sm_100a). "
                       "ssc_b200 has no CPU fallback." % LIB_PATH)
 
 lib = C.CDLL(LIB_PATH)
