@@ -13,13 +13,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
 
 
-@pytest.fixture(scope="session", autouse=True)
-def _built():
-    # build the product library and the oracle if they are missing (no-op when up to date)
-    from ssc_b200 import build
-    build.build()
+def _ensure_built():
+    # Build the product library and the oracle if they are missing or stale (no-op when up to date).  At conftest import
+    # time, i.e. before the test modules are collected: they import ssc_b200, which refuses to load without its library;
+    # build.py is therefore loaded by path, not through the package.
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ssc_b200_build", os.path.join(ROOT, "ssc_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    b.build()
     from oracle import oracle
     oracle.build()
+
+
+_ensure_built()
 
 
 def meshes():
