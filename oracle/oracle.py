@@ -196,6 +196,13 @@ class OraclePatchPC(object):
         self._chk(self.L.oracle_apply_local(self.h, C.c_int64(localX.size), _dp(localX), _dp(y), int(nthreads)))
         return y
 
+    def applyScale(self, x):
+        """scale_i = sum over the patches containing local dof i of max|B_p^-1 R_p x| (tests/helpers.entry_err)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        s = np.zeros_like(x)
+        self._chk(self.L.oracle_apply_scale(self.h, C.c_int64(x.size), _dp(x), _dp(s)))
+        return s
+
     def multiplicityLocal(self, nlocal):
         y = np.zeros(nlocal)
         self._chk(self.L.oracle_multiplicity_local(self.h, C.c_int64(nlocal), _dp(y)))

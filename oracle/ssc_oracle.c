@@ -607,6 +607,30 @@ int oracle_apply_local(OraclePC *pc, i64 nlocal, const double *localX, double *l
     return 0;
 }
 
+/* Test scaffolding for the per-entry parity check (tests/helpers.entry_err), not a reference function:
+ * scale[i] = sum over the patches p containing local dof i of max_l |(B_p^{-1} R_p x)_l| -- the magnitude the
+ * patch solves of ssc/libssc.c:1374 that are added into entry i (:1190) work at.  Sweeps count twice (:1336-1343). */
+int oracle_apply_scale(OraclePC *pc, i64 nlocal, const double *localX, double *scale) {
+    i64 np = pc->npatch, nsweep = pc->symmetrise_sweep ? 2 : 1;
+    i64 niter = pc->construct_type == 2 ? pc->niter : np;
+    memset(scale, 0, nlocal * sizeof(double));
+    if (!pc->lu) { snprintf(pc->err, 256, "operators not set up"); return 73; }
+    i64 maxn = 0; for (i64 i = 0; i < np; i++) if (pc->gtolDof[i] > maxn) maxn = pc->gtolDof[i];
+    double *px = malloc((maxn + 1) * sizeof(double)), *py = malloc((maxn + 1) * sizeof(double));
+    for (i64 jj = 0; jj < niter; jj++) {
+        i64 i = pc->construct_type == 2 ? pc->iterationSet[jj] : jj;
+        i64 len = pc->gtolDof[i]; const i64 *g = pc->gtol + pc->gtolOff[i];
+        if (len <= 0) continue;
+        for (i64 l = 0; l < len; l++) px[l] = localX[g[l]];
+        lu_solve(pc->lu[i], pc->piv[i], len, px, py);
+        double m = 0.0;
+        for (i64 l = 0; l < len; l++) if (fabs(py[l]) > m) m = fabs(py[l]);
+        for (i64 l = 0; l < len; l++) scale[g[l]] += nsweep * m;
+    }
+    free(px); free(py);
+    return 0;
+}
+
 /* one-process PCApply_PATCH (identity star forest): steps 2-7 of ssc/libssc.c:1321-1421.
  * VecReciprocal (:1282, PETSc) leaves zero entries at zero; restated here. */
 int oracle_setup_weights(OraclePC *pc, i64 n) {

@@ -119,14 +119,10 @@ struct SSCPatchPC_s {
     bool save_operators = true, partition_of_unity = false, multiplicative = false, print_patches = false;
     bool symmetrise_sweep = false, keep_operators = false, dim_set = false, codim_set = false;
     int sub_pc = SSC_SUB_LU;
-    int factor_tile = 4;          // register tiles of the n <= 128 factor kernel: 4 (8x4, default) or 8 (8x8, measured slower)
     int factor_ctas = 0;          // concurrent CTAs of the blocked factor kernel (0 = fill the SMs)
     int factor_panel = 16;        // panel width of the blocked factor kernel (16 or 32)
-    int factor_searchers = 1;     // blocked look-ahead kernel: searcher warps (1 or 2)
-    bool factor_remap = true;     // blocked look-ahead kernel: keep the searcher's SM sub-partition nearly free of worker warps
-    int factor_variant = -1;      // n <= 128: 0 shared-memory Gauss-Jordan, 1 register-resident, 2 + look-ahead pivot search, 3 blocked look-ahead;
-                                  // 4 blocked look-ahead with the searcher two panels ahead;
-                                  // -1 (default): for 100 <= n <= 128 (one CTA per SM anyway) 4 with pivoting (lu), 3 without (cholesky); 1 below (many small CTAs per SM hide the latency)
+    int factor_variant = -1;      // -1 (default) by size: n <= 96 register tiles (1), 97..128 register-resident DMMA accumulators with look-ahead (2), larger blocked DMMA on the
+                                  // L2-resident block (3), beyond its shared-memory panels the in-place global-memory Gauss-Jordan (0); 0..3 force one where it applies
     int apply_variant = 1;        // 0: simple loop, 1: pipelined LDG.64, 2: pipelined LDG.128 (even row stride)
     std::string sub_mat_type, sub_ksp_type = "preonly";
     BuildOptions bopt;

@@ -33,7 +33,28 @@ def make_gpu(form, bcs, device=0, **opts):
 
 
 def relerr(a, b):
-    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+    """Relative error of a against b: the worse of the 2-norm ratio and the max-norm ratio, so that no single entry may
+    be off by more than the tolerance times the largest entry (a 2-norm alone would let a few entries hide)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if b.size == 0:
+        return 0.0
+    e2 = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+    emax = np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+    return max(e2, emax)
+
+
+def entry_err(a, b, scale):
+    """Per-entry error: max_i |a_i - b_i| / scale_i, where scale_i = sum over the patches p containing dof i of
+    max|B_p^-1 R_p x| (OraclePatchPC.applyScale) -- the magnitude the patch solves that write into entry i work at.
+    A patch solve is accurate to a few ulps of ITS largest entry, so this is the sharpest bound that holds entry by entry:
+    entries near Dirichlet faces, whose patches have small solutions, are checked at their own small scale.  Entries
+    with scale 0 (Dirichlet dofs: passed through) must agree exactly."""
+    a, b, scale = (np.asarray(v, dtype=np.float64) for v in (a, b, scale))
+    d = np.abs(a - b)
+    zero = scale == 0
+    if np.any(d[zero] != 0):
+        return np.inf
+    return float((d[~zero] / scale[~zero]).max()) if np.any(~zero) else 0.0
 
 
 class OraclePythonPC(object):

@@ -102,7 +102,7 @@ def test_extension_options_are_range_checked_and_listed():
     for name, bad in (("ssc_factor_variant", 9), ("ssc_apply_group_threads", 16), ("ssc_apply_group_threads", 1024), ("ssc_assemble_threads", 100)):
         with pytest.raises(SSCError):
             pc.setOption(name, bad)
-    for name, ok in (("ssc_factor_variant", 4), ("ssc_apply_group_threads", 128), ("ssc_host_pipeline_taper", "false"), ("ssc_apply_exact_groups", True)):
+    for name, ok in (("ssc_factor_variant", 2), ("ssc_apply_group_threads", 128), ("ssc_host_pipeline_taper", "false"), ("ssc_apply_exact_groups", True)):
         pc.setOption(name, ok)
 
 
