@@ -42,11 +42,12 @@ def parse():
     ap.add_argument("--degree", type=int, default=3)
     ap.add_argument("--workload", default="poisson_hex", choices=["poisson_hex", "elasticity_tets"],
                     help="poisson_hex = BASELINE.json configs[2] (default); elasticity_tets = configs[3]: vector P2 linear elasticity on a Freudenthal tet mesh (N=1 only)")
-    ap.add_argument("--cpu-sample", type=int, default=16384, help="patches in the CPU-baseline sample")
     ap.add_argument("--operator", default="csr", choices=["csr", "elements"],
                     help="source of the patch operators: the assembled CSR (extract kernel, default) or element matrices (the reference's own route; hex workloads, no CSR is built: the CPU baseline and the packed-symmetric extra are skipped)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-setup-serial", action="store_true", help="CPU baseline: factorise the window's patch operators on one core too (the reference's set-up is serial per rank); adds ~10 s")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-rank parity leg (oracle on the patches around every rank interface)")
     ap.add_argument("--apply-variant", type=int, default=None, help="ssc_apply_variant (kernel selection; default = library default)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo exchange: NVLink peer memory (default) or NCCL send/recv")
     ap.add_argument("--factor-panel", type=int, default=None)
@@ -162,62 +163,189 @@ def operator_csr(V, disc):
     return synth.tensor_poisson_csr(V, disc.ghost_bc_nodes)
 
 
-def cpu_baseline(V, disc, csr, args, nthreads=None, x=None, y_gpu=None):
-    """The oracle's PCApply loop (gather, LU solve with precomputed factors, scatter-add) on a contiguous sample of the
-    workload's patches, all host threads; scaled to the whole vector by sum(n^2) (the loop is bound by streaming factors)."""
+def window_oracle(args, nthreads):
+    """The CPU oracle on a 6-cell-thick window (6, c, c) of the hex workload, everything built by oracle/ and the synthetic
+    FE generator alone (no product library on this path): mesh, operator, dof lists (oracle restatement of
+    ssc/libssc.c:452-900), LU factors.  The window's vertex planes 1..5 carry patches identical to those of any interior
+    plane of the full mesh, planes 0 and 6 those of its two boundary planes.  Returns (oracle, V, times)."""
     from oracle import oracle
-    from ssc_b200 import PC
-    from ssc_b200.patch import setup_patch_pc
-    nthreads = nthreads or os.cpu_count()
-    h = PC(device=-1)                         # host-only handle: dof lists only
-    setup_patch_pc(h, disc, None)
-    off, gtol = h.getPatches()
-    sizes = np.diff(off)
-    np_all = sizes.size
-    S = min(args.cpu_sample, np_all)
-    lo = (np_all - S) // 2                     # middle of the mesh: the interior (n = (2p-1)^3) patches that dominate
+    from ssc_b200 import fem, plex, synth
+    c, p = args.cells, args.degree
+    h = 1.0 / c
+    t0 = time.perf_counter()
+    mesh = plex.TensorPlex((min(6, c), c, c), lengths=(min(6, c) * h, c * h, c * h))
+    V = fem.FunctionSpace(mesh, p)
+    disc = fem.Discretisation([V])
+    synth.set_threads(max(1, nthreads))
+    csr = synth.tensor_poisson_csr(V, disc.ghost_bc_nodes)
+    t1 = time.perf_counter()
     o = oracle.OraclePatchPC()
-    soff = off[lo:lo + S + 1] - off[lo]
-    o.setPatches(soff, gtol[off[lo]:off[lo + S]], disc.total_dofs)
+    o.setFromDiscretisation(disc)
+    o.setOptions()
+    o.setUpPatches()
+    t2 = time.perf_counter()
     o.setOperatorCSRArrays(*csr)
-    o.setUpOperators(nthreads=nthreads)
-    if x is None:
-        x = np.random.default_rng(20260101).uniform(-1, 1, disc.total_dofs)
-    yo = o.applyLocal(x, nthreads=nthreads)    # warm-up; also the parity sample below
+    o.setUpOperators(nthreads=1 if args.cpu_setup_serial else nthreads)
+    t3 = time.perf_counter()
+    return o, V, {"mesh_and_operator_s": t1 - t0, "patch_lists_s": t2 - t1, "operators_and_lu_s": t3 - t2,
+                  "operators_and_lu_threads": 1 if args.cpu_setup_serial else nthreads}
+
+
+def hex_census(c, p):
+    """(number of patches, sum n, sum n^2) of the c^3 Q_p vertex-star problem with Dirichlet faces (sizes are
+    products of the 1D sizes 2p-1 (interior vertex) and p-1 (boundary vertex))."""
+    one = np.array([p - 1] + [2 * p - 1] * (c - 1) + [p - 1], dtype=np.float64)
+    return (c + 1) ** 3, float(one.sum()) ** 3, float((one ** 2).sum()) ** 3
+
+
+def cpu_baseline(args, nthreads=None, x_lat=None, y_lat=None):
+    """The reference's CPU path restated (oracle/ssc_oracle.c: gather, LU solve with precomputed factors, scatter-add --
+    the patch loop of ssc/libssc.c:1342-1388) timed on the window of `window_oracle` (7 vertex planes of (c+1)^2 patches)
+    and scaled to the whole mesh by sum n^2 (the loop streams the factors).  Reported on all host threads and on ONE
+    core (the reference is single-threaded per rank), with the oracle's own set-up times scaled by patch count.
+    x_lat / y_lat: optional global input and GPU result as lattice arrays (X, Y, Z) for the parity sample."""
+    nthreads = nthreads or os.cpu_count() or 1
+    c, p = args.cells, args.degree
+    o, V, times = window_oracle(args, nthreads)
+    off, _ = o.patches()
+    sizes = np.diff(off).astype(np.float64)
+    npatch_all, sum_n_all, sum_n2_all = hex_census(c, p)
+    frac = float((sizes ** 2).sum() / sum_n2_all)
+    L = np.indices(V.lattice_shape).reshape(3, -1)
+    node = V.lattice_node.ravel()
+    k = c // 2                                   # the window sits mid-mesh: cells [k-3, k+3)
+    if x_lat is not None:
+        xs = np.empty(V.node_count)
+        xs[node] = x_lat[L[0] + (k - 3) * p, L[1], L[2]] if c > 6 else x_lat[L[0], L[1], L[2]]
+    else:
+        xs = np.random.default_rng(20260101).uniform(-1, 1, V.node_count)
+    yo = o.apply(xs, nthreads=nthreads)           # warm-up; also the parity sample below
     parity = None
-    if y_gpu is not None:
-        # dofs all of whose patches are inside the sample: there the oracle's partial sum is the complete PCApply value
-        mult_all = np.bincount(gtol, minlength=disc.total_dofs)
-        part = np.bincount(gtol[off[lo]:off[lo + S]], minlength=disc.total_dofs)
-        sel = np.nonzero((part > 0) & (part == mult_all))[0]
-        if sel.size:
-            err = float(np.abs(y_gpu[sel] - yo[sel]).max() / np.abs(yo[sel]).max())
-            parity = {"dofs_checked": int(sel.size), "max_rel_err_vs_oracle": err, "ok": bool(err < 1e-12)}
+    if y_lat is not None:
+        good = (L[0] >= p) & (L[0] <= (min(6, c) - 1) * p) if c > 6 else np.ones(node.size, dtype=bool)
+        yg = y_lat[L[0] + (k - 3) * p, L[1], L[2]] if c > 6 else y_lat[L[0], L[1], L[2]]
+        d = np.abs(yg[good] - yo[node][good])
+        scale = o.applyScale(xs)[node][good]
+        err = float(d.max() / np.abs(yo[node][good]).max())
+        eerr = float("inf") if np.any(d[scale == 0] != 0) else float((d[scale > 0] / scale[scale > 0]).max())
+        parity = {"dofs_checked": int(good.sum()), "max_rel_err_vs_oracle": err, "max_entry_err_vs_oracle": eerr, "ok": bool(err < 1e-12 and eerr < 1e-12)}
     reps, t = 0, 0.0
-    while t < 10.0 and reps < 20:
+    while t < 8.0 and reps < 20:
         t0 = time.perf_counter()
-        o.applyLocal(x, nthreads=nthreads)
+        o.apply(xs, nthreads=nthreads)
         t += time.perf_counter() - t0
         reps += 1
     per = t / reps
-    frac = float((sizes[lo:lo + S].astype(np.float64) ** 2).sum() / (sizes.astype(np.float64) ** 2).sum())
-    full = per / frac
-    return {"value": disc.total_dofs / full, "unit": "dofs/s", "cores": int(nthreads), "kind": "port",
-            "sample": "%d contiguous mid-mesh patches of %d (%.2f%% of sum n^2), %d applies, scaled by sum n^2; CPU restatement of libssc PCApply (oracle/ssc_oracle.c), factors precomputed"
-                      % (S, np_all, 100 * frac, reps),
-            "ms_per_step_full_estimate": full * 1e3, "parity": parity}
+    t0 = time.perf_counter()
+    o.apply(xs, nthreads=1)
+    per1 = time.perf_counter() - t0
+    ndofs = (c * p + 1) ** 3
+    pfrac = sizes.size / npatch_all
+    return {"value": ndofs / (per / frac), "unit": "dofs/s", "cores": int(nthreads), "kind": "port", "extrapolated": True,
+            "sample": "window of %d x %d x %d cells mid-mesh = %d patches of %d (%.2f%% of sum n^2), %d applies, scaled by sum n^2; CPU restatement of libssc PCApply "
+                      "(oracle/ssc_oracle.c) with its own dof lists and LU factors; nothing of the product library on this path" % (min(6, c), c, c, sizes.size, npatch_all, 100 * frac, reps),
+            "ms_per_step_full_estimate": per / frac * 1e3,
+            "one_core": {"value": ndofs / (per1 / frac), "unit": "dofs/s", "cores": 1, "ms_per_step_full_estimate": per1 / frac * 1e3,
+                         "note": "the reference is single-threaded per MPI rank (SURVEY.md 8d)"},
+            "setup": {"note": "oracle set-up on the window, scaled to the whole mesh by patch count (dof lists) and by sum n^3 ~ patch count (LU); "
+                              "the reference factorises lazily inside the first KSPSolve (ssc/libssc.c:1374), so its set-up cost = these + the first apply",
+                      "window": times, "patch_lists_s_full_estimate": times["patch_lists_s"] / pfrac,
+                      "operators_and_lu_s_full_estimate": times["operators_and_lu_s"] / pfrac,
+                      "setup_plus_first_apply_s_full_estimate_one_core": None if not args.cpu_setup_serial else (times["patch_lists_s"] + times["operators_and_lu_s"]) / pfrac + per1 / frac},
+            "parity": parity}
+
+
+def interface_parity(args, dist, rank, nranks, slab, x_owned, results):
+    """Multi-rank parity against the CPU oracle (SCALE runs prove the halo fill and the overlap sum themselves).
+
+    The reference's contract across ranks is exactness of SFBcast / SFReduce (ssc/libssc.c:1323-1324, :1399-1400): the
+    result must not depend on the partition.  For every rank interface (vertex plane k = r * cells of the global
+    (cells * N, cells, cells) mesh) rank 0 builds the 6-cell-thick sub-mesh [k-3, k+3) x cells x cells on its own, runs
+    the oracle (its own dof lists, its own LU solves) on it with the global input restricted to it, and compares every
+    dof whose patches all lie within two cells of the interface (vertex planes k-2 .. k+2: their stars are complete inside
+    the sub-mesh, so their patch problems are those of the global mesh) -- owned dofs of both neighbours, dofs that
+    were ghosts on one side, and the overlap sums in between.  `results` maps a label to this rank's owned result
+    vector (device-resident apply, host-space apply)."""
+    c, p = args.cells, args.degree
+    gshape = slab.global_shape
+    plane = gshape[1] * gshape[2]
+    gid = np.asarray(slab.global_ids[:slab.nowned])
+    X = gid // plane
+    sel = np.zeros(gid.size, dtype=bool)
+    for r in range(1, nranks):
+        k = r * c
+        sel |= (X >= (k - 3) * p) & (X <= (k + 3) * p)
+    mine = {"gid": gid[sel], "x": np.asarray(x_owned)[sel]}
+    for name, y in results.items():
+        mine[name] = np.asarray(y)[sel]
+    parts = _allgather(dist, mine, nranks)
+    if rank != 0:
+        return None
+    from oracle import oracle
+    from ssc_b200 import fem, plex, synth
+    allg = np.concatenate([q["gid"] for q in parts])
+    order = np.argsort(allg)
+    allg = allg[order]
+    if np.any(np.diff(allg) == 0):
+        raise SystemExit("interface parity: a dof is owned by two ranks")
+    vals = {name: np.concatenate([q[name] for q in parts])[order] for name in ["x"] + list(results)}
+    h = 1.0 / c
+    mesh = plex.TensorPlex((6, c, c), lengths=(6 * h, c * h, c * h))
+    V = fem.FunctionSpace(mesh, p)
+    disc = fem.Discretisation([V])
+    csr = synth.tensor_poisson_csr(V, disc.ghost_bc_nodes)
+    L = np.indices(V.lattice_shape).reshape(3, -1)
+    node = V.lattice_node.ravel()
+    o = oracle.OraclePatchPC()
+    o.setFromDiscretisation(disc)
+    o.setOptions()
+    o.setUpPatches()
+    o.setOperatorCSRArrays(*csr)
+    nth = os.cpu_count() or 1
+    o.setUpOperators(nthreads=nth)            # the sub-meshes of all interfaces are congruent: one set of oracle factors serves them all
+    out = {"interfaces": nranks - 1, "dofs_checked": 0, "patches_per_interface": int(5 * (c + 1) ** 2),
+           "method": "CPU oracle on the 6-cell sub-mesh around every rank interface; dofs whose patches all lie within two cells of it"}
+    worst = {name: 0.0 for name in results}
+    worst_entry = {name: 0.0 for name in results}
+    for r in range(1, nranks):
+        k = r * c
+        g = np.ravel_multi_index((L[0] + (k - 3) * p, L[1], L[2]), gshape)
+        pos = np.searchsorted(allg, g)
+        if np.any(pos >= allg.size) or np.any(allg[np.minimum(pos, allg.size - 1)] != g):
+            raise SystemExit("interface parity: the ranks did not deliver every dof around interface %d" % r)
+        xs = np.empty(V.node_count)
+        xs[node] = vals["x"][pos]
+        yo = o.apply(xs, nthreads=nth)
+        scale = o.applyScale(xs)
+        good = node[(L[0] >= p) & (L[0] <= 5 * p)]
+        out["dofs_checked"] += int(good.size)
+        for name in results:
+            yg = np.empty(V.node_count)
+            yg[node] = vals[name][pos]
+            d = np.abs(yg[good] - yo[good])
+            worst[name] = max(worst[name], float(d.max() / np.abs(yo[good]).max()))
+            sc = scale[good]
+            if np.any(d[sc == 0] != 0):
+                worst_entry[name] = float("inf")
+            else:
+                worst_entry[name] = max(worst_entry[name], float((d[sc > 0] / sc[sc > 0]).max()))
+    out["max_rel_err_vs_oracle"] = worst
+    out["max_entry_err_vs_oracle"] = worst_entry
+    out["ok"] = bool(all(v < 1e-12 for v in worst.values()) and all(v < 1e-12 for v in worst_entry.values()))
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
 def run_reference(args, rank, nranks):
     if rank != 0:
         return
-    V, disc, slab, info = build_problem(args, 0, 1)
-    csr = operator_csr(V, disc)
+    if args.workload != "poisson_hex":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU restatement arm is wired for the poisson_hex workload (BASELINE.json configs[2]) only"}))
+        return
     vals = []
     base = None
     for i in range(args.warmup + args.steps):
-        base = cpu_baseline(V, disc, csr, args) if base is None or i >= args.warmup else base
+        base = cpu_baseline(args) if base is None or i >= args.warmup else base
         if i >= args.warmup:
             vals.append(base["value"])
         if len(vals) >= 3:           # bounded: a step here is seconds of CPU work
@@ -226,7 +354,7 @@ def run_reference(args, rank, nranks):
     # dofs/s of the host cores does not depend on how many slabs the job has: at N GPUs the same throughput is quoted for
     # the N-times larger problem (the whole box's cores were already used for one slab), and a step takes N times longer
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "dofs/s", "n_gpus": args.gpus, "steps": len(vals),
-           "warmup": args.warmup, "ms_per_step": disc.total_dofs * nranks / v * 1e3, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": (args.cells * args.degree + 1) ** 3 * nranks / v * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": workload_config(args, nranks),
            "cpu_baseline": dict(base, value=v),
@@ -410,6 +538,14 @@ def main():
         e2e = {"value": nglobal / (ems * 1e-3), "unit": "dofs/s", "h2d_bytes_per_step": 8 * nowned, "d2h_bytes_per_step": 8 * nowned,
                "ms_per_step": ems, "api": "ssc_b200.PC.apply(x, y) on pinned host vectors (SSCPatchApply, SSC_MEM_HOST)", "cpus_bound_near_gpu": ncpus_bound}
 
+    # ---- multi-rank parity leg: the oracle on the patches around every rank interface -----------------------
+    parity = None
+    if nranks > 1 and args.workload == "poisson_hex" and not args.no_parity:
+        res = {"device_resident": dy.get()}
+        if e2e is not None:
+            res["host_vectors"] = np.array(yh.array)
+        parity = interface_parity(args, dist, rank, nranks, slab, xh.array, res)
+
     # size-independent property at full size (all N): the additive operator is symmetric for an SPD problem, so
     # <M a, b> == <a, M b> over the whole (distributed) vector; a broken halo fill or overlap sum breaks it
     rng2 = np.random.default_rng(777 + rank)
@@ -435,6 +571,8 @@ def main():
         return
     if symmetry["rel_diff"] > 1e-10:
         raise SystemExit("symmetry check failed: %r" % (symmetry,))
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("multi-rank PCApply differs from the CPU oracle around the rank interfaces: %r" % (parity,))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -460,6 +598,8 @@ def main():
            "dtype": "f64", "data": "synthetic", "config": workload_config(args, nranks),
            "dofs": nglobal, "patches_per_gpu": pc.size("npatch"), "hbm_gbs_step": bytes_apply * nranks / (ms_step * 1e-3) / 1e9,
            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "setup": setup, "symmetry_check": symmetry}
+    if parity is not None:
+        out["parity"] = parity
     if flush:
         out["config"]["l2"] = "working set %.2f GB: L2 flushed (256 MB write) before every timed step, each step timed on its own" % (pc.size("block_bytes") / 1e9)
     if nranks == 1 and not args.no_spd_packed and args.workload == "poisson_hex" and not elements:
@@ -467,10 +607,11 @@ def main():
             out["spd_packed"] = spd_packed_line(args, disc, csr, dx, dy, peak)
         except Exception as exc:                     # an extra, never allowed to take the main line down
             out["spd_packed"] = {"error": str(exc)}
-    if nranks == 1 and not args.no_cpu_baseline and not elements:
+    if nranks == 1 and not args.no_cpu_baseline and args.workload == "poisson_hex":
         pc.apply(dx, dy)
         pc.synchronize()
-        out["cpu_baseline"] = cpu_baseline(V, disc, csr, args, x=np.array(xh.array), y_gpu=dy.get())
+        lat = V.lattice_node                       # (X, Y, Z) lattice -> dof number
+        out["cpu_baseline"] = cpu_baseline(args, x_lat=np.asarray(xh.array)[lat], y_lat=dy.get()[lat])
         if out["cpu_baseline"]["parity"] and not out["cpu_baseline"]["parity"]["ok"]:
             raise SystemExit("PCApply differs from the CPU oracle on the sampled dofs: %r" % (out["cpu_baseline"]["parity"],))
     print(json.dumps(out))

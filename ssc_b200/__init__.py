@@ -1,9 +1,26 @@
 """ssc_b200: B200-native patch subspace-correction preconditioner (the hot path of wence-/ssc).
 
-Importing the package loads the CUDA shared library; there is no CPU fallback.
+The product names (PC, PatchPC, SSC, ...) load the CUDA shared library on first use; there is no CPU fallback: without
+the library they raise ImportError.  The synthetic problem generator (``fem``, ``plex``, ``synth``, ``partition``) is
+plain numpy scaffolding and imports without it -- bench.py's reference arm and the oracle tests use it alone.
 """
-from ._lib import SSCError, device_count, LIB_PATH          # noqa: F401
-from .pcpatch import PC, DeviceVec, PinnedArray            # noqa: F401
-from .patch import PatchPC, setup_patch_pc                 # noqa: F401
-from .lo import P1PC                                        # noqa: F401
-from .ssc_pc import SSC                                    # noqa: F401
+import importlib
+
+_LAZY = {"SSCError": "._lib", "device_count": "._lib", "LIB_PATH": "._lib",
+         "PC": ".pcpatch", "DeviceVec": ".pcpatch", "PinnedArray": ".pcpatch",
+         "PatchPC": ".patch", "setup_patch_pc": ".patch", "P1PC": ".lo", "SSC": ".ssc_pc"}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        value = getattr(importlib.import_module(_LAZY[name], __name__), name)
+        globals()[name] = value
+        return value
+    try:
+        return importlib.import_module("." + name, __name__)
+    except ImportError:
+        raise AttributeError("module %r has no attribute %r" % (__name__, name))
+
+
+def __dir__():
+    return sorted(list(globals()) + list(_LAZY))

@@ -12,8 +12,15 @@ import numpy as np
 
 from . import _lib
 from ._lib import CHKERR, MEM_DEVICE, MEM_HOST, as_i64, dp, ip, lib
-from . import PatchPC as cPatchPC      # the Cython shim (the package later rebinds this name to the python class,
-                                       # exactly like ssc/patch.py:12 + ssc/__init__.py:2 in the reference)
+import importlib
+import sys
+
+# the Cython shim ssc_b200/PatchPC.pyx.  Importing a submodule binds it as the package attribute `PatchPC`; that name belongs
+# to the python class (ssc_b200.PatchPC, resolved lazily by the package): exactly the collision of ssc/patch.py:12 +
+# ssc/__init__.py:2 in the reference, where the package rebinds the name to the class.
+cPatchPC = importlib.import_module(".PatchPC", __package__)
+if getattr(sys.modules[__package__], "PatchPC", None) is cPatchPC:
+    delattr(sys.modules[__package__], "PatchPC")
 
 # option names of PCSetFromOptions_PATCH (ssc/libssc.c:1551-1620) and of the per-patch KSP prefix "sub_" (:1240-1241)
 PATCH_OPTIONS = ("pc_patch_save_operators", "pc_patch_partition_of_unity", "pc_patch_multiplicative",

@@ -34,7 +34,7 @@ def _oracle_for(disc, V):
     return o
 
 
-def _worker(rank, nranks, port, outdir, axis=2):
+def _worker(rank, nranks, port, outdir, axis=2, parity_leg=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -83,6 +83,22 @@ def _worker(rank, nranks, port, outdir, axis=2):
     bc = slab.discretisation.global_bc_nodes
     y[bc] = x[bc]
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), y=y, gid=slab.global_ids[:slab.nowned])
+    if parity_leg:
+        # bench.py's multi-rank parity leg on the same data: correct results pass, a result without the overlap sum fails
+        import argparse
+        import json
+        import bench
+        args = argparse.Namespace(cells=C, degree=P)
+        y_no_sum = np.zeros(slab.nowned)
+        y_no_sum[sr] += yl[sl]
+        y_no_sum[bc] = x[bc]
+        xg = np.array(x)
+        if rank == 1:
+            xg[sroot[so[0]]] += 1.0                       # "stale ghost": what the neighbour saw differs from what the owner holds
+        res = bench.interface_parity(args, dist, rank, nranks, slab, x, {"good": y, "no_overlap_sum": y_no_sum})
+        res2 = bench.interface_parity(args, dist, rank, nranks, slab, xg, {"stale_ghost": y})
+        if rank == 0:
+            json.dump({"a": res, "b": res2}, open(os.path.join(outdir, "parity.json"), "w"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -112,3 +128,19 @@ def test_slabs_over_gloo_match_single_rank(nranks, axis, tmp_path):
         seen[d["gid"]] += 1
         assert np.abs(d["y"] - ylat[d["gid"]]).max() <= 1e-14 * np.abs(ylat).max()
     assert np.all(seen == 1)          # every global dof is owned by exactly one rank
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_bench_parity_leg_accepts_correct_and_rejects_broken_exchanges(nranks, tmp_path):
+    """bench.py's N>1 parity leg (oracle on the 6-cell sub-mesh around every rank interface): correct multi-rank results
+    pass at 1e-12; a result whose overlap sum was skipped, or whose halo was filled with other values than the owner's,
+    is rejected."""
+    import json
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(nranks, _free_port(), str(tmp_path), 0, True), nprocs=nranks, join=True)
+    r = json.load(open(os.path.join(str(tmp_path), "parity.json")))
+    a, b = r["a"], r["b"]
+    assert a["interfaces"] == nranks - 1 and a["dofs_checked"] == (nranks - 1) * (4 * P + 1) * (C * P + 1) ** 2
+    assert a["max_rel_err_vs_oracle"]["good"] < 1e-12 and a["max_entry_err_vs_oracle"]["good"] < 1e-12
+    assert a["max_rel_err_vs_oracle"]["no_overlap_sum"] > 1e-3 and not a["ok"]
+    assert b["max_rel_err_vs_oracle"]["stale_ghost"] > 1e-6 and not b["ok"]
