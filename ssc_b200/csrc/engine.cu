@@ -199,6 +199,9 @@ struct SSCPatchPC_s {
     int *d_colidx = nullptr;
     double *d_vals = nullptr;
     bool csr_owned = false;
+    bool csr_dup = false;            // some row of the CSR has unsorted or repeated columns: the extract kernel accumulates instead of storing
+    int *d_flag = nullptr;
+    int extract_row_buffers = -1;    // -ssc_extract_row_buffers: warps of an extract CTA that get a shared-memory row buffer (-1: as many as fit; 0: hits go straight to global memory, the path of very large patches)
     i64 csr_dev_rows = 0, csr_dev_nnz = 0;   // shape of the owned device copy
     // element matrices (the reference's own source of the patch operators, ssc/libssc.c:1120-1156): borrowed like the CSR arrays
     bool elem_set = false, elem_owned = false, elem_lists_ready = false, elem_maps_ready = false;

@@ -4,25 +4,47 @@
 
 // ---------------------------------------------------------------------------------------------
 // K1 extract: B_p[i][j] = A[gtol_p[i], gtol_p[j]]   (replaces MatZeroEntries + callback assembly,
-// ssc/libssc.c:1286-1291, :1120-1156).  One CTA per patch; a shared-memory hash maps global column -> patch
-// column; each warp owns one output row at a time, accumulates it in shared memory and stores it coalesced.
+// ssc/libssc.c:1286-1291, :1120-1156).  One CTA per patch.  A shared-memory hash table (one 64-bit entry = global
+// column, patch column; load factor <= 1/4, so a miss -- two thirds of the probes: the columns of a row that lie outside
+// the patch -- costs 1.4 probes) maps global column -> patch column.  A warp owns one output row at a time: it has four
+// 32-entry chunks of the CSR row (index + value) in flight per lane, drops the hits into a row buffer in shared memory and
+// streams the finished row out with coalesced evict-first stores (the blocks are written once and must not push the CSR
+// lines, which the neighbouring patches read again, out of L2), zeroing the buffer in the same pass.
+// kAccumulate = false: every row of the CSR has strictly increasing columns (checked once on the device when the operator
+// is set, ssc_csr_sorted_kernel), so a hit is a plain store; true: duplicates are summed with shared-memory atomics.
+// rowbuf_warps = 0: the patch is too large for row buffers; hits go straight to the zero-filled row in global memory.
 // ---------------------------------------------------------------------------------------------
+__global__ void ssc_csr_sorted_kernel(const ll *__restrict__ rowptr, const int *__restrict__ colidx, ll nrows, int *__restrict__ unsorted)
+{
+    // a warp per row: columns strictly increasing?
+    const ll warp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((ll)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    int bad = 0;
+    for (ll r = warp; r < nrows; r += nw) {
+        const ll a = rowptr[r], b = rowptr[r + 1];
+        for (ll k = a + 1 + lane; k < b; k += 32) bad |= colidx[k] <= colidx[k - 1];
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) *unsorted = 1;
+}
+
+template <bool kAccumulate>
 __global__ void __launch_bounds__(256)
 ssc_extract_kernel(const ll *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals,
-                   const int *__restrict__ gtol, double *__restrict__ blocks, int n, int ld, ll stride, ll count, int H)
+                   const int *__restrict__ gtol, double *__restrict__ blocks, int n, int ld, ll stride, ll count, int H, int rowbuf_warps)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int *keys = reinterpret_cast<int *>(smem_raw);
-    int *slotval = keys + H;
-    ll *rbeg = reinterpret_cast<ll *>(slotval + H);            // n: start of every patch row in the CSR arrays
-    int *rlen = reinterpret_cast<int *>(rbeg + n);            // n (+1 pad): its length
+    int2 *table = reinterpret_cast<int2 *>(smem_raw);           // H entries: (global column, patch column); x = -1: empty
+    ll *rbeg = reinterpret_cast<ll *>(table + H);               // n: start of every patch row in the CSR arrays
+    int *rlen = reinterpret_cast<int *>(rbeg + n);              // n (+1 pad): its length
     double *rowbuf = reinterpret_cast<double *>(rlen + ((n + 2) & ~1));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const bool buffered = rowbuf_warps > 0;
+    if (buffered) for (int t = tid; t < nwarps * ld; t += blockDim.x) rowbuf[t] = 0.0;
     for (ll p = blockIdx.x; p < count; p += gridDim.x) {
         const int *g = gtol + p * n;
-        for (int t = tid; t < H; t += blockDim.x) keys[t] = -1;
+        for (int t = tid; t < H; t += blockDim.x) table[t].x = -1;
         __syncthreads();
-        // one round of dependent loads for the whole patch: dof -> row extent; and the column hash
+        // one round of dependent loads for the whole patch: dof -> row extent; and the column table
         for (int t = tid; t < n; t += blockDim.x) {
             const int key = g[t];
             const ll a = rowptr[key];
@@ -30,45 +52,54 @@ ssc_extract_kernel(const ll *__restrict__ rowptr, const int *__restrict__ colidx
             rlen[t] = (int)(rowptr[key + 1] - a);
             unsigned s = hash_dof(key) & (H - 1);
             while (true) {
-                const int prev = atomicCAS(&keys[s], -1, key);
-                if (prev == -1 || prev == key) { slotval[s] = t; break; }
+                const int prev = atomicCAS(&table[s].x, -1, key);
+                if (prev == -1 || prev == key) { table[s].y = t; break; }
                 s = (s + 1) & (H - 1);
             }
         }
         __syncthreads();
         double *B = blocks + p * stride;
-        // a warp owns two output rows at a time: both rows' index/value loads are issued before either is consumed
-        double *rb0 = rowbuf + (2 * warp) * n, *rb1 = rb0 + n;
-        for (int i0 = 2 * warp; i0 < n; i0 += 2 * nwarps) {
-            const int i1 = i0 + 1;
-            const bool two = i1 < n;
-            for (int t = lane; t < n; t += 32) { rb0[t] = 0.0; rb1[t] = 0.0; }
-            __syncwarp();
-            const ll a0 = rbeg[i0], a1 = two ? rbeg[i1] : 0;
-            const int l0 = rlen[i0], l1 = two ? rlen[i1] : 0;
-            const int lmax = l0 > l1 ? l0 : l1;
-            for (int k = lane; k < lmax; k += 32) {
-                int c0 = -1, c1 = -1;
-                double v0 = 0.0, v1 = 0.0;
-                if (k < l0) { c0 = colidx[a0 + k]; v0 = vals[a0 + k]; }
-                if (k < l1) { c1 = colidx[a1 + k]; v1 = vals[a1 + k]; }
-                if (c0 >= 0) {
-                    unsigned s = hash_dof(c0) & (H - 1);
-                    int kk;
-                    while ((kk = keys[s]) != -1) { if (kk == c0) { atomicAdd(&rb0[slotval[s]], v0); break; } s = (s + 1) & (H - 1); }
+        double *rb = rowbuf + warp * ld;                       // entries n .. ld-1 stay zero
+        for (int i = warp; i < n; i += nwarps) {
+            const int len = rlen[i];
+            const int *ci = colidx + rbeg[i] + lane;            // 64-bit row start once, 32-bit offsets below
+            const double *va = vals + rbeg[i] + lane;
+            double *Brow = B + (ll)i * ld;
+            if (!buffered) {
+                for (int t = lane; t < ld; t += 32) Brow[t] = 0.0;
+                __syncwarp();
+            }
+            double *dst = buffered ? rb : Brow;
+            for (int k0 = lane; k0 < len + lane; k0 += 128) {   // uniform trip count; four chunks of the row in flight per lane
+                int c[4];
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool in = k0 + 32 * u < len;
+                    c[u] = in ? __ldg(ci + (k0 - lane) + 32 * u) : -1;
+                    v[u] = in ? __ldg(va + (k0 - lane) + 32 * u) : 0.0;
                 }
-                if (c1 >= 0) {
-                    unsigned s = hash_dof(c1) & (H - 1);
-                    int kk;
-                    while ((kk = keys[s]) != -1) { if (kk == c1) { atomicAdd(&rb1[slotval[s]], v1); break; } s = (s + 1) & (H - 1); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (c[u] < 0) continue;
+                    unsigned s = hash_dof(c[u]) & (H - 1);
+                    int2 e = table[s];
+                    while (e.x != c[u] && e.x != -1) { s = (s + 1) & (H - 1); e = table[s]; }
+                    if (e.x == c[u]) {
+                        if (kAccumulate) atomicAdd(dst + e.y, v[u]);
+                        else dst[e.y] = v[u];
+                    }
                 }
             }
-            __syncwarp();
-            for (int t = lane; t < ld; t += 32) {
-                B[(ll)i0 * ld + t] = t < n ? rb0[t] : 0.0;
-                if (two) B[(ll)i1 * ld + t] = t < n ? rb1[t] : 0.0;
+            if (buffered) {
+                __syncwarp();
+                for (int t = lane; t < ld; t += 32) {
+                    const double val = rb[t];
+                    rb[t] = 0.0;
+                    __stcs(Brow + t, val);
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
         __syncthreads();
     }

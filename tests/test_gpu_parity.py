@@ -511,3 +511,42 @@ def test_released_operator_cannot_be_set_up_again():
     pc.apply(x, y2)
     free = np.setdiff1d(np.arange(x.size), disc.global_bc_nodes)
     assert relerr(2.0 * y2[free], y[free]) < 1e-13
+
+
+@pytest.mark.parametrize("row_buffers", [-1, 2, 0])
+@pytest.mark.parametrize("mode", ["sorted", "unsorted", "duplicates"])
+def test_extract_from_unsorted_and_duplicated_csr(mode, row_buffers):
+    """The extract kernel stores a hit when every CSR row has strictly increasing columns (checked on the device when the
+    operator is set) and accumulates otherwise: rows with shuffled columns, and rows whose entries are split into several
+    duplicates (what MatSetValues(ADD_VALUES) leaves before assembly compresses them), give the same blocks.  Row buffers in
+    shared memory (8 warps, fewer, or none: the path of very large patches) do not change the result."""
+    import scipy.sparse as sp
+    form, bcs, disc, A = _problem(plex.TensorPlex((3, 3, 3)), 3, "scalar")
+    o = make_oracle(disc, A)
+    indptr, indices, data = A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data.copy()
+    rng = np.random.default_rng(5)
+    if mode == "unsorted":
+        for r in range(A.shape[0]):
+            perm = rng.permutation(indptr[r + 1] - indptr[r]) + indptr[r]
+            indices[indptr[r]:indptr[r + 1]] = indices[perm]
+            data[indptr[r]:indptr[r + 1]] = data[perm]
+    elif mode == "duplicates":
+        # every entry split into two halves that are powers-of-two fractions (exactly summable), placed apart
+        rows = np.repeat(np.arange(A.shape[0]), np.diff(indptr))
+        rows2, cols2, vals2 = np.concatenate([rows, rows]), np.concatenate([indices, indices]), np.concatenate([0.25 * data, 0.75 * data])
+        order = np.lexsort((rng.permutation(rows2.size), rows2))
+        rows2, cols2, vals2 = rows2[order], cols2[order], vals2[order]
+        indptr = np.concatenate(([0], np.cumsum(np.bincount(rows2, minlength=A.shape[0])))).astype(np.int64)
+        indices, data = cols2.astype(np.int32), vals2
+    pc = make_gpu(form, bcs, ssc_keep_patch_operators=True, ssc_extract_row_buffers=row_buffers)
+    pc._compute_op = None
+    pc.setOperatorCSR(indptr, indices, data)
+    pc.setUp()
+    sizes = np.diff(pc.getPatches()[0])
+    for i in (int(np.argmax(sizes)), int(sizes.size // 2), 0):
+        if sizes[i]:
+            assert np.array_equal(pc.getPatchMatrix(i), o.patchMatrix(i))
+    x = rhs_vector(disc.total_dofs)
+    y = np.zeros_like(x)
+    pc.apply(x, y)
+    assert relerr(y, o.apply(x)) < TOL
