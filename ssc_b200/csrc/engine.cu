@@ -99,6 +99,8 @@ struct SizeClass {
     i64 poff = 0, pstride = 0;    // packed-symmetric storage: class offset and per-patch stride (doubles)
     unsigned pbytes = 0;          // bytes of one packed triangle moved by the bulk copy
     int tp = 0, ppb = 0;          // apply launch shape
+    bool refine = false;          // -ssc_sub_solve: this class is applied with one step of iterative refinement against the kept operators
+    double kappa = 0.0;           // largest ||B||_1 ||B^-1||_inf of the class (computed when -ssc_sub_solve is refine or auto)
 };
 
 struct SSCPatchPC_s {
@@ -119,6 +121,10 @@ struct SSCPatchPC_s {
     bool save_operators = true, partition_of_unity = false, multiplicative = false, print_patches = false;
     bool symmetrise_sweep = false, keep_operators = false, dim_set = false, codim_set = false;
     int sub_pc = SSC_SUB_LU;
+    int sub_solve = 0;            // -ssc_sub_solve: 0 inverse (stored-inverse product), 1 refine (+ one refinement step, every class), 2 auto (refine where kappa > refine_kappa)
+    int refine_steps = 1;         // -ssc_refine_steps: refinement steps of a refined class (each contracts the error by ||I - S B||)
+    double refine_kappa = 1.0e3;  // -ssc_refine_kappa: threshold of auto (kappa * eps = 2e-13 there)
+    unsigned long long *d_kappa = nullptr;
     int factor_ctas = 0;          // concurrent CTAs of the blocked factor kernel (0 = fill the SMs)
     int factor_panel = 16;        // panel width of the blocked factor kernel (16 or 32)
     int factor_variant = -1;      // -1 (default) by size: n <= 96 register tiles (1), 97..128 register-resident DMMA accumulators with look-ahead (2), larger blocked DMMA on the
