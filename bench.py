@@ -538,6 +538,23 @@ def main():
         e2e = {"value": nglobal / (ems * 1e-3), "unit": "dofs/s", "h2d_bytes_per_step": 8 * nowned, "d2h_bytes_per_step": 8 * nowned,
                "ms_per_step": ems, "api": "ssc_b200.PC.apply(x, y) on pinned host vectors (SSCPatchApply, SSC_MEM_HOST)", "cpus_bound_near_gpu": ncpus_bound}
 
+    # ---- the same with PAGEABLE caller vectors (what a PETSc Vec hands over): the library page-locks them on first use ----
+    e2e_pageable = None
+    if not args.no_e2e:
+        xp, yp = np.array(xh.array), np.empty(nowned)
+        for _ in range(args.warmup):
+            pc.apply(xp, yp)
+        barrier()
+        pc.eventRecord(e0)
+        for _ in range(args.steps):
+            pc.apply(xp, yp)
+        pc.eventRecord(e1)
+        pms = _max_over_ranks(dist, pc.eventElapsed(e0, e1), nranks) / args.steps
+        barrier()
+        e2e_pageable = {"value": nglobal / (pms * 1e-3), "unit": "dofs/s", "ms_per_step": pms, "host_vectors_registered": pc.size("host_vectors_registered"),
+                        "max_abs_diff_vs_pinned": float(np.abs(yp - yh.array).max()),
+                        "api": "ssc_b200.PC.apply(x, y) on plain numpy (pageable) vectors; cudaHostRegister on first use, cached by address"}
+
     # ---- multi-rank parity leg: the oracle on the patches around every rank interface -----------------------
     parity = None
     if nranks > 1 and args.workload == "poisson_hex" and not args.no_parity:
@@ -600,6 +617,8 @@ def main():
            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "setup": setup, "symmetry_check": symmetry}
     if parity is not None:
         out["parity"] = parity
+    if e2e_pageable is not None:
+        out["e2e_pageable"] = e2e_pageable
     if flush:
         out["config"]["l2"] = "working set %.2f GB: L2 flushed (256 MB write) before every timed step, each step timed on its own" % (pc.size("block_bytes") / 1e9)
     if nranks == 1 and not args.no_spd_packed and args.workload == "poisson_hex" and not elements:

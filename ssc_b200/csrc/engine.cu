@@ -246,6 +246,11 @@ struct SSCPatchPC_s {
         int nsend_pieces = 0, nghost_slabs = 0;
     } pp;
     std::vector<cudaEvent_t> ev_in, ev_k;
+    // caller's host vectors page-locked on first use (a PETSc Vec's array is pageable: without this the asynchronous copies of the
+    // host-space apply are staged and serialised by the driver and the slab overlap is lost)
+    bool register_host = true;       // -ssc_register_host_vectors
+    std::vector<std::pair<const void *, size_t>> host_reg;
+    i64 host_reg_count = 0;
     // timing
     std::map<std::string, double> event_ms;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

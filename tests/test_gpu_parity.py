@@ -638,3 +638,33 @@ def test_refined_sub_solve_on_the_p_sweep(p):
         assert entry_err(y, ref, o.applyScale(x)) < TOL
         errs[mode] = float(np.abs(y - truth).max() / np.abs(truth).max())
     assert errs["refine"] < 1e-15 and errs["refine"] <= errs["inverse"] * 1.01, errs
+
+
+def test_pageable_host_vectors_are_registered_once_and_give_the_same_result():
+    """Host-space applies on plain numpy (pageable) vectors, the kind a PETSc Vec hands over: the library page-locks them
+    on first use (cached by address), results equal those from pinned vectors; -ssc_register_host_vectors false leaves
+    them alone; after reset the vectors are usable as ordinary memory again."""
+    from ssc_b200 import PinnedArray
+    form, bcs, disc, A = _problem(plex.TensorPlex((20, 16, 16)), 3, "scalar")
+    assert disc.total_dofs * 8 > (1 << 20)
+    o = make_oracle(disc, A)
+    x = rhs_vector(disc.total_dofs)
+    ref = o.apply(x)
+    for reg in (True, False):
+        pc = make_gpu(form, bcs, ssc_host_pipeline=-4, ssc_register_host_vectors=reg)
+        pc.setUp()
+        xs = [x.copy(), x.copy()]
+        ys = [np.empty_like(x), np.empty_like(x)]
+        for rep in range(3):
+            for xv, yv in zip(xs, ys):
+                yv[:] = np.nan
+                pc.apply(xv, yv)
+                assert relerr(yv, ref) < TOL
+        assert pc.size("host_vectors_registered") == (4 if reg else 0)
+        xh, yh = PinnedArray(pc, x.size), PinnedArray(pc, x.size)
+        xh.array[:] = x
+        pc.apply(xh.array, yh.array)
+        assert relerr(yh.array, ys[0]) < 1e-14
+        pc.reset()
+        xs[0][:] = 0.0                           # plain memory again
+        del pc
