@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-setup-serial", action="store_true", help="CPU baseline: factorise the window's patch operators on one core too (the reference's set-up is serial per rank); adds ~10 s")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak (default): --cells^3 per GPU; strong: ONE --cells^3 mesh split over the GPUs")
+    ap.add_argument("--partition", default="slab", choices=["slab", "brick"], help="multi-GPU partition: x-slabs (default) or bricks (2x1x1, 2x2x1, 2x2x2)")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-rank parity leg (oracle on the patches around every rank interface)")
     ap.add_argument("--apply-variant", type=int, default=None, help="ssc_apply_variant (kernel selection; default = library default)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo exchange: NVLink peer memory (default) or NCCL send/recv")
@@ -146,7 +148,10 @@ def build_problem(args, rank, nranks):
         disc = fem.Discretisation([V])
         slab = None
     else:
-        slab = partition.XSlab((c * nranks, c, c), p, rank, nranks)   # cut along the slowest axis: interface dofs contiguous at the ends
+        # slabs are cut along x, the slowest axis of the numbering: a rank's interface dofs are contiguous at the ends of its vectors
+        grid = {"slab": (nranks, 1, 1), "brick": {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(nranks, (nranks, 1, 1))}[args.partition]
+        cells = (c, c, c) if args.scaling == "strong" else tuple(c * g for g in grid)
+        slab = partition.Brick(cells, p, rank, grid)
         V, disc = slab.space, slab.discretisation
     info = {"t_mesh": time.time() - t0}
     return V, disc, slab, info
@@ -259,22 +264,22 @@ def interface_parity(args, dist, rank, nranks, slab, x_owned, results):
     """Multi-rank parity against the CPU oracle (SCALE runs prove the halo fill and the overlap sum themselves).
 
     The reference's contract across ranks is exactness of SFBcast / SFReduce (ssc/libssc.c:1323-1324, :1399-1400): the
-    result must not depend on the partition.  For every rank interface (vertex plane k = r * cells of the global
-    (cells * N, cells, cells) mesh) rank 0 builds the 6-cell-thick sub-mesh [k-3, k+3) x cells x cells on its own, runs
-    the oracle (its own dof lists, its own LU solves) on it with the global input restricted to it, and compares every
-    dof whose patches all lie within two cells of the interface (vertex planes k-2 .. k+2: their stars are complete inside
-    the sub-mesh, so their patch problems are those of the global mesh) -- owned dofs of both neighbours, dofs that
-    were ghosts on one side, and the overlap sums in between.  `results` maps a label to this rank's owned result
-    vector (device-resident apply, host-space apply)."""
-    c, p = args.cells, args.degree
+    result must not depend on the partition.  For every plane at which the partition cuts the mesh (vertex plane k along
+    axis a: slabs have N - 1 of them, 2 x 2 x 2 bricks three) rank 0 builds the 6-cell-thick window [k-3, k+3) across the
+    whole mesh on its own, runs the oracle (its own dof lists, its own LU solves) on it with the global input restricted
+    to it, and compares every dof whose patches all lie within two cells of the cut (vertex planes k-2 .. k+2: their
+    stars are complete inside the window, so their patch problems are those of the global mesh) -- owned dofs of all
+    ranks meeting there, dofs that were ghosts on some of them, and the overlap sums in between.  `results` maps a label
+    to this rank's owned result vector (device-resident apply, host-space apply)."""
+    p = args.degree
     gshape = slab.global_shape
-    plane = gshape[1] * gshape[2]
+    gcells = tuple((g - 1) // p for g in gshape)
+    cuts = [(a, k) for a in range(3) for k in slab.cuts[a]]
     gid = np.asarray(slab.global_ids[:slab.nowned])
-    X = gid // plane
+    XYZ = np.unravel_index(gid, gshape)
     sel = np.zeros(gid.size, dtype=bool)
-    for r in range(1, nranks):
-        k = r * c
-        sel |= (X >= (k - 3) * p) & (X <= (k + 3) * p)
+    for a, k in cuts:
+        sel |= (XYZ[a] >= (k - 3) * p) & (XYZ[a] <= (k + 3) * p)
     mine = {"gid": gid[sel], "x": np.asarray(x_owned)[sel]}
     for name, y in results.items():
         mine[name] = np.asarray(y)[sel]
@@ -289,36 +294,47 @@ def interface_parity(args, dist, rank, nranks, slab, x_owned, results):
     if np.any(np.diff(allg) == 0):
         raise SystemExit("interface parity: a dof is owned by two ranks")
     vals = {name: np.concatenate([q[name] for q in parts])[order] for name in ["x"] + list(results)}
-    h = 1.0 / c
-    mesh = plex.TensorPlex((6, c, c), lengths=(6 * h, c * h, c * h))
-    V = fem.FunctionSpace(mesh, p)
-    disc = fem.Discretisation([V])
-    csr = synth.tensor_poisson_csr(V, disc.ghost_bc_nodes)
-    L = np.indices(V.lattice_shape).reshape(3, -1)
-    node = V.lattice_node.ravel()
-    o = oracle.OraclePatchPC()
-    o.setFromDiscretisation(disc)
-    o.setOptions()
-    o.setUpPatches()
-    o.setOperatorCSRArrays(*csr)
+    h = slab.h
     nth = os.cpu_count() or 1
-    o.setUpOperators(nthreads=nth)            # the sub-meshes of all interfaces are congruent: one set of oracle factors serves them all
-    out = {"interfaces": nranks - 1, "dofs_checked": 0, "patches_per_interface": int(5 * (c + 1) ** 2),
-           "method": "CPU oracle on the 6-cell sub-mesh around every rank interface; dofs whose patches all lie within two cells of it"}
+    windows = {}                                   # window shape -> (oracle, V, lattice indices, node numbers): congruent windows share one set of oracle factors
+
+    def window(shape):
+        if shape not in windows:
+            mesh = plex.TensorPlex(shape, lengths=tuple(c * h for c in shape))
+            V = fem.FunctionSpace(mesh, p)
+            disc = fem.Discretisation([V])
+            synth.set_threads(nth)
+            csr = synth.tensor_poisson_csr(V, disc.ghost_bc_nodes)
+            o = oracle.OraclePatchPC()
+            o.setFromDiscretisation(disc)
+            o.setOptions()
+            o.setUpPatches()
+            o.setOperatorCSRArrays(*csr)
+            o.setUpOperators(nthreads=nth)
+            windows[shape] = (o, V, np.indices(V.lattice_shape).reshape(3, -1), V.lattice_node.ravel())
+        return windows[shape]
+    out = {"cut_planes": len(cuts), "dofs_checked": 0, "patches_checked": 0,
+           "method": "CPU oracle on the 6-cell window around every plane at which the partition cuts the mesh; dofs whose patches all lie within two cells of it"}
     worst = {name: 0.0 for name in results}
     worst_entry = {name: 0.0 for name in results}
-    for r in range(1, nranks):
-        k = r * c
-        g = np.ravel_multi_index((L[0] + (k - 3) * p, L[1], L[2]), gshape)
+    for a, k in cuts:
+        if k < 3 or k + 3 > gcells[a]:
+            raise SystemExit("interface parity: cut plane %d along axis %d is closer than 3 cells to the mesh boundary" % (k, a))
+        others = [b for b in range(3) if b != a]
+        o, V, L, node = window((6, gcells[others[0]], gcells[others[1]]))
+        G = [None, None, None]
+        G[a], G[others[0]], G[others[1]] = L[0] + (k - 3) * p, L[1], L[2]
+        g = np.ravel_multi_index(tuple(G), gshape)
         pos = np.searchsorted(allg, g)
         if np.any(pos >= allg.size) or np.any(allg[np.minimum(pos, allg.size - 1)] != g):
-            raise SystemExit("interface parity: the ranks did not deliver every dof around interface %d" % r)
+            raise SystemExit("interface parity: the ranks did not deliver every dof around cut plane %d of axis %d" % (k, a))
         xs = np.empty(V.node_count)
         xs[node] = vals["x"][pos]
         yo = o.apply(xs, nthreads=nth)
         scale = o.applyScale(xs)
         good = node[(L[0] >= p) & (L[0] <= 5 * p)]
         out["dofs_checked"] += int(good.size)
+        out["patches_checked"] += int(5 * (gcells[others[0]] + 1) * (gcells[others[1]] + 1))
         for name in results:
             yg = np.empty(V.node_count)
             yg[node] = vals[name][pos]
@@ -354,7 +370,7 @@ def run_reference(args, rank, nranks):
     # dofs/s of the host cores does not depend on how many slabs the job has: at N GPUs the same throughput is quoted for
     # the N-times larger problem (the whole box's cores were already used for one slab), and a step takes N times longer
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "dofs/s", "n_gpus": args.gpus, "steps": len(vals),
-           "warmup": args.warmup, "ms_per_step": (args.cells * args.degree + 1) ** 3 * nranks / v * 1e3, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": (args.cells * args.degree + 1) ** 3 * (1 if args.scaling == "strong" else nranks) / v * 1e3, "higher_is_better": True, "scaling": args.scaling,
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": workload_config(args, nranks),
            "cpu_baseline": dict(base, value=v),
@@ -369,11 +385,16 @@ def workload_config(args, nranks):
         return {"workload": "3D linear elasticity, vector P2 on %dx%dx%d cubes split into tets, vertex-star patches (n = 45 interior), additive" % (c, c, c),
                 "cells_per_gpu": 6 * c ** 3, "degree": 2, "parallelism": "single GPU", "exchange": None,
                 "l2": "L2 flushed between timed steps" }
-    return {"workload": "3D Q%d Poisson, %dx%dx%d hex cells%s, vertex-star patches, additive, stored inverse (sub_pc_type lu)"
-                        % (p, c * nranks, c, c, " (x-slabs of %d^3 per GPU)" % c if nranks > 1 else ""),
-            "cells_per_gpu": c ** 3, "degree": p, "parallelism": "patches by mesh slab x%d" % nranks, "exchange": getattr(args, "exchange_used", None),
+    strong = args.scaling == "strong" and nranks > 1
+    grid = {"slab": (nranks, 1, 1), "brick": {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(nranks, (nranks, 1, 1))}[args.partition]
+    cells = (c, c, c) if strong or nranks == 1 else tuple(c * g for g in grid)
+    per_gpu = c ** 3 // nranks if strong else c ** 3
+    note = "" if nranks == 1 else " (%s %dx%dx%d, %s)" % ("x-slabs" if args.partition == "slab" else "bricks", grid[0], grid[1], grid[2],
+                                                         "one mesh split over the GPUs" if strong else "%d^3 per GPU" % c)
+    return {"workload": "3D Q%d Poisson, %dx%dx%d hex cells%s, vertex-star patches, additive, stored inverse (sub_pc_type lu)" % (p, cells[0], cells[1], cells[2], note),
+            "cells_per_gpu": per_gpu, "degree": p, "parallelism": "patches by mesh %s %dx%dx%d" % (args.partition, grid[0], grid[1], grid[2]), "exchange": getattr(args, "exchange_used", None),
             "operator": "assembled CSR -> extract kernel" if args.operator == "csr" else "one shared element matrix -> assemble kernel (no CSR)",
-            "l2": "inputs larger than L2 (patch blocks %.1f GB per GPU), no flush" % (8 * ((2 * p - 1) ** 3) ** 2 * (c - 1) ** 3 / 1e9)}
+            "l2": "inputs larger than L2 (patch blocks %.1f GB per GPU), no flush" % (8 * ((2 * p - 1) ** 3) ** 2 * (c - 1) ** 3 / 1e9 / (nranks if strong else 1))}
 
 
 def main():
@@ -562,6 +583,7 @@ def main():
         if e2e is not None:
             res["host_vectors"] = np.array(yh.array)
         parity = interface_parity(args, dist, rank, nranks, slab, xh.array, res)
+        dist.barrier()          # rank 0 spent seconds in the oracle: the neighbour barriers of the next applies spin for 4 s at most
 
     # size-independent property at full size (all N): the additive operator is symmetric for an SPD problem, so
     # <M a, b> == <a, M b> over the whole (distributed) vector; a broken halo fill or overlap sum breaks it
@@ -611,10 +633,12 @@ def main():
                 "traffic": traffic, "kernel": "ssc_apply_pipe_kernel<1,8> (+ ssc_apply_stream_kernel<8> for the small classes: all size-class launches of one apply; traffic = ncu capture of the dominant launch)", "kernel_ms": kernel_ms,
                 "algorithmic_bytes": bytes_apply, "stream_read_gbs_this_gpu": read_peak, "frac_of_stream_read": achieved / read_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
     out = {"metric": METRIC if args.workload == "poisson_hex" else "PCApply dofs/s (3D vector P2 elasticity on tets, vertex-star patches, additive, fp64)", "value": nglobal / (ms_step * 1e-3), "unit": "dofs/s", "n_gpus": nranks, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling if nranks > 1 else "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(args, nranks),
            "dofs": nglobal, "patches_per_gpu": pc.size("npatch"), "hbm_gbs_step": bytes_apply * nranks / (ms_step * 1e-3) / 1e9,
            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "setup": setup, "symmetry_check": symmetry}
+    if nranks > 1:
+        out["exchange_ms_per_apply"] = ms_step - kernel_ms      # halo push, the two neighbour barriers and the fold: whatever of a step is not the patch kernels (rank 0's kernels, max-over-ranks step)
     if parity is not None:
         out["parity"] = parity
     if e2e_pageable is not None:

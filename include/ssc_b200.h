@@ -197,8 +197,12 @@ int SSCEventDestroy(SSCPatchPC pc, void *ev);
 
 /* ---- low-order (P1) coarse correction, SURVEY.md 8(f) N1: class P1PC of ssc/lo.py:105-198 ------------------ */
 /* y = R^T A1^{-1} R x with Dirichlet values carried over.  The host assembles R (ssc/lo.py:83-102) and the coarse
- * operator A1 (ssc/lo.py:142-144); the device does the two sparse products and the coarse solve (dense LU: coarse
- * spaces up to 3000 dofs in this build).  Option names: lo_ksp_type (preonly), lo_pc_type (lu | cholesky), lo_mat_type. */
+ * operator A1 (ssc/lo.py:142-144); the device does the two sparse products and the coarse solve.  The reference hands A1 to
+ * the KSP/PC its options name (ssc/lo.py:164-166); here, under the same option names:
+ *   lo_ksp_type preonly + lo_pc_type lu | cholesky : dense factorisation on the device, coarse spaces up to 4096 dofs;
+ *   lo_ksp_type cg + lo_pc_type jacobi [lo_ksp_rtol 1e-10, lo_ksp_max_it 10000] : device-resident preconditioned conjugate
+ *       gradients on the coarse CSR operator, any size (the Q1 space of a 64^3 mesh has 274 625 dofs).
+ * lo_mat_type is accepted and ignored. */
 typedef struct SSCLowOrderPC_s *SSCLowOrderPC;
 int SSCLowOrderCreate(int device, SSCLowOrderPC *lo);                       /* P1PC.__init__            ssc/lo.py:107-110 */
 int SSCLowOrderDestroy(SSCLowOrderPC *lo);
@@ -210,6 +214,9 @@ int SSCLowOrderSetOperator(SSCLowOrderPC lo, SSCInt n, const SSCInt *rowptr, con
 int SSCLowOrderSetBcs(SSCLowOrderPC lo, SSCInt nbc, const SSCInt *bcIndices);      /* bc_indices        ssc/lo.py:175-183 */
 int SSCLowOrderSetUp(SSCLowOrderPC lo);                                     /* initialize / update      ssc/lo.py:112-186 */
 int SSCLowOrderApply(SSCLowOrderPC lo, const double *x, double *y, int memspace);  /* apply             ssc/lo.py:187-198 */
+int SSCLowOrderGetIterations(SSCLowOrderPC lo, SSCInt *last, SSCInt *total, SSCInt *solves);   /* coarse CG iterations (KSPGetIterationNumber of the lo KSP) */
+int SSCLowOrderAXPY(SSCLowOrderPC lo, SSCInt n, double a, const double *x, double *y);  /* device y += a x on the coarse PC's stream: the additive PCCOMPOSITE of ssc/ssc.py:38-49 */
+int SSCLowOrderSynchronize(SSCLowOrderPC lo);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,9 @@ _sigs = {
     "SSCLowOrderSetBcs": [_H, C.c_int64, i64p],
     "SSCLowOrderSetUp": [_H],
     "SSCLowOrderApply": [_H, C.c_void_p, C.c_void_p, C.c_int],
+    "SSCLowOrderGetIterations": [_H, i64p, i64p, i64p],
+    "SSCLowOrderAXPY": [_H, C.c_int64, C.c_double, C.c_void_p, C.c_void_p],
+    "SSCLowOrderSynchronize": [_H],
 }
 EXPORTS = sorted(_sigs) + ["SSCGetLastError"]
 for _name, _args in _sigs.items():

@@ -28,8 +28,12 @@
 #pragma once
 #include "kernels_common.cuh"
 
+#ifndef SSC_DMMA_PROBE
+#define SSC_DMMA_PROBE 0        // tools/micro/factor_probe.cu: 1 skips the tensor-core updates, 2 the panel steps (timing experiments only)
+#endif
 __device__ __forceinline__ void ssc_dmma_acc(double2 &c, double a, double b)
 {
+    if (SSC_DMMA_PROBE == 1) return;
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
 }
@@ -208,7 +212,7 @@ ssc_invert_dmma_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, l
                 bool bad = false;
 #pragma unroll
                 for (int s = 0; s < NB; ++s) {
-                    if (s >= bw) break;
+                    if (s >= bw || SSC_DMMA_PROBE == 2) break;
                     const int cur = s & 1;
                     ssc_nbar_sync(B4, 32 * G);
                     int prow = kb + s;

@@ -62,3 +62,103 @@ __global__ void ssc_spmv_kernel(ll nrows, const ll *__restrict__ rowptr, const i
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if (lane == 0) y[warp] = s;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Coarse solve of the low-order PC for coarse spaces too large for a dense factorisation (ssc/lo.py:141-166 hands the P1
+// operator to whatever PETSc solver the options name): Jacobi-preconditioned conjugate gradients, device-resident.
+// Three kernels per iteration, no host round trip inside: the scalars (r.z, p.Ap, r.r) live in device memory, double-
+// buffered by iteration parity b so that a kernel never zeroes an accumulator another kernel of the same iteration reads:
+//   k1(b): q = A p;  pq[b] += p.q;                        zeroes rz[b^1], rr[b^1]  (accumulated by k2(b))
+//   k2(b): alpha = rz[b]/pq[b];  x += alpha p;  r -= alpha q;  z = r/diag;  rz[b^1] += r.z;  rr[b^1] += r.r
+//   k3(b): beta = rz[b^1]/rz[b];  p = z + beta p;         zeroes pq[b^1]
+// s = {rz[2], pq[2], rr[2]}.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_sum_atomic(double v, double *dst)
+{
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd(dst, v);
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(256)
+ssc_cg_spmv_kernel(ll n, const ll *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals,
+                   const double *__restrict__ p, double *__restrict__ q, double *__restrict__ s, int b)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) { s[b ^ 1] = 0.0; s[4 + (b ^ 1)] = 0.0; }
+    const int lane = threadIdx.x & 31;
+    const ll nw = ((ll)gridDim.x * blockDim.x) >> 5;
+    double part = 0.0;
+    for (ll row = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += nw) {
+        double a = 0.0;
+        for (ll k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) a = fma(vals[k], __ldg(p + colidx[k]), a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+        if (lane == 0) { q[row] = a; part = fma(a, p[row], part); }
+    }
+    block_sum_atomic(part, s + 2 + b);
+}
+__global__ void __launch_bounds__(256)
+ssc_cg_update_kernel(ll n, const double *__restrict__ dinv, const double *__restrict__ p, const double *__restrict__ q,
+                     double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, double *__restrict__ s, int b)
+{
+    const double pq = s[2 + b];
+    const double alpha = pq != 0.0 ? s[b] / pq : 0.0;
+    double rz = 0.0, rr = 0.0;
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) {
+        x[i] = fma(alpha, p[i], x[i]);
+        const double ri = fma(-alpha, q[i], r[i]);
+        const double zi = ri * dinv[i];
+        r[i] = ri; z[i] = zi;
+        rz = fma(ri, zi, rz); rr = fma(ri, ri, rr);
+    }
+    block_sum_atomic(rz, s + (b ^ 1));
+    block_sum_atomic(rr, s + 4 + (b ^ 1));
+}
+__global__ void __launch_bounds__(256)
+ssc_cg_direction_kernel(ll n, const double *__restrict__ z, double *__restrict__ p, double *__restrict__ s, int b)
+{
+    const double rz = s[b];
+    const double beta = rz != 0.0 ? s[b ^ 1] / rz : 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) s[2 + (b ^ 1)] = 0.0;
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) p[i] = fma(beta, p[i], z[i]);
+}
+// start: x = 0, r = rhs, z = r/diag, p = z, rz[0] = r.z, rr[0] = r.r  (s zeroed by the caller)
+__global__ void __launch_bounds__(256)
+ssc_cg_start_kernel(ll n, const double *__restrict__ dinv, const double *__restrict__ rhs, double *__restrict__ x, double *__restrict__ r,
+                    double *__restrict__ z, double *__restrict__ p, double *__restrict__ s)
+{
+    double rz = 0.0, rr = 0.0;
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) {
+        const double ri = rhs[i], zi = ri * dinv[i];
+        x[i] = 0.0; r[i] = ri; z[i] = zi; p[i] = zi;
+        rz = fma(ri, zi, rz); rr = fma(ri, ri, rr);
+    }
+    block_sum_atomic(rz, s + 0);
+    block_sum_atomic(rr, s + 4);
+}
+// 1 / diagonal of a CSR matrix (a warp per row)
+__global__ void ssc_csr_inv_diag_kernel(ll n, const ll *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals, double *__restrict__ dinv)
+{
+    const ll row = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double d = 0.0;
+    for (ll k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) if (colidx[k] == row) d += vals[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
+    if (lane == 0) dinv[row] = d != 0.0 ? 1.0 / d : 0.0;
+}
+// y += a x
+__global__ void ssc_axpy_kernel(ll n, double a, const double *__restrict__ x, double *__restrict__ y)
+{
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) y[i] = fma(a, x[i], y[i]);
+}

@@ -12,7 +12,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from . import fem, petsc_lite
-from ._lib import CHKERR, MEM_HOST, as_i64, dp, ip, lib
+from ._lib import CHKERR, MEM_DEVICE, MEM_HOST, as_i64, dp, ip, lib
 from .patch import PCBase, _form_and_bcs
 
 
@@ -96,6 +96,22 @@ class LowOrderCore(object):
     def setUp(self):
         CHKERR(lib.SSCLowOrderSetUp(self.handle))
 
+    def applyDevice(self, dx, dy):
+        """Device-resident apply (DeviceVec in, DeviceVec out), asynchronous on the coarse PC's stream."""
+        CHKERR(lib.SSCLowOrderApply(self.handle, dx.ptr, dy.ptr, MEM_DEVICE))
+
+    def axpyDevice(self, a, dx, dy):
+        CHKERR(lib.SSCLowOrderAXPY(self.handle, C.c_int64(dx.n), C.c_double(a), dx.ptr, dy.ptr))
+
+    def synchronize(self):
+        CHKERR(lib.SSCLowOrderSynchronize(self.handle))
+
+    def iterations(self):
+        """(last, total, solves) of the coarse CG (zeros with the dense coarse factorisation)."""
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        CHKERR(lib.SSCLowOrderGetIterations(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def apply(self, x, y):
         xa = x if isinstance(x, np.ndarray) else x.array
         ya = y if isinstance(y, np.ndarray) else y.array
@@ -127,7 +143,7 @@ class P1PC(PCBase):
         prefix = pc.getOptionsPrefix() or ""
         opts = petsc_lite.Options(prefix)
         self.lo = LowOrderCore(self.device)
-        for name in ("lo_mat_type", "lo_ksp_type", "lo_pc_type"):    # ssc/lo.py:141, :164-166
+        for name in ("lo_mat_type", "lo_ksp_type", "lo_pc_type", "lo_ksp_rtol", "lo_ksp_max_it"):    # ssc/lo.py:141, :164-166
             if opts.hasName(name):
                 self.lo.setOption(name, opts.getString(name))
         self.lo.setRestriction(restriction_matrix(J.spaces, lo_J.spaces, disc.ghost_bc_nodes, lo_disc.ghost_bc_nodes))

@@ -12,35 +12,44 @@ from . import fem, plex
 from .plex import IntType
 
 
-class Slab(object):
-    """Rank ``rank`` of ``nranks`` slabs of a structured (cx, cy, cz) box of tensor cells, degree p, cut along ``axis``.
+class Brick(object):
+    """Rank ``rank`` of a ``grid = (gx, gy, gz)`` brick partition of a structured (cx, cy, cz) box of tensor cells, degree p.
 
-    Vertex planes are dealt out in contiguous ranges; the local mesh holds every cell that touches an owned
-    vertex.  Local dofs are numbered owned first, then ghosts.  ``global_ids`` maps local node -> node of the
-    global lattice (used only to match ghosts with their owners at set-up).
-
-    ``axis = 0`` (the slowest axis of the cell, patch and dof numbering) keeps a rank's interface dofs and the patches
-    that touch ghosts contiguous at the two ends of its numbering -- what the overlapped host-space apply wants;
-    ``axis = 2`` scatters them through the whole numbering (every x-range of the slab touches the interface).
+    Vertex planes are dealt out in contiguous ranges along every axis; a rank owns the vertices of its index box and
+    every mesh entity whose lowest vertex it owns, builds patches only around owned vertices (ssc/libssc.c:500-521), and
+    its local mesh holds every cell that touches an owned vertex (one layer of vertex overlap,
+    tests/test_jacobi_equivalent.py:9).  Local dofs are numbered owned first, then ghosts.  ``global_ids`` maps local
+    node -> node of the global lattice (used only to match ghosts with their owners at set-up).  Ranks are numbered with
+    the last axis fastest.  A 2 x 2 x 2 grid gives every rank 7 neighbours (faces, edges, the corner); slabs are the
+    special case of a grid that is 1 along two axes.
     """
 
-    def __init__(self, cells, p, rank, nranks, axis=2):
+    def __init__(self, cells, p, rank, grid):
         cells = tuple(int(c) for c in cells)
-        ca = cells[axis]
-        k0 = rank * ca // nranks
-        k1 = (rank + 1) * ca // nranks if rank < nranks - 1 else ca + 1     # owned vertex planes [k0, k1)
-        lo, hi = max(k0 - 1, 0), min(k1 - 1, ca - 1)                        # local cell layers [lo, hi]
-        nl = hi - lo + 1
-        h = 1.0 / cells[(axis + 1) % 3]
-        local = list(cells)
-        local[axis] = nl
+        grid = tuple(int(g) for g in grid)
+        nranks = int(np.prod(grid))
+        if not 0 <= rank < nranks:
+            raise ValueError("rank %d outside the %s grid" % (rank, grid))
+        coord = np.unravel_index(rank, grid)
+        lo, own_lo, own_hi, local = [], [], [], []
+        for a in range(3):
+            ca, ga, ra = cells[a], grid[a], int(coord[a])
+            if ga > ca:
+                raise ValueError("more ranks than cell layers along axis %d" % a)
+            k0 = ra * ca // ga
+            k1 = (ra + 1) * ca // ga if ra < ga - 1 else ca + 1       # owned vertex planes [k0, k1)
+            l, h = max(k0 - 1, 0), min(k1 - 1, ca - 1)                  # local cell layers [l, h]
+            lo.append(l); local.append(h - l + 1); own_lo.append(k0 - l); own_hi.append(k1 - 1 - l)
+        h = 1.0 / min(cells)                                        # cubic cells whose size does not depend on the partition
+        self.h = h
         mesh = plex.TensorPlex(tuple(local), lengths=tuple(c * h for c in local))
-        mesh.mark_ghost_vertices(axis, k0 - lo, k1 - 1 - lo)
+        mesh.mark_ghost_box(own_lo, own_hi)
         V = fem.FunctionSpace(mesh, p)
-        self.mesh, self.space, self.rank, self.nranks, self.axis = mesh, V, rank, nranks, axis
+        self.mesh, self.space, self.rank, self.nranks, self.grid, self.coord = mesh, V, rank, nranks, grid, tuple(int(c) for c in coord)
         self.nowned = V.owned_node_count
         L = list(np.indices(V.lattice_shape).reshape(3, -1))
-        L[axis] = L[axis] + p * lo
+        for a in range(3):
+            L[a] = L[a] + p * lo[a]
         gshape = tuple(p * c + 1 for c in cells)
         gid = np.ravel_multi_index(tuple(L), gshape)
         self.global_ids = np.empty(V.node_count, dtype=IntType)
@@ -51,6 +60,23 @@ class Slab(object):
         bc_nodes = np.sort(V.lattice_node.ravel()[onb])
         self.discretisation = fem.Discretisation([V], bc_nodes=[bc_nodes], owned_nodes=[self.nowned])
         self.global_shape = gshape
+        # vertex planes at which this partition cuts the mesh, per axis (the first plane owned by every rank but the first)
+        self.cuts = tuple(tuple(r * cells[a] // grid[a] for r in range(1, grid[a])) for a in range(3))
+
+
+class Slab(Brick):
+    """Rank ``rank`` of ``nranks`` slabs cut along ``axis``: a Brick partition with a grid that is 1 along the other axes.
+
+    ``axis = 0`` (the slowest axis of the cell, patch and dof numbering) keeps a rank's interface dofs and the patches
+    that touch ghosts contiguous at the two ends of its numbering -- what the overlapped host-space apply wants;
+    ``axis = 2`` scatters them through the whole numbering (every x-range of the slab touches the interface).
+    """
+
+    def __init__(self, cells, p, rank, nranks, axis=2):
+        grid = [1, 1, 1]
+        grid[axis] = nranks
+        Brick.__init__(self, cells, p, rank, tuple(grid))
+        self.axis = axis
 
 
 class ZSlab(Slab):

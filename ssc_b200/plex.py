@@ -337,6 +337,16 @@ class TensorPlex(Plex):
         _, shape, start = self.groups[self.group_of[frozenset(S)]]
         return np.ravel_multi_index(tuple(idx), shape) + start
 
+    def mark_ghost_box(self, lo, hi):
+        """Label as ``pyop2_ghost`` every point whose lowest vertex lies outside the index box lo <= i <= hi (per axis):
+        the owned points of a brick partition (an entity belongs to the rank that owns its lowest vertex)."""
+        for S, shape, start in self.groups:
+            idx = np.indices(shape).reshape(self.dim, -1)
+            g = np.zeros(idx.shape[1], dtype=bool)
+            for a in range(self.dim):
+                g |= (idx[a] < lo[a]) | (idx[a] > hi[a])
+            self.ghost[start:start + g.size] = g.astype(np.uint8)
+
     def mark_ghost_vertices(self, axis, lo, hi):
         """Label as ``pyop2_ghost`` every point that has a vertex outside [lo, hi] along ``axis``
         ... i.e. keep as owned exactly the points whose lowest vertex plane lies in [lo, hi]."""

@@ -10,7 +10,7 @@ import numpy as np
 from . import petsc_lite
 from .lo import P1PC
 from .patch import PCBase, _form_and_bcs, setup_patch_pc
-from .pcpatch import PC as PatchPCCore
+from .pcpatch import PC as PatchPCCore, DeviceVec
 
 
 class SSC(PCBase):
@@ -43,13 +43,25 @@ class SSC(PCBase):
         self.lo_pc.setUp()
 
     def apply(self, pc, x, y):
+        """PCCOMPOSITE additive (PETSc's default, ssc/ssc.py:38-49): y = patch(x) + lo(x).  The residual goes to the device
+        once, both sub-PCs run there (the patch PC on its stream, the coarse PC beside it on its own), the sum is formed on
+        the device and the result comes back once."""
         xa = x.array if hasattr(x, "array") else x
         ya = y.array if hasattr(y, "array") else y
-        if self._work is None or self._work.size != xa.size:
-            self._work = np.zeros_like(xa)
-        self.patch.apply(xa, ya)                                                 # PCCOMPOSITE additive: sum of the sub-PCs
-        self.lo.apply(self.lo_pc, xa, self._work)
-        ya += self._work
+        if self._work is None or self._work[0].n != xa.size:
+            self._work = tuple(DeviceVec(self.patch, xa.size) for _ in range(3))
+        dx, dy, dw = self._work
+        dx.set(xa)
+        self.applyDevice(dx, dy, dw)
+        ya[:] = dy.get()
+
+    def applyDevice(self, dx, dy, dw):
+        """The same on device-resident vectors (dw: work vector); returns when dy is complete."""
+        self.patch.apply(dx, dy)
+        self.lo.lo.applyDevice(dx, dw)
+        self.patch.synchronize()
+        self.lo.lo.axpyDevice(1.0, dw, dy)
+        self.lo.lo.synchronize()
 
     def applyTranspose(self, pc, x, y):
         self.patch.applyTranspose(x, y)

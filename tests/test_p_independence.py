@@ -98,3 +98,34 @@ def test_gpu_ssc_reproduces_reference_iteration_counts(name):
         assert np.linalg.norm(A @ x.array - b) <= 1e-5 * np.linalg.norm(b)
     pl.Options.clear()
     assert nits == EXPECTED[name]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["Rectangle", "Box"])
+def test_gpu_ssc_with_the_iterative_coarse_solver(name):
+    """ssc.SSC with -lo_ksp_type cg -lo_pc_type jacobi (the coarse solver that scales past the dense factorisation): the
+    coarse CG solves to rtol 1e-10, so the preconditioner is the same operator and the reference's iteration counts
+    (tests/test_p_independence.py:17-24) come out unchanged."""
+    from conftest import meshes
+    mesh = meshes()[name]
+    nits = []
+    for p in range(1, 5):
+        form, bcs, A, b = _system(mesh, p)
+        pl.Options.clear()
+        pl.Options.insert_parameters({
+            "mat_type": "matfree", "ksp_type": "cg", "ksp_rtol": KSP_RTOL, "pc_type": "python", "pc_python_type": "ssc.SSC",
+            "ssc_sub_0": {"pc_patch_sub_mat_type": "aij", "pc_patch_save_operators": True, "sub_ksp_type": "preonly", "sub_pc_type": "lu"},
+            "ssc_sub_1": {"lo_mat_type": "aij", "lo_ksp_type": "cg", "lo_pc_type": "jacobi", "lo_ksp_rtol": 1e-12}})
+        ksp = pl.KSP()
+        ksp.setOperators(pl.Mat(context=fem.ImplicitMatrixContext(form, bcs), size=A.shape))
+        ksp.setFromOptions()
+        x = pl.Vec(np.zeros(b.size))
+        ksp.solve(pl.Vec(b), x)
+        nits.append(ksp.getIterationNumber())
+        ctx = ksp.getPC().getPythonContext()
+        last, total, solves = ctx.lo.lo.iterations()
+        assert solves == nits[-1] + 1 or solves == nits[-1] or solves >= nits[-1]      # one coarse solve per PC apply
+        assert 0 < last <= A.shape[0]
+        assert np.linalg.norm(A @ x.array - b) <= 1e-5 * np.linalg.norm(b)
+    pl.Options.clear()
+    assert nits == EXPECTED[name]

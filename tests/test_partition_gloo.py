@@ -34,7 +34,7 @@ def _oracle_for(disc, V):
     return o
 
 
-def _worker(rank, nranks, port, outdir, axis=2, parity_leg=False):
+def _worker(rank, nranks, port, outdir, axis=2, parity_leg=False, grid=None, cells_override=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -50,7 +50,11 @@ def _worker(rank, nranks, port, outdir, axis=2, parity_leg=False):
         return out
     cells = [C, C, C]
     cells[axis] = C * nranks
-    slab = partition.Slab(tuple(cells), P, rank, nranks, axis=axis)
+    if grid is not None:
+        cells = list(cells_override)
+        slab = partition.Brick(tuple(cells), P, rank, grid)
+    else:
+        slab = partition.Slab(tuple(cells), P, rank, nranks, axis=axis)
     sl, sr, neigh, so, sroot, ro, rleaf = partition.star_forest(slab.global_ids, slab.nowned, rank, nranks, allgather)
     o = _oracle_for(slab.discretisation, slab.space)
     xlat = np.random.default_rng(7).uniform(-1, 1, int(np.prod(slab.global_shape)))     # same on every rank
@@ -140,7 +144,48 @@ def test_bench_parity_leg_accepts_correct_and_rejects_broken_exchanges(nranks, t
     mp.spawn(_worker, args=(nranks, _free_port(), str(tmp_path), 0, True), nprocs=nranks, join=True)
     r = json.load(open(os.path.join(str(tmp_path), "parity.json")))
     a, b = r["a"], r["b"]
-    assert a["interfaces"] == nranks - 1 and a["dofs_checked"] == (nranks - 1) * (4 * P + 1) * (C * P + 1) ** 2
+    assert a["cut_planes"] == nranks - 1 and a["dofs_checked"] == (nranks - 1) * (4 * P + 1) * (C * P + 1) ** 2
+    assert a["max_rel_err_vs_oracle"]["good"] < 1e-12 and a["max_entry_err_vs_oracle"]["good"] < 1e-12
+    assert a["max_rel_err_vs_oracle"]["no_overlap_sum"] > 1e-3 and not a["ok"]
+    assert b["max_rel_err_vs_oracle"]["stale_ghost"] > 1e-6 and not b["ok"]
+
+
+@pytest.mark.parametrize("grid,cells", [((2, 2, 1), (6, 5, 4)), ((1, 2, 2), (4, 6, 6)), ((2, 2, 2), (4, 4, 4))])
+def test_bricks_over_gloo_match_single_rank(grid, cells, tmp_path):
+    """Brick partitions (SURVEY.md 8e names 2 x 2 x 2 bricks): ranks with face, edge and corner neighbours; a ghost dof on a
+    brick edge is owned by exactly one of the up to 7 neighbours, and the overlap sum collects contributions from all."""
+    import torch.multiprocessing as mp
+    from ssc_b200 import fem, plex
+    nranks = int(np.prod(grid))
+    mp.spawn(_worker, args=(nranks, _free_port(), str(tmp_path), 0, False, grid, cells), nprocs=nranks, join=True)
+    h = 1.0 / min(cells)
+    mesh = plex.TensorPlex(tuple(cells), lengths=tuple(c * h for c in cells))
+    V = fem.FunctionSpace(mesh, P)
+    disc = fem.Discretisation([V])
+    o = _oracle_for(disc, V)
+    lat_of_node = np.empty(V.node_count, dtype=np.int64)
+    lat_of_node[V.lattice_node.ravel()] = np.arange(V.node_count)
+    xlat = np.random.default_rng(7).uniform(-1, 1, V.node_count)
+    y = o.apply(xlat[lat_of_node])
+    ylat = np.empty_like(y)
+    ylat[lat_of_node] = y
+    seen = np.zeros(V.node_count, dtype=int)
+    for r in range(nranks):
+        d = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        seen[d["gid"]] += 1
+        assert np.abs(d["y"] - ylat[d["gid"]]).max() <= 1e-13 * np.abs(ylat).max()
+    assert np.all(seen == 1)
+
+
+def test_bench_parity_leg_on_bricks(tmp_path):
+    """The parity leg on a 2 x 2 x 1 brick partition: two cut planes (one along x, one along y), windows that span two
+    ranks each and meet at the brick edge."""
+    import json
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(4, _free_port(), str(tmp_path), 0, True, (2, 2, 1), (8, 8, 4)), nprocs=4, join=True)
+    r = json.load(open(os.path.join(str(tmp_path), "parity.json")))
+    a, b = r["a"], r["b"]
+    assert a["cut_planes"] == 2 and a["dofs_checked"] == 2 * (4 * P + 1) * (8 * P + 1) * (4 * P + 1)
     assert a["max_rel_err_vs_oracle"]["good"] < 1e-12 and a["max_entry_err_vs_oracle"]["good"] < 1e-12
     assert a["max_rel_err_vs_oracle"]["no_overlap_sum"] > 1e-3 and not a["ok"]
     assert b["max_rel_err_vs_oracle"]["stale_ghost"] > 1e-6 and not b["ok"]
