@@ -127,8 +127,8 @@ struct SSCPatchPC_s {
     unsigned long long *d_kappa = nullptr;
     int factor_ctas = 0;          // concurrent CTAs of the blocked factor kernel (0 = fill the SMs)
     int factor_panel = 16;        // panel width of the blocked factor kernel (16 or 32)
-    int factor_variant = -1;      // -1 (default) by size: n <= 96 register tiles (1), 97..128 register-resident DMMA accumulators with look-ahead (2), larger blocked DMMA on the
-                                  // L2-resident block (3), beyond its shared-memory panels the in-place global-memory Gauss-Jordan (0); 0..3 force one where it applies
+    int factor_variant = -1;      // -1 (default) by size: n <= 64 register tiles (1), 65..128 tensor-core Gauss-Jordan on the L2-resident block, four patches per SM (2),
+                                  // larger blocked DMMA (3), beyond its shared-memory panels the in-place global-memory Gauss-Jordan (0); 0..3 force one where it applies
     int apply_variant = 1;        // 0: simple loop, 1: pipelined LDG.64, 2: pipelined LDG.128 (even row stride)
     std::string sub_mat_type, sub_ksp_type = "preonly";
     BuildOptions bopt;
@@ -190,7 +190,7 @@ struct SSCPatchPC_s {
     int *d_gtol = nullptr;
     double *d_blocks = nullptr, *d_blocks0 = nullptr;
     i64 block_elems = 0, sum_n = 0, sum_n2 = 0, max_n = 0;
-    int *d_fail = nullptr;
+    int *d_fail = nullptr, *d_anyfail = nullptr;
     i64 failed = 0;
     std::vector<i64> failed_list;
     int *d_bc = nullptr;

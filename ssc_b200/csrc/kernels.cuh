@@ -3,7 +3,7 @@
 #include "kernels_common.cuh"
 #include "kernels_operators.cuh"   // K1 extract, K1e assemble
 #include "kernels_factor.cuh"      // K2 Gauss-Jordan family
-#include "kernels_factor_dmma.cuh" // K2, n <= 128: register-resident blocked Gauss-Jordan on the fp64 tensor cores
+#include "kernels_factor_l2.cuh"   // K2, 33 <= n <= 128: blocked Gauss-Jordan on the fp64 tensor cores, block in L2, four patches in flight per SM
 #include "kernels_apply.cuh"       // K3+K4+K5 fused apply
 #include "kernels_vector.cuh"      // BC rows, weights, slot sum, SpMV, calibration read
 #include "kernels_peer.cuh"        // NVLink peer exchange

@@ -26,6 +26,13 @@ __global__ void ssc_reciprocal_kernel(ll n, double *__restrict__ w)
 {
     for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) { const double v = w[i]; w[i] = v != 0.0 ? 1.0 / v : 0.0; }
 }
+// any non-zero flag? (per-patch failure flags of a -pc_patch_save_operators false apply)
+__global__ void ssc_any_kernel(ll n, const int *__restrict__ flags, int *__restrict__ any)
+{
+    int f = 0;
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) f |= flags[i];
+    if (__any_sync(0xffffffffu, f) && (threadIdx.x & 31) == 0) *any = 1;
+}
 // star-forest pieces: dst[di[i]] (=|+=) src[si[i]]
 __global__ void ssc_gather_kernel(ll n, const int *__restrict__ si, const double *__restrict__ src, double *__restrict__ dst)
 {

@@ -11,6 +11,8 @@ per-patch callback into PETSc Mats (ssc/patch.py:210-213); it is given the assem
 cuts the dense patch blocks out of it on the GPU.
 """
 
+import numpy as np
+
 from . import fem, petsc_lite
 from .pcpatch import PC as PatchPCCore
 
@@ -36,9 +38,23 @@ def user_construction_op(pc, *args, **kwargs):
 
 
 def _csr_of(J, bcs, P):
-    """Assembled local operator as (indptr, indices, data): from P if it is assembled, else by assembling J."""
+    """Assembled LOCAL operator as (indptr, indices, data): from P if it is assembled, else by assembling J.
+
+    The extract kernel indexes rows and columns by local dof numbers (owned + ghost, the numbering of the dof lists) and
+    needs the ghost rows as well.  ``Mat.getValuesCSR`` of a parallel (MPIAIJ) matrix returns the owned rows only, with
+    GLOBAL column indices: this adapter is therefore for a sequential (one-rank) P; across ranks hand the local operator
+    over explicitly (``setOperatorCSR`` with the locally assembled matrix, as bench.py does) or use the element-matrix
+    route (``setElementMatrices``), which needs no assembled operator.  A matrix that is not square over the local dofs is
+    rejected here rather than cut wrongly."""
     if P is not None and hasattr(P, "getType") and P.getType() != "python" and hasattr(P, "getValuesCSR"):
-        return P.getValuesCSR()
+        comm_size = P.getComm().getSize() if hasattr(P, "getComm") and hasattr(P.getComm(), "getSize") else 1
+        if comm_size > 1:
+            raise ValueError("Mat.getValuesCSR of a parallel matrix gives owned rows with global columns; pass the locally "
+                             "assembled operator with setOperatorCSR or use setElementMatrices")
+        indptr, indices, data = P.getValuesCSR()
+        if len(indices) and int(np.max(indices)) >= 2 ** 31:
+            raise ValueError("column index %d does not fit the device's 32-bit dof index" % int(np.max(indices)))
+        return indptr, indices, data
     A = J.assemble(bcs)
     return A.indptr, A.indices, A.data
 

@@ -668,3 +668,30 @@ def test_pageable_host_vectors_are_registered_once_and_give_the_same_result():
         pc.reset()
         xs[0][:] = 0.0                           # plain memory again
         del pc
+
+
+def test_unsaved_operators_report_a_singular_block_and_option_state_is_consistent():
+    """(i) with -pc_patch_save_operators false a block that cannot be factorised inside PCApply used to add
+    garbage silently; now the next synchronising call raises the reference's error code.  (ii) the storage mode cannot be
+    switched after the first SetUp.  (iii) multiplicative sweeps reject the combinations they do not implement at SetUp."""
+    import scipy.sparse as sp
+    from ssc_b200 import PC, SSCError
+    A = sp.csr_matrix(np.array([[1.0, 2.0, 0.0], [2.0, 4.0, 0.0], [0.0, 0.0, 1.0]]))
+    pc = PC(device=0)
+    pc.setOption("pc_patch_save_operators", False)
+    pc.setPatches([0, 2, 3], [0, 1, 2], 3)
+    pc.setOperatorCSR(A.indptr, A.indices, A.data)
+    pc.setUp()                                       # nothing is factorised yet
+    x, y = np.ones(3), np.zeros(3)
+    with pytest.raises(SSCError) as e:
+        pc.apply(x, y)
+    assert e.value.ierr == 71
+    with pytest.raises(SSCError) as e:
+        pc.setOption("pc_patch_save_operators", True)
+    assert e.value.ierr == 73
+    form, bcs, disc, A = _problem(plex.TensorPlex((3, 3, 3)), 2, "scalar")
+    for extra in (dict(ssc_deterministic=True), dict(pc_patch_save_operators=False)):
+        pc = make_gpu(form, bcs, pc_patch_multiplicative=True, **extra)
+        with pytest.raises(SSCError) as e:
+            pc.setUp()
+        assert e.value.ierr == 56

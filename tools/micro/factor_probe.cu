@@ -1,4 +1,6 @@
-// Stand-alone timing harness of the register-resident DMMA factor kernel (ssc_b200/csrc/kernels_factor_dmma.cuh).
+// Stand-alone timing harness of the DMMA factor kernels: the L2-resident one that ships (ssc_b200/csrc/kernels_factor_l2.cuh, kernel = 4)
+// and the register-resident one that was measured and rejected (tools/micro/factor_reg_dmma.cuh, kernel = 2).
+// usage: factor_probe [n] [count] [pivot 0|1] [kernel 2|4] [CTAs per SM of kernel 4]
 // Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo [-DSSC_DMMA_PROBE=k] -o tools/micro/factor_probe tools/micro/factor_probe.cu
 //   SSC_DMMA_PROBE = 0 the kernel as shipped; 1 tensor-core updates skipped (what the pivot chain alone costs);
 //                    2 panel steps skipped (what the updates and the data movement alone cost).  Results of 1 and 2 are garbage by design.
@@ -6,14 +8,17 @@
 #include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
-#include "../../ssc_b200/csrc/kernels_factor_dmma.cuh"
+#include "../../ssc_b200/csrc/kernels_factor_l2.cuh"
+#include "factor_reg_dmma.cuh"
 
 int main(int argc, char **argv)
 {
     const int n = argc > 1 ? atoi(argv[1]) : 125;
     const long long count = argc > 2 ? atoll(argv[2]) : 148 * 40;
     const int pivot = argc > 3 ? atoi(argv[3]) : 1;
-    const int ld = n;
+    const int kernel = argc > 4 ? atoi(argv[4]) : 2;      // 2 register-resident, 4 L2-resident
+    const int ctas = argc > 5 ? atoi(argv[5]) : 4;
+    const int ld = (n + 1) & ~1;
     const long long stride = ((long long)n * ld + 15) / 16 * 16;
     std::vector<double> h((size_t)stride * count, 0.0);
     srand(1);
@@ -31,7 +36,15 @@ int main(int argc, char **argv)
     for (int rep = 0; rep < 4; ++rep) {
         cudaMemcpy(d, d0, h.size() * sizeof(double), cudaMemcpyDeviceToDevice);
         cudaEventRecord(e0);
-        if (pivot) ssc_invert_dmma_kernel<true, 4><<<148, 640, smem>>>(d, n, ld, stride, count, fail);
+        if (kernel == 4) {
+            const size_t sm4 = (size_t)(128 * 20 + 16 * 132) * sizeof(double);
+            cudaFuncSetAttribute(ssc_invert_l2_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
+            cudaFuncSetAttribute(ssc_invert_l2_kernel<true, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(ssc_invert_l2_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
+            cudaFuncSetAttribute(ssc_invert_l2_kernel<false, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            if (pivot) ssc_invert_l2_kernel<true, 16><<<148 * ctas, 128, sm4>>>(d, n, ld, stride, count, fail);
+            else ssc_invert_l2_kernel<false, 16><<<148 * ctas, 128, sm4>>>(d, n, ld, stride, count, fail);
+        } else if (pivot) ssc_invert_dmma_kernel<true, 4><<<148, 640, smem>>>(d, n, ld, stride, count, fail);
         else ssc_invert_dmma_kernel<false, 4><<<148, 640, smem>>>(d, n, ld, stride, count, fail);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -41,12 +54,12 @@ int main(int argc, char **argv)
     cudaMemcpy(hf.data(), fail, count * sizeof(int), cudaMemcpyDeviceToHost);
     long long nf = 0; for (int f : hf) nf += f;
     // residual of patch 0
-    std::vector<double> S((size_t)n * n);
-    cudaMemcpy(S.data(), d, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost);
+    std::vector<double> S((size_t)n * ld);
+    cudaMemcpy(S.data(), d, (size_t)n * ld * sizeof(double), cudaMemcpyDeviceToHost);
     double worst = 0;
     for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { double a = 0; for (int k = 0; k < n; ++k) a += h[(size_t)i * ld + k] * S[(size_t)j * ld + k]; a -= (i == j); if (a < 0) a = -a; if (a > worst) worst = a; }
     const double per = best * 1e3 / (count / 148.0);
-    printf("probe %d  n %d  count %lld  pivot %d: %.3f ms  = %.2f us per patch per SM = %.0f clk at 1.9 GHz  (%.2f TFLOP/s of 2n^3)  failed %lld  max|B S^T - I| %.2e  %s\n",
-           SSC_DMMA_PROBE, n, count, pivot, best, per, per * 1900, 2.0 * n * n * n * count / (best * 1e-3) * 1e-12, nf, worst, cudaGetErrorString(cudaGetLastError()));
+    printf("kernel %d ctas/SM %d probe %d  n %d  count %lld  pivot %d: %.3f ms  = %.2f us per patch per SM = %.0f clk at 1.9 GHz  (%.2f TFLOP/s of 2n^3)  failed %lld  max|B S^T - I| %.2e  %s\n",
+           kernel, ctas, SSC_DMMA_PROBE, n, count, pivot, best, per, per * 1900, 2.0 * n * n * n * count / (best * 1e-3) * 1e-12, nf, worst, cudaGetErrorString(cudaGetLastError()));
     return 0;
 }

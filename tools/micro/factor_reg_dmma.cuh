@@ -1,3 +1,7 @@
+// MEASURED AND REJECTED (round 2; kept for the probe harness tools/micro/factor_probe.cu, not part of the library):
+// 142 ms (lu) / 122 ms (cholesky) at 64^3 Q3 against 118 / 111 ms for the L2-resident kernel that ships (ssc_b200/csrc/kernels_factor_l2.cuh).
+// The pivot chain's fp64 FMAs share the FP64 pipe with the DMMA updates, so the look-ahead overlap is lost: cost = chain + update.
+//
 // K2 for n <= 128: blocked Gauss-Jordan with the whole block resident in REGISTERS as fp64 tensor-core accumulators,
 // and the panel factorisation running one panel ahead of the update (look-ahead) on warps of its own.
 //
@@ -26,23 +30,14 @@
 // 2 n^3 flop per block, of which all but the n x 16 panel steps are DMMA.  Result stored as S = (B^-1)^T row-major,
 // like every other factor kernel: S[qinv[i]][perm[j]] = M[i][j].
 #pragma once
-#include "kernels_common.cuh"
+#include "../../ssc_b200/csrc/kernels_factor_l2.cuh"      // ssc_dmma_acc, SSC_DMMA_PROBE
 
-#ifndef SSC_DMMA_PROBE
-#define SSC_DMMA_PROBE 0        // tools/micro/factor_probe.cu: 1 skips the tensor-core updates, 2 the panel steps (timing experiments only)
-#endif
-__device__ __forceinline__ void ssc_dmma_acc(double2 &c, double a, double b)
-{
-    if (SSC_DMMA_PROBE == 1) return;
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
-}
 __device__ __forceinline__ void ssc_nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void ssc_nbar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 template <int G> struct DmmaFactorSmem {
     static constexpr int NB = 16, N = 32 * G, QP = 20, WP = N + 4;      // QP, WP = 4 mod 16: conflict-free A / B fragment loads
-    static constexpr size_t bytes = (size_t)(3 * N * QP + NB * WP + 2 * N) * sizeof(double) + (size_t)(8 + 3 * N + 4) * sizeof(int);
+    static constexpr size_t bytes = (size_t)(2 * N * QP + NB * WP + 2 * (NB + 2)) * sizeof(double) + (size_t)(8 + 3 * N + 4) * sizeof(int);
 };
 
 template <bool kPivot, int G>
@@ -55,10 +50,10 @@ ssc_invert_dmma_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, l
     constexpr int NT = 32 * G * (G + 1);
     constexpr int B1 = 1, B2 = 2, B3 = 3, B4 = 4, B5 = 5;         // named barriers; B5 is CTA-wide (the two roles meet it from different code)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *R = reinterpret_cast<double *>(smem_raw);             // [3][N * QP] rotating panel buffers
-    double *Wbuf = R + 3 * N * QP;                                // [NB][WP] pivot rows of the current panel, all columns
-    double *invb = Wbuf + NB * WP;                                // [2][N] candidate reciprocals, by step parity
-    unsigned *keyb = reinterpret_cast<unsigned *>(invb + 2 * N);  // [2][4] per-warp maxima of the pivot keys
+    double *R = reinterpret_cast<double *>(smem_raw);             // [2][N * QP] panel buffers: panel j (being applied) and panel j+1 (being factored)
+    double *Wbuf = R + 2 * N * QP;                                // [NB][WP] pivot rows of the current panel, all columns
+    double *rowv = Wbuf + NB * WP;                                // [2][NB + 2] the pivot row of a step and the reciprocal of its pivot, by step parity
+    unsigned *keyb = reinterpret_cast<unsigned *>(rowv + 2 * (NB + 2));  // [2][4] per-warp maxima of the pivot keys
     int *perm = reinterpret_cast<int *>(keyb + 8);                // step -> pivot row
     int *rowk = perm + N;                                         // row -> step at which it was the pivot (-1: not yet)
     int *qinv = rowk + N;
@@ -85,7 +80,7 @@ ssc_invert_dmma_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, l
             // iteration j applies panel j (j >= 0) and prepares panel j + 1
             for (int j = -1; j < npanels; ++j) {
                 const bool have_next = j + 1 < npanels;
-                const double *Q = R + ((j >= 0 && (min(NB, n - NB * j) & 1)) ? (j + 1) % 3 : (j + 3) % 3) * (N * QP);   // where panel j's steps ended
+                const double *Q = R + ((j + 2) % 2) * (N * QP);
                 // halves of this warp's columns: h = 0 -> fragment columns 0, 1; h = 1 -> 2, 3; half h is panel 2 wc + h
                 bool doh[2];
 #pragma unroll
@@ -108,7 +103,7 @@ ssc_invert_dmma_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, l
                                     for (int ti = 0; ti < 4; ++ti) ssc_dmma_acc(c[ti][2 * h + t], a[ti], b[t]);
                             }
                         }
-                        double *In = R + ((j + 1) % 3) * (N * QP);
+                        double *In = R + ((j + 1) % 2) * (N * QP);
 #pragma unroll
                         for (int ti = 0; ti < 4; ++ti) {
                             double2 *dst = reinterpret_cast<double2 *>(In + (32 * wr + 8 * ti + gr) * QP + 2 * gc);
@@ -194,68 +189,77 @@ ssc_invert_dmma_kernel(double *__restrict__ blocks, int n, int ldg, ll stride, l
             bool used = i >= n;                                   // row i cannot be a pivot row (any more)
             for (int j = -1; j + 1 < npanels; ++j) {
                 const int kb = NB * (j + 1), bw = min(NB, n - kb);
-                double *Pc = R + ((j + 1) % 3) * (N * QP), *Pn = R + ((j + 2) % 3) * (N * QP);   // rows before / after the current step
+                double *Pj = R + ((j + 1) % 2) * (N * QP);        // panel j+1: published by its owners, factored in registers, written back as Q
                 ssc_nbar_sync(B1, 64 * G);
                 double pr[NB];
                 {
-                    const double2 *src = reinterpret_cast<const double2 *>(Pc + i * QP);
+                    const double2 *src = reinterpret_cast<const double2 *>(Pj + i * QP);
 #pragma unroll
                     for (int h = 0; h < NB / 2; ++h) { const double2 t = src[h]; pr[2 * h] = t.x; pr[2 * h + 1] = t.y; }
                 }
-                // candidates of step 0
+                // candidates of step 0: this row's key (one redux per warp) and the reciprocal of its entry
                 if (kPivot) {
-                    unsigned key = used ? 0u : (((unsigned)__double2hiint(fabs(pr[0])) & 0xFFFFFF80u) | (unsigned)(127 - i));
+                    unsigned key = used ? 0u : (((unsigned)__double2hiint(pr[0]) & 0x7FFFFF80u) | (unsigned)(127 - i));
                     key = __reduce_max_sync(0xffffffffu, key);
                     if (lane == 0) keyb[pwarp] = key;
                 }
-                invb[i] = 1.0 / pr[0];
+                double myinv = 1.0 / pr[0];
                 bool bad = false;
 #pragma unroll
                 for (int s = 0; s < NB; ++s) {
-                    if (s >= bw || SSC_DMMA_PROBE == 2) break;
+                    if (s >= bw || SSC_DMMA_PROBE >= 2) break;
                     const int cur = s & 1;
-                    ssc_nbar_sync(B4, 32 * G);
                     int prow = kb + s;
                     if (kPivot) {
+                        ssc_nbar_sync(B4, 32 * G);
                         unsigned m = keyb[4 * cur];
 #pragma unroll
                         for (int w = 1; w < G; ++w) m = max(m, keyb[4 * cur + w]);
                         prow = 127 - (int)(m & 127u);
                         if (m == 0) { bad = true; break; }                       // no candidate left (uniform)
                     }
-                    const double dinv = invb[cur * N + prow];
+                    const bool win = i == prow;
+                    if (win) {
+                        // the pivot row as it stands, and the reciprocal of the pivot
+                        double2 *dst = reinterpret_cast<double2 *>(rowv + cur * (NB + 2));
+#pragma unroll
+                        for (int h = 0; h < NB / 2; ++h) dst[h] = make_double2(pr[2 * h], pr[2 * h + 1]);
+                        rowv[cur * (NB + 2) + NB] = myinv;
+                        used = true; perm[kb + s] = i; rowk[i] = kb + s;
+                    }
+                    ssc_nbar_sync(B4, 32 * G);
+                    const double dinv = rowv[cur * (NB + 2) + NB];
                     if (kPivot ? !(fabs(dinv) > 0.0 && fabs(dinv) < 1.0e300) : !(dinv > 0.0 && dinv < 1.0e300)) { bad = true; break; }   // uniform
                     double rv[NB];
                     {
-                        const double2 *src = reinterpret_cast<const double2 *>(Pc + prow * QP);
+                        const double2 *src = reinterpret_cast<const double2 *>(rowv + cur * (NB + 2));
 #pragma unroll
                         for (int h = 0; h < NB / 2; ++h) { const double2 t = src[h]; rv[2 * h] = t.x; rv[2 * h + 1] = t.y; }
                     }
-                    if (i == prow) {
+                    // one update formula for all rows: the pivot row starts from zero with the multiplier 1/d, every other row
+                    // from itself with -a[i][s]/d; entry s becomes the multiplier itself (1/d, resp. -a[i][s]/d)
+                    const double g = win ? dinv : -pr[s] * dinv;
+                    if (win) {
 #pragma unroll
-                        for (int jj = 0; jj < NB; ++jj) pr[jj] = (jj == s) ? dinv : rv[jj] * dinv;
-                        used = true; perm[kb + s] = i; rowk[i] = kb + s;
-                    } else {
-                        const double g = -pr[s] * dinv;
-                        if (s + 1 < NB) pr[s + 1] = fma(g, rv[s + 1], pr[s + 1]);            // the next pivot column first
-#pragma unroll
-                        for (int jj = 0; jj < NB; ++jj) if (jj != s && jj != s + 1) pr[jj] = fma(g, rv[jj], pr[jj]);
-                        pr[s] = g;
+                        for (int jj = 0; jj < NB; ++jj) pr[jj] = 0.0;
                     }
+                    if (s + 1 < NB) pr[s + 1] = fma(g, rv[s + 1], pr[s + 1]);                // the next pivot column first
                     if (s + 1 < bw) {
                         if (kPivot) {
-                            unsigned key = used ? 0u : (((unsigned)__double2hiint(fabs(pr[s + 1])) & 0xFFFFFF80u) | (unsigned)(127 - i));
+                            unsigned key = used ? 0u : (((unsigned)__double2hiint(pr[s + 1]) & 0x7FFFFF80u) | (unsigned)(127 - i));
                             key = __reduce_max_sync(0xffffffffu, key);
                             if (lane == 0) keyb[4 * (cur ^ 1) + pwarp] = key;
                         }
-                        invb[(cur ^ 1) * N + i] = 1.0 / pr[s + 1];
+                        myinv = 1.0 / pr[s + 1];
                     }
-                    {
-                        double2 *dst = reinterpret_cast<double2 *>(Pn + i * QP);
 #pragma unroll
-                        for (int h = 0; h < NB / 2; ++h) dst[h] = make_double2(pr[2 * h], pr[2 * h + 1]);
-                    }
-                    double *t = Pc; Pc = Pn; Pn = t;
+                    for (int jj = 0; jj < NB; ++jj) if (jj != s && jj != s + 1) pr[jj] = fma(g, rv[jj], pr[jj]);
+                    pr[s] = g;
+                }
+                {
+                    double2 *dst = reinterpret_cast<double2 *>(Pj + i * QP);
+#pragma unroll
+                    for (int h = 0; h < NB / 2; ++h) dst[h] = make_double2(pr[2 * h], pr[2 * h + 1]);
                 }
                 if (bad) *s_fail = 1;
                 ssc_nbar_sync(B2, NW + 32 * G);
