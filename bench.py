@@ -451,6 +451,8 @@ def main():
         pc.setOption("ssc_factor_ctas", args.factor_ctas)
     if args.factor_panel is not None:
         pc.setOption("ssc_factor_panel", args.factor_panel)
+    if os.environ.get("SSC_OVERLAP_EXCHANGE"):          # A/B switch of the overlapped device-resident exchange (tools/r2/gpu2_overlap.sh)
+        pc.setOption("ssc_overlap_exchange", os.environ["SSC_OVERLAP_EXCHANGE"])
     if args.host_pipeline is not None:
         pc.setOption("ssc_host_pipeline", args.host_pipeline)
     if args.pipeline_taper is not None:

@@ -109,6 +109,7 @@ struct SSCPatchPC_s {
     cudaStream_t side_stream = nullptr, launch_stream = nullptr;   // the small size classes of an apply run beside the big one; launch_apply_class launches on launch_stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap_classes = true;
+    bool overlap_exchange = true;    // -ssc_overlap_exchange: device-resident applies across ranks hide both neighbour barriers under patch kernels
     int apply_stream_min_waves = 4;  // ... and only when every CTA gets at least this many rounds of patches (tests: 0)
     int apply_stream_ctas = 0;       // CTAs of the persistent kernel (0: fill the GPU; tests use a few to get many rounds on small cases)
     int apply_stream_max_n = 96;     // largest patch the persistent apply kernel takes (n = 125: measured no better than the one-patch-per-CTA kernel)
@@ -129,7 +130,7 @@ struct SSCPatchPC_s {
     int factor_panel = 16;        // panel width of the blocked factor kernel (16 or 32)
     int factor_variant = -1;      // -1 (default) by size: n <= 64 register tiles (1), 65..128 tensor-core Gauss-Jordan on the L2-resident block, four patches per SM (2),
                                   // larger blocked DMMA (3), beyond its shared-memory panels the in-place global-memory Gauss-Jordan (0); 0..3 force one where it applies
-    int apply_variant = 1;        // 0: simple loop, 1: pipelined LDG.64, 2: pipelined LDG.128 (even row stride)
+    int apply_variant = 1;        // 0: simple loop (also the fallback for patches too large for one thread per row), 1: pipelined LDG.64 (default)
     std::string sub_mat_type, sub_ksp_type = "preonly";
     BuildOptions bopt;
     // host inputs
@@ -179,9 +180,6 @@ struct SSCPatchPC_s {
                                      // (measured no faster end to end: the lists have to come back to the host, profiles/README.md)
     bool lists_from_device = false;
     bool symmetric = false;          // packed lower triangle of the (symmetric) inverse only
-    bool sym_two_chunk = false;      // packed apply: two bulk copies split at a column, two threads per row
-    bool sym_bulk = true;            // packed apply: TMA bulk copy (true, 3.24 ms at 64^3 Q3) or per-thread cp.async (false, 4.46 ms)
-    bool sym_persistent = false;     // persistent ring-buffered form of the packed apply kernel (measured slower: profiles/README.md)
     double *d_packed = nullptr;
     i64 packed_elems = 0;
     double *d_ypatch = nullptr;

@@ -27,7 +27,7 @@ def random_problem(seed, N=1500, npatch=60, nmax=260):
     return A, off, gtol, bc, N
 
 
-@pytest.mark.parametrize("opts", [{}, {"ssc_apply_variant": 0}, {"ssc_apply_variant": 2}, {"ssc_deterministic": True},
+@pytest.mark.parametrize("opts", [{}, {"ssc_apply_variant": 0}, {"ssc_deterministic": True},
                                   {"sub_pc_type": "cholesky"}, {"sub_pc_type": "cholesky", "ssc_symmetric_storage": True, "nmax": 200},
                                   {"pc_patch_save_operators": False}, {"pc_patch_partition_of_unity": True, "pc_patch_symmetrise_sweep": True}])
 @pytest.mark.parametrize("seed", [1, 2])
