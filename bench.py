@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak (default): --cells^3 per GPU; strong: ONE --cells^3 mesh split over the GPUs")
     ap.add_argument("--partition", default="slab", choices=["slab", "brick"], help="multi-GPU partition: x-slabs (default) or bricks (2x1x1, 2x2x1, 2x2x2)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the extra single-GPU measurements of BASELINE.json configs[3] (elasticity on tets) and configs[4] (Q4) that the default N=1 run appends")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-rank parity leg (oracle on the patches around every rank interface)")
     ap.add_argument("--apply-variant", type=int, default=None, help="ssc_apply_variant (kernel selection; default = library default)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo exchange: NVLink peer memory (default) or NCCL send/recv")
@@ -451,8 +452,6 @@ def main():
         pc.setOption("ssc_factor_ctas", args.factor_ctas)
     if args.factor_panel is not None:
         pc.setOption("ssc_factor_panel", args.factor_panel)
-    if os.environ.get("SSC_OVERLAP_EXCHANGE"):          # A/B switch of the overlapped device-resident exchange (tools/r2/gpu2_overlap.sh)
-        pc.setOption("ssc_overlap_exchange", os.environ["SSC_OVERLAP_EXCHANGE"])
     if args.host_pipeline is not None:
         pc.setOption("ssc_host_pipeline", args.host_pipeline)
     if args.pipeline_taper is not None:
@@ -482,13 +481,22 @@ def main():
     pc.setUp()
     pc.synchronize()
     info["t_setup_wall"] = time.time() - t0
+    first = {k: pc.eventTime(k) for k in ("PCPATCHCreate", "PCPATCHComputeOp", "PCPATCHSolve", "SSCSetupLists", "SSCSetupUploadOperator", "SSCSetupAllocBlocks", "SSCSetupKernels", "SSCSetupFreeOperator")}
+    # the second set-up (new values, same shape: what every Newton step of a nonlinear solve pays, PatchPC.update ssc/patch.py:269-270)
+    t0 = time.time()
+    pc.setUp()
+    pc.synchronize()
+    info["t_resetup_wall"] = time.time() - t0
+    resetup = {"resetup_wall_s": info["t_resetup_wall"], "resetup_upload_operator_ms": pc.eventTime("SSCSetupUploadOperator"), "resetup_lists_ms": pc.eventTime("SSCSetupLists"),
+               "resetup_kernels_wall_ms": pc.eventTime("SSCSetupKernels"), "resetup_extract_ms": pc.eventTime("PCPATCHComputeOp"), "resetup_factor_ms": pc.eventTime("PCPATCHSolve")}
     if nranks > 1:
         pc.releaseOperator()         # the CSR was only borrowed until SetUp returned; N=1 keeps it for the CPU baseline
         csr = None
-    setup = {"note": "setup_wall_s = SSCPatchSetUp with the CSR in pageable host memory: patch construction on the host, H2D of dof lists and CSR, extract, factor" if not elements else "setup_wall_s = SSCPatchSetUp from one shared element matrix: patch construction on the host, H2D of dof lists / cell lists / cell-node maps, assemble kernel (extract_ms), factor", "create_patches_ms": pc.eventTime("PCPATCHCreate"), "extract_ms": pc.eventTime("PCPATCHComputeOp"),
-             "factor_ms": pc.eventTime("PCPATCHSolve"), "lists_ms": pc.eventTime("SSCSetupLists"), "upload_operator_ms": pc.eventTime("SSCSetupUploadOperator"),
-             "alloc_blocks_ms": pc.eventTime("SSCSetupAllocBlocks"), "kernels_wall_ms": pc.eventTime("SSCSetupKernels"), "free_operator_ms": pc.eventTime("SSCSetupFreeOperator"), "setup_wall_s": info["t_setup_wall"],
+    setup = {"note": "setup_wall_s = SSCPatchSetUp with the CSR in pageable host memory: patch construction on the host, H2D of dof lists and CSR, extract, factor" if not elements else "setup_wall_s = SSCPatchSetUp from one shared element matrix: patch construction on the host, H2D of dof lists / cell lists / cell-node maps, assemble kernel (extract_ms), factor", "create_patches_ms": first["PCPATCHCreate"], "extract_ms": first["PCPATCHComputeOp"],
+             "factor_ms": first["PCPATCHSolve"], "lists_ms": first["SSCSetupLists"], "upload_operator_ms": first["SSCSetupUploadOperator"],
+             "alloc_blocks_ms": first["SSCSetupAllocBlocks"], "kernels_wall_ms": first["SSCSetupKernels"], "free_operator_ms": first["SSCSetupFreeOperator"], "setup_wall_s": info["t_setup_wall"],
              "assemble_wall_s": info["t_assemble"], "mesh_wall_s": info["t_mesh"]}
+    setup.update(resetup)
     if setup["extract_ms"] > 0 and not elements:
         setup["extract_gbs"] = pc.size("bytes_extract") / (setup["extract_ms"] * 1e-3) / 1e9      # algorithmic bytes of SURVEY.md 8(d)
     if setup["factor_ms"] > 0:
@@ -664,7 +672,36 @@ def main():
         out["cpu_baseline"] = cpu_baseline(args, x_lat=np.asarray(xh.array)[lat], y_lat=dy.get()[lat])
         if out["cpu_baseline"]["parity"] and not out["cpu_baseline"]["parity"]["ok"]:
             raise SystemExit("PCApply differs from the CPU oracle on the sampled dofs: %r" % (out["cpu_baseline"]["parity"],))
+    if nranks == 1 and args.workload == "poisson_hex" and args.cells == 64 and args.degree == 3 and not args.no_other_configs:
+        # BASELINE.json configs[3] and configs[4] measured by the same run (single GPU, sizes that set up in seconds), each
+        # through its own `bench.py` process once this one has released the device
+        for v in (dx, dy):
+            v.free()
+        pc.destroy()
+        out["other_configs"] = other_configs(args)
     print(json.dumps(out))
+
+
+def other_configs(args):
+    res = {}
+    runs = {"elasticity_tets_p2_vector_24^3": ["--workload", "elasticity_tets", "--cells", "24", "--no-e2e"],
+            "poisson_hex_q4_32^3_from_element_matrices": ["--degree", "4", "--cells", "32", "--operator", "elements", "--no-e2e"]}
+    for name, extra in runs.items():
+        cmd = [sys.executable, os.path.abspath(__file__), "--steps", str(max(5, min(args.steps, 20))), "--warmup", "3", "--no-cpu-baseline", "--no-spd-packed", "--no-other-configs"] + extra
+        try:
+            p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+            line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+            if p.returncode != 0 or not line:
+                res[name] = {"error": (p.stderr or "no output")[-400:]}
+                continue
+            d = json.loads(line[-1])
+            res[name] = {k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "dofs", "patches_per_gpu", "config", "gpu_launches")}
+            res[name]["roofline"] = {k: d["roofline"].get(k) for k in ("achieved", "peak", "frac", "algorithmic_bytes", "kernel_ms")}
+            res[name]["setup"] = {k: d["setup"].get(k) for k in ("setup_wall_s", "extract_ms", "factor_ms", "factor_tflops")}
+            res[name]["symmetry_check_rel_diff"] = d["symmetry_check"]["rel_diff"]
+        except Exception as exc:                      # an extra, never allowed to take the main line down
+            res[name] = {"error": str(exc)}
+    return res
 
 
 def spd_packed_line(args, disc, csr, dx, dy, peak):

@@ -109,7 +109,6 @@ struct SSCPatchPC_s {
     cudaStream_t side_stream = nullptr, launch_stream = nullptr;   // the small size classes of an apply run beside the big one; launch_apply_class launches on launch_stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap_classes = true;
-    bool overlap_exchange = true;    // -ssc_overlap_exchange: device-resident applies across ranks hide both neighbour barriers under patch kernels
     int apply_stream_min_waves = 4;  // ... and only when every CTA gets at least this many rounds of patches (tests: 0)
     int apply_stream_ctas = 0;       // CTAs of the persistent kernel (0: fill the GPU; tests use a few to get many rounds on small cases)
     int apply_stream_max_n = 96;     // largest patch the persistent apply kernel takes (n = 125: measured no better than the one-patch-per-CTA kernel)

@@ -15,7 +15,6 @@ PY
 }
 SSC_PIPE_TRACE=1 run slab_weak
 run slab_strong --scaling strong --no-e2e
-SSC_OVERLAP_EXCHANGE=false run slab_strong_nooverlap --scaling strong --no-e2e
 run brick_strong --scaling strong --partition brick --no-e2e
 run brick_weak --partition brick --no-e2e
 timeout 300 python tools/mgpu_pcie.py > gpurun_out/r2/mgpu_pcie_8.txt 2>&1; tail -12 gpurun_out/r2/mgpu_pcie_8.txt
