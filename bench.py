@@ -483,6 +483,8 @@ def main():
     info["t_setup_wall"] = time.time() - t0
     first = {k: pc.eventTime(k) for k in ("PCPATCHCreate", "PCPATCHComputeOp", "PCPATCHSolve", "SSCSetupLists", "SSCSetupUploadOperator", "SSCSetupAllocBlocks", "SSCSetupKernels", "SSCSetupFreeOperator")}
     # the second set-up (new values, same shape: what every Newton step of a nonlinear solve pays, PatchPC.update ssc/patch.py:269-270)
+    if not elements:
+        pc.setOperatorValues(csr[2])          # same nonzero pattern: only the values travel again
     t0 = time.time()
     pc.setUp()
     pc.synchronize()

@@ -118,6 +118,10 @@ int SSCPatchPeerConnect(SSCPatchPC pc, const char *neighHandles, const int *slot
  * numbering.  memspace says where the three arrays live.  The arrays are BORROWED until the next SetUp returns. */
 int SSCPatchSetOperatorCSR(SSCPatchPC pc, SSCInt nrows, const SSCInt *rowptr, const int32_t *colidx,
                            const double *vals, int memspace);
+/* New values on the nonzero pattern of the previous SSCPatchSetOperatorCSR (the matrix was re-assembled with
+ * SAME_NONZERO_PATTERN, as before every PatchPC.update of a nonlinear solve, ssc/patch.py:269-270): the next SetUp moves
+ * only `vals` to the device (two thirds of the bytes of the operator).  Same memspace as the pattern. */
+int SSCPatchSetOperatorValues(SSCPatchPC pc, const double *vals);
 
 /* The reference's own source of the patch operators: element matrices added cell by cell through the per-cell
  * dof table with negative (BC) indices dropped -- PCPatchSetComputeOperator / PCPatchComputeOperator

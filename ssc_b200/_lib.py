@@ -47,6 +47,7 @@ _sigs = {
     "SSCPatchPeerExport": [_H, C.c_char_p],
     "SSCPatchPeerConnect": [_H, C.c_char_p, i32p, i64p, i64p],
     "SSCPatchSetOperatorCSR": [_H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int],
+    "SSCPatchSetOperatorValues": [_H, C.c_void_p],
     "SSCPatchSetElementMatrices": [_H, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int],
     "SSCPatchReleaseOperator": [_H],
     "SSCPatchSetUp": [_H],

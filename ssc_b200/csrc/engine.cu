@@ -202,6 +202,7 @@ struct SSCPatchPC_s {
     int *d_colidx = nullptr;
     double *d_vals = nullptr;
     bool csr_owned = false;
+    bool csr_values_only = false;    // SSCPatchSetOperatorValues: the device copy of rowptr / colidx is current, only the values travel
     bool csr_dup = false;            // some row of the CSR has unsorted or repeated columns: the extract kernel accumulates instead of storing
     int *d_flag = nullptr;
     int extract_row_buffers = -1;    // -ssc_extract_row_buffers: warps of an extract CTA that get a shared-memory row buffer (-1: as many as fit; 0: hits go straight to global memory, the path of very large patches)

@@ -248,6 +248,14 @@ class PC(object):
         n, ptrs = indptr[0], [C.c_void_p(p) for p in (indptr[1], indices, data)]
         CHKERR(lib.SSCPatchSetOperatorCSR(self.handle, C.c_int64(n), ptrs[0], ptrs[1], ptrs[2], int(memspace)))
 
+    def setOperatorValues(self, data):
+        """New values on the pattern of the last setOperatorCSR (host arrays): the next setUp uploads only them."""
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        if getattr(self, "_csr_keep", None) is None or len(self._csr_keep) != 3 or data.size != self._csr_keep[2].size:
+            raise ValueError("setOperatorValues needs the pattern of a previous setOperatorCSR of the same size")
+        self._csr_keep = (self._csr_keep[0], self._csr_keep[1], data)
+        CHKERR(lib.SSCPatchSetOperatorValues(self.handle, data.ctypes.data_as(C.c_void_p)))
+
     def setElementMatrices(self, Ke, memspace=MEM_HOST, ncells=None, dofs_per_cell=None):
         """The reference's source of the patch operators (PCPatchSetComputeOperator, ssc/PatchPC.pyx:158-163 with the
         element kernel of ssc/patch.py:28-62): Ke[cell] is the element matrix of that cell, rows/columns in the order

@@ -693,3 +693,28 @@ def test_unsaved_operators_report_a_singular_block_and_option_state_is_consisten
         with pytest.raises(SSCError) as e:
             pc.setUp()
         assert e.value.ierr == 56
+
+
+def test_new_values_on_the_same_pattern():
+    """SSCPatchSetOperatorValues: the update path of a nonlinear solve (new values, same nonzero pattern) re-uploads only the
+    values; the result is that of a full setOperatorCSR with the new values."""
+    from ssc_b200 import SSCError
+    form, bcs, disc, A = _problem(plex.TensorPlex((4, 3, 3)), 3, "scalar")
+    o = make_oracle(disc, A)
+    x = rhs_vector(disc.total_dofs)
+    ref = o.apply(x)
+    free = np.setdiff1d(np.arange(x.size), disc.global_bc_nodes)
+    pc = make_gpu(form, bcs)
+    pc._compute_op = None
+    with pytest.raises((SSCError, ValueError)):
+        pc.setOperatorValues(A.data)                  # no pattern yet
+    pc.setOperatorCSR(A.indptr, A.indices, A.data)
+    pc.setUp()
+    y = np.zeros_like(x)
+    pc.apply(x, y)
+    assert relerr(y, ref) < TOL
+    for scale in (4.0, 0.5):
+        pc.setOperatorValues(scale * A.data)
+        pc.setUp()
+        pc.apply(x, y)
+        assert relerr(scale * y[free], ref[free]) < TOL
