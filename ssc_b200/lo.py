@@ -143,7 +143,7 @@ class P1PC(PCBase):
         prefix = pc.getOptionsPrefix() or ""
         opts = petsc_lite.Options(prefix)
         self.lo = LowOrderCore(self.device)
-        for name in ("lo_mat_type", "lo_ksp_type", "lo_pc_type", "lo_ksp_rtol", "lo_ksp_max_it"):    # ssc/lo.py:141, :164-166
+        for name in ("lo_mat_type", "lo_ksp_type", "lo_pc_type", "lo_ksp_rtol", "lo_ksp_max_it", "lo_ksp_cg_persistent"):    # ssc/lo.py:141, :164-166
             if opts.hasName(name):
                 self.lo.setOption(name, opts.getString(name))
         self.lo.setRestriction(restriction_matrix(J.spaces, lo_J.spaces, disc.ghost_bc_nodes, lo_disc.ghost_bc_nodes))
