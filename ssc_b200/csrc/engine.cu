@@ -127,7 +127,7 @@ struct SSCPatchPC_s {
     unsigned long long *d_kappa = nullptr;
     int factor_ctas = 0;          // concurrent CTAs of the blocked factor kernel (0 = fill the SMs)
     int factor_panel = 16;        // panel width of the blocked factor kernel (16 or 32)
-    int factor_variant = -1;      // -1 (default) by size: n <= 64 register tiles (1), 65..128 tensor-core Gauss-Jordan on the L2-resident block, four patches per SM (2),
+    int factor_variant = -1;      // -1 (default) by size: n <= 64 register tiles (1), 65..256 tensor-core Gauss-Jordan on the L2-resident block, several patches per SM (2),
                                   // larger blocked DMMA (3), beyond its shared-memory panels the in-place global-memory Gauss-Jordan (0); 0..3 force one where it applies
     int apply_variant = 1;        // 0: simple loop (also the fallback for patches too large for one thread per row), 1: pipelined LDG.64 (default)
     std::string sub_mat_type, sub_ksp_type = "preonly";

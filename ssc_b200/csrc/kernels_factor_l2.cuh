@@ -1,4 +1,4 @@
-// K2 for 32 < n <= 128, throughput form: blocked Gauss-Jordan with the block resident in L2 and SEVERAL patches in flight per SM.
+// K2 for 32 < n <= 256, throughput form: blocked Gauss-Jordan with the block resident in L2 and SEVERAL patches in flight per SM.
 //
 // Replaces the lazy PCSetUp_LU inside the first KSPSolve of every patch (ssc/libssc.c:1374) by an explicit inverse.
 //
@@ -6,7 +6,7 @@
 // lone warp group), and fp64 FMAs of that chain share the FP64 pipe with the tensor-core updates, so a design with ONE patch
 // per SM (tools/micro/factor_reg_dmma.cuh: block in registers as DMMA accumulators, panel one ahead; measured 142 ms at 64^3 Q3
 // against 118 ms here) cannot overlap the two: it costs chain + update.  Here a CTA is
-// 128 threads and five of them share an SM, each on its own patch, so the SM always has other patches' work to issue while
+// 128 threads and four of them share an SM (256 threads and two for 128 < n <= 256), each on its own patch, so the SM always has other patches' work to issue while
 // one waits in its chain; the price is that the block (125 KB at n = 125) lives in L2 and every panel's update streams it
 // through the SM once (2 MB of L2 traffic per patch; measured L2 read+write bandwidth 14 TB/s, tools/micro/l2_micro.cu).
 //
@@ -35,16 +35,18 @@ __device__ __forceinline__ void ssc_dmma_acc(double2 &c, double a, double b)
                  : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
 }
 
-template <bool kPivot, int NB>
-__global__ void __launch_bounds__(128, NB == 16 ? 4 : 3)
+// N = 128 (n <= 128, 128 threads, four CTAs per SM) or 256 (n <= 256, 256 threads, two CTAs per SM): N threads, thread = row.
+template <bool kPivot, int NB, int N>
+__global__ void __launch_bounds__(N, N == 256 ? 2 : (NB == 16 ? 4 : 3))
 ssc_invert_l2_kernel(double *__restrict__ blocks, int n, int ld, ll stride, ll count, int *__restrict__ fail_flags)
 {
-    constexpr int N = 128, QP = NB + 4, WP = N + 4;               // QP, WP = 4 mod 16: conflict-free A / B fragment loads
+    constexpr int QP = NB + 4, WP = N + 4, NWARP = N / 32;        // QP, WP = 4 mod 16: conflict-free A / B fragment loads
+    constexpr unsigned kRowMask = N - 1;                          // the pivot key packs N - 1 - row into its low bits
     extern __shared__ __align__(16) unsigned char l2_smem[];      // (N * QP + NB * WP) doubles
     double *Pbuf = reinterpret_cast<double *>(l2_smem);           // Q of the current panel
     double *Wbuf = Pbuf + N * QP;                                 // its pivot rows, all columns
     __shared__ __align__(16) double rowv[2][NB + 2];              // the pivot row of a step + the reciprocal of its pivot, by step parity
-    __shared__ __align__(16) unsigned keyb[2][4];
+    __shared__ __align__(16) unsigned keyb[2][NWARP];
     __shared__ int perm[N], rowk[N], qinv[N], leaders[N];
     __shared__ int s_fail, s_offdiag, s_nleaders;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gr = lane >> 2, gc = lane & 3;
@@ -71,7 +73,7 @@ ssc_invert_l2_kernel(double *__restrict__ blocks, int n, int ld, ll stride, ll c
                 }
             }
             if (kPivot) {
-                unsigned key = used ? 0u : (((unsigned)__double2hiint(pr[0]) & 0x7FFFFF80u) | (unsigned)(127 - i));
+                unsigned key = used ? 0u : (((unsigned)__double2hiint(pr[0]) & (0x7FFFFFFFu & ~kRowMask)) | (kRowMask - (unsigned)i));
                 key = __reduce_max_sync(0xffffffffu, key);
                 if (lane == 0) keyb[0][warp] = key;
             }
@@ -84,9 +86,13 @@ ssc_invert_l2_kernel(double *__restrict__ blocks, int n, int ld, ll stride, ll c
                 int prow = kb + s;
                 if (kPivot) {
                     __syncthreads();
-                    const uint4 k4 = *reinterpret_cast<const uint4 *>(keyb[cur]);
-                    const unsigned m = max(max(k4.x, k4.y), max(k4.z, k4.w));
-                    prow = 127 - (int)(m & 127u);
+                    unsigned m = 0;
+#pragma unroll
+                    for (int w4 = 0; w4 < NWARP / 4; ++w4) {
+                        const uint4 k4 = reinterpret_cast<const uint4 *>(keyb[cur])[w4];
+                        m = max(m, max(max(k4.x, k4.y), max(k4.z, k4.w)));
+                    }
+                    prow = (int)(kRowMask - (m & kRowMask));
                     if (m == 0) { bad = true; break; }                           // no candidate left (uniform)
                 }
                 const bool win = i == prow;
@@ -119,7 +125,7 @@ ssc_invert_l2_kernel(double *__restrict__ blocks, int n, int ld, ll stride, ll c
                 }
                 if (s + 1 < bw) {
                     if (kPivot) {
-                        unsigned key = used ? 0u : (((unsigned)__double2hiint(pr[s + 1]) & 0x7FFFFF80u) | (unsigned)(127 - i));
+                        unsigned key = used ? 0u : (((unsigned)__double2hiint(pr[s + 1]) & (0x7FFFFFFFu & ~kRowMask)) | (kRowMask - (unsigned)i));
                         key = __reduce_max_sync(0xffffffffu, key);
                         if (lane == 0) keyb[cur ^ 1][warp] = key;
                     }
@@ -153,7 +159,7 @@ ssc_invert_l2_kernel(double *__restrict__ blocks, int n, int ld, ll stride, ll c
             __syncthreads();
             // M <- M + Q W on the tensor cores; pivot rows of this panel start from zero
             const int ptile = kb >> 3;                                           // the panel is tile columns ptile .. ptile + NB/8 - 1
-            for (int ti = warp; ti < TR; ti += 4) {
+            for (int ti = warp; ti < TR; ti += NWARP) {
                 const int r = 8 * ti + gr;
                 const bool valid = r < n;
                 const bool fresh = valid && rowk[r] >= kb;
@@ -188,11 +194,13 @@ ssc_invert_l2_kernel(double *__restrict__ blocks, int n, int ld, ll stride, ll c
                         if (!skip && valid && j < ld) *reinterpret_cast<double2 *>(Mrow + j) = c[u];
                     }
                 };
-                double2 c0[8], c1[8];
-                load_strip(0, c0);
-                if (TR > 8) load_strip(8, c1);
-                finish_strip(0, c0);
-                if (TR > 8) finish_strip(8, c1);
+                for (int t0 = 0; t0 < TR; t0 += 16) {
+                    double2 c0[8], c1[8];
+                    load_strip(t0, c0);
+                    if (TR > t0 + 8) load_strip(t0 + 8, c1);
+                    finish_strip(t0, c0);
+                    if (TR > t0 + 8) finish_strip(t0 + 8, c1);
+                }
             }
             __syncthreads();
         }
@@ -204,24 +212,25 @@ ssc_invert_l2_kernel(double *__restrict__ blocks, int n, int ld, ll stride, ll c
             {
                 // 32 x 32 tile pairs through shared memory: 16 coalesced loads in flight per thread, coalesced stores
                 double *tA = Pbuf, *tB = Pbuf + 32 * 33;                         // two 32 x 33 tiles (17 KB of the 20 KB panel buffer)
-                const int nt = (n + 31) >> 5, cx = tid & 31, ry = tid >> 5;      // thread: column cx, rows ry, ry + 4, ...
+                const int nt = (n + 31) >> 5, cx = tid & 31, ry = tid >> 5;      // thread: column cx, rows ry, ry + NWARP, ...
+                constexpr int RPT = 32 / NWARP;                                  // rows of a 32 x 32 tile per thread
                 for (int ta = 0; ta < nt; ++ta)
                     for (int tb = ta; tb < nt; ++tb) {
-                        double va[8], vb[8];
+                        double va[RPT], vb[RPT];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int r = ry + 4 * k;
+                        for (int k = 0; k < RPT; ++k) {
+                            const int r = ry + NWARP * k;
                             const int ia = 32 * ta + r, ja = 32 * tb + cx;       // tile (ta, tb)
                             const int ib = 32 * tb + r, jb = 32 * ta + cx;       // tile (tb, ta)
                             va[k] = (ia < n && ja < n) ? B[(ll)ia * ld + ja] : 0.0;
                             vb[k] = (ib < n && jb < n) ? B[(ll)ib * ld + jb] : 0.0;
                         }
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) { tA[(ry + 4 * k) * 33 + cx] = va[k]; tB[(ry + 4 * k) * 33 + cx] = vb[k]; }
+                        for (int k = 0; k < RPT; ++k) { tA[(ry + NWARP * k) * 33 + cx] = va[k]; tB[(ry + NWARP * k) * 33 + cx] = vb[k]; }
                         __syncthreads();
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int r = ry + 4 * k;
+                        for (int k = 0; k < RPT; ++k) {
+                            const int r = ry + NWARP * k;
                             const int ia = 32 * ta + r, ja = 32 * tb + cx, ib = 32 * tb + r, jb = 32 * ta + cx;
                             if (ia < n && ja < n) B[(ll)ia * ld + ja] = tB[cx * 33 + r];     // (ta, tb)[r][cx] = (tb, ta)[cx][r]
                             if (ta != tb && ib < n && jb < n) B[(ll)ib * ld + jb] = tA[cx * 33 + r];
@@ -245,7 +254,7 @@ ssc_invert_l2_kernel(double *__restrict__ blocks, int n, int ld, ll stride, ll c
                     s_nleaders = nl;
                 }
                 __syncthreads();                                                 // also orders the transpose before the permutations
-                for (int col = tid; col < n; col += 128) {
+                for (int col = tid; col < n; col += N) {
                     for (int l = 0; l < s_nleaders; ++l) {
                         const int s0 = leaders[l];
                         // new[a] = old[qinv[a]]: walk a = s0, qinv[s0], ... keeping the first value for the last write
@@ -262,7 +271,7 @@ ssc_invert_l2_kernel(double *__restrict__ blocks, int n, int ld, ll stride, ll c
                 __syncthreads();
                 // columns: S[a][b] = row[perm[b]], a warp per row through a shared-memory copy of the row
                 double *rowbuf = Wbuf + warp * WP;
-                for (int a = warp; a < n; a += 4) {
+                for (int a = warp; a < n; a += NWARP) {
                     double *row = B + (ll)a * ld;
                     for (int b = lane; b < n; b += 32) rowbuf[b] = row[b];
                     __syncwarp();

@@ -161,7 +161,7 @@ def test_apply_kernel_variants(variant, shape, p, kind):
 
 
 @pytest.mark.parametrize("factor_variant", [-1, 0, 1, 2, 3])
-@pytest.mark.parametrize("n", [5, 33, 64, 65, 97, 100, 128, 150])
+@pytest.mark.parametrize("n", [5, 33, 64, 65, 97, 100, 128, 150, 200, 256, 300])
 def test_general_blocks_need_pivoting(n, factor_variant):
     """Non-symmetric operator with zero diagonal entries: -sub_pc_type lu must pivot.  Patches are arbitrary dof sets
     handed over with SSCPatchSetPatches; the oracle solves with LAPACK-style partial-pivot LU."""
@@ -181,7 +181,9 @@ def test_general_blocks_need_pivoting(n, factor_variant):
     lists = [np.sort(rng.choice(N, size=n, replace=False)) for _ in range(npatch)]
     # make every block nonsingular: include, for each row dof, the column where its big entry sits
     lists = [np.unique(np.concatenate([l[: n // 2], perm[l[: n // 2]]]))[:n] for l in lists]
-    lists = [l for l in lists if np.linalg.cond(A[l][:, l].toarray()) < 1e6]
+    # kappa <= 3e4: two correct fp64 solvers (the oracle's LU, a stored inverse) agree to ~kappa * eps, so north_star's 1e-12 is a statement about
+    # blocks in this range; worse-conditioned blocks are the subject of test_refined_sub_solve_on_ill_conditioned_blocks (against an exact-residual solve)
+    lists = [l for l in lists if np.linalg.cond(A[l][:, l].toarray()) < 3e4]
     assert lists
     off = np.concatenate(([0], np.cumsum([l.size for l in lists])))
     gtol = np.concatenate(lists)
@@ -219,7 +221,7 @@ def test_singular_block_is_reported(factor_variant):
 
 
 @pytest.mark.parametrize("factor_variant", [-1, 0, 1, 2, 3])
-@pytest.mark.parametrize("case", ["rank1_4", "nan_6", "zero_column_40", "zero_column_100", "zero_row_128", "zero_column_150"])
+@pytest.mark.parametrize("case", ["rank1_4", "nan_6", "zero_column_40", "zero_column_100", "zero_row_128", "zero_column_150", "zero_row_250"])
 def test_block_that_fails_early_is_reported(case, factor_variant):
     """A block whose elimination breaks down at an EARLY step (rank 1, a NaN entry, a zero column): the kernels must leave
     through their failure path with the permutation only partly written (the unguarded qinv[perm[tid]]),

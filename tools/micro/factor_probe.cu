@@ -38,12 +38,12 @@ int main(int argc, char **argv)
         cudaEventRecord(e0);
         if (kernel == 4) {
             const size_t sm4 = (size_t)(128 * 20 + 16 * 132) * sizeof(double);
-            cudaFuncSetAttribute(ssc_invert_l2_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
-            cudaFuncSetAttribute(ssc_invert_l2_kernel<true, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            cudaFuncSetAttribute(ssc_invert_l2_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
-            cudaFuncSetAttribute(ssc_invert_l2_kernel<false, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            if (pivot) ssc_invert_l2_kernel<true, 16><<<148 * ctas, 128, sm4>>>(d, n, ld, stride, count, fail);
-            else ssc_invert_l2_kernel<false, 16><<<148 * ctas, 128, sm4>>>(d, n, ld, stride, count, fail);
+            cudaFuncSetAttribute(ssc_invert_l2_kernel<true, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
+            cudaFuncSetAttribute(ssc_invert_l2_kernel<true, 16, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(ssc_invert_l2_kernel<false, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
+            cudaFuncSetAttribute(ssc_invert_l2_kernel<false, 16, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            if (pivot) ssc_invert_l2_kernel<true, 16, 128><<<148 * ctas, 128, sm4>>>(d, n, ld, stride, count, fail);
+            else ssc_invert_l2_kernel<false, 16, 128><<<148 * ctas, 128, sm4>>>(d, n, ld, stride, count, fail);
         } else if (pivot) ssc_invert_dmma_kernel<true, 4><<<148, 640, smem>>>(d, n, ld, stride, count, fail);
         else ssc_invert_dmma_kernel<false, 4><<<148, 640, smem>>>(d, n, ld, stride, count, fail);
         cudaEventRecord(e1); cudaEventSynchronize(e1);

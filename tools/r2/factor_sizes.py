@@ -3,13 +3,13 @@ import sys, numpy as np
 sys.path.insert(0, ".")
 from ssc_b200 import PC, fem, plex
 from ssc_b200.patch import setup_patch_pc
-cases = [((64, 64, 64), 3), ((1200, 1200), 4), ((700, 700), 5), ((500, 500), 6), ((400, 400), 7)]
+cases = [((64, 64, 64), 3), ((1200, 1200), 4), ((700, 700), 5), ((500, 500), 6), ((400, 400), 7), ((350, 350), 8)]
 for shape, p in cases:
     mesh = plex.TensorPlex(shape); V = fem.FunctionSpace(mesh, p); disc = fem.Discretisation([V])
     Ke = fem.element_matrix_tensor(V)
     for sub in ("lu", "cholesky"):
         out = []
-        for variant in (1, 2):
+        for variant in (1, 2, 3):
             pc = PC(0); setup_patch_pc(pc, disc, None); pc._compute_op = None
             pc.setElementMatrices(Ke)
             pc.setOption("sub_pc_type", sub); pc.setOption("ssc_factor_variant", variant)
