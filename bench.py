@@ -644,7 +644,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "ssc_apply_pipe_kernel<1,8> (+ ssc_apply_stream_kernel<8> for the small classes: all size-class launches of one apply; traffic = ncu capture of the dominant launch)", "kernel_ms": kernel_ms,
                 "algorithmic_bytes": bytes_apply, "stream_read_gbs_this_gpu": read_peak, "frac_of_stream_read": achieved / read_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
-    out = {"metric": METRIC if args.workload == "poisson_hex" else "PCApply dofs/s (3D vector P2 elasticity on tets, vertex-star patches, additive, fp64)", "value": nglobal / (ms_step * 1e-3), "unit": "dofs/s", "n_gpus": nranks, "steps": args.steps,
+    out = {"metric": METRIC.replace("Q3", "Q%d" % args.degree) if args.workload == "poisson_hex" else "PCApply dofs/s (3D vector P2 elasticity on tets, vertex-star patches, additive, fp64)", "value": nglobal / (ms_step * 1e-3), "unit": "dofs/s", "n_gpus": nranks, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling if nranks > 1 else "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(args, nranks),
            "dofs": nglobal, "patches_per_gpu": pc.size("npatch"), "hbm_gbs_step": bytes_apply * nranks / (ms_step * 1e-3) / 1e9,

@@ -111,9 +111,9 @@ struct SSCPatchPC_s {
     bool overlap_classes = true;
     int apply_stream_min_waves = 4;  // ... and only when every CTA gets at least this many rounds of patches (tests: 0)
     int apply_stream_ctas = 0;       // CTAs of the persistent kernel (0: fill the GPU; tests use a few to get many rounds on small cases)
-    int apply_stream_max_n = 96;     // largest patch the persistent apply kernel takes (n = 125: measured no better than the one-patch-per-CTA kernel)
-    bool apply_exact_groups = true;  // n < 32: a group has exactly n threads (false: n rounded up to a multiple of 8)
-    int apply_group_threads = 128;   // threads of a CTA that carries several small patches (n <= 96): 96 / 128 / 192 / 256 measured, tools/gpu_apply_sizes.py
+    static constexpr int apply_stream_max_n = 96;     // largest patch the persistent apply kernel takes (n = 125: measured no better than the one-patch-per-CTA kernel)
+    static constexpr bool apply_exact_groups = true;  // n < 32: a group has exactly n threads (measured against n rounded up to a multiple of 8)
+    static constexpr int apply_group_threads = 128;   // threads of a CTA that carries several small patches (n <= 96): 96 / 128 / 192 / 256 measured in round 1
     bool apply_stream_small = true;  // n <= 96: persistent apply kernel with the gathers prefetched across patches
     int sm_count = 148;
     size_t total_mem = (size_t)180 << 30;
@@ -210,9 +210,8 @@ struct SSCPatchPC_s {
     // element matrices (the reference's own source of the patch operators, ssc/libssc.c:1120-1156): borrowed like the CSR arrays
     bool elem_set = false, elem_owned = false, elem_lists_ready = false, elem_maps_ready = false;
     i64 elem_map_rows = 0, elem_dev_len = 0;
-    bool asm_shared = false;         // assemble kernel: accumulate in place through L2 (13.7 ms at 64^3 Q3) or in shared memory when the block fits (26 ms)
-    int asm_threads = 256;
-    int asm_ctas_per_sm = 16;        // blocks being accumulated at once per SM (their in-place working set competes for L2)
+    static constexpr int asm_threads = 256;
+    static constexpr int asm_ctas_per_sm = 16;        // blocks being accumulated at once per SM (their in-place working set competes for L2; sweep flat in round 1)
     const double *elem_K = nullptr;
     i64 elem_ncells = 0, elem_t = 0, elem_stride = 0;
     int elem_space = 0;

@@ -28,7 +28,7 @@ PATCH_OPTIONS = ("pc_patch_save_operators", "pc_patch_partition_of_unity", "pc_p
                  "pc_patch_vanka_dim", "pc_patch_vanka_space", "pc_patch_sub_mat_type", "pc_patch_print_patches",
                  "pc_patch_symmetrise_sweep", "pc_patch_exclude_subspace", "sub_ksp_type", "sub_pc_type",
                  "sub_pc_factor_mat_solver_type", "sub_pc_factor_mat_ordering_type",
-                 "ssc_keep_dofs_table", "ssc_keep_patch_operators", "ssc_builder_threads", "ssc_apply_variant", "ssc_factor_variant", "ssc_factor_panel", "ssc_extract_row_buffers", "ssc_sub_solve", "ssc_register_host_vectors", "ssc_refine_kappa", "ssc_refine_steps", "ssc_factor_ctas", "ssc_host_pipeline", "ssc_deterministic", "ssc_device_patch_construction", "ssc_symmetric_storage", "ssc_assemble_shared", "ssc_assemble_threads", "ssc_overlap_classes", "ssc_apply_stream_small", "ssc_apply_group_threads", "ssc_apply_stream_max_n", "ssc_apply_exact_groups", "ssc_host_pipeline_taper", "ssc_apply_stream_min_waves", "ssc_apply_stream_ctas", "ssc_assemble_ctas_per_sm")
+                 "ssc_keep_dofs_table", "ssc_keep_patch_operators", "ssc_builder_threads", "ssc_apply_variant", "ssc_factor_variant", "ssc_factor_panel", "ssc_extract_row_buffers", "ssc_sub_solve", "ssc_register_host_vectors", "ssc_refine_kappa", "ssc_refine_steps", "ssc_factor_ctas", "ssc_host_pipeline", "ssc_deterministic", "ssc_device_patch_construction", "ssc_symmetric_storage", "ssc_overlap_classes", "ssc_apply_stream_small", "ssc_host_pipeline_taper", "ssc_apply_stream_min_waves", "ssc_apply_stream_ctas")
 
 
 class DeviceVec(object):

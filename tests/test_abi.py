@@ -31,10 +31,12 @@ def test_no_torch_types_and_no_oracle_in_product():
     assert "torch" not in code.lower() and "at::" not in code and "cuda" not in code.lower()
     for dirpath, _, files in os.walk(os.path.join(ROOT, "ssc_b200")):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+            if f.endswith((".py", ".pyx", ".cu", ".cuh", ".inc", ".cpp", ".h")):      # .inc: the engine's functions by theme; .pyx: the Cython shim
                 src = open(os.path.join(dirpath, f)).read()
-                assert "import oracle" not in src and "from oracle" not in src and "ssc_oracle" not in src, f
+                assert "import oracle" not in src and "from oracle" not in src and "ssc_oracle" not in src and "oracle/" not in src, f
                 assert "import torch" not in src, f
+    scanned = [f for _, _, files in os.walk(os.path.join(ROOT, "ssc_b200")) for f in files]
+    assert any(f.endswith(".inc") for f in scanned) and any(f.endswith(".pyx") for f in scanned)
 
 
 def test_host_only_handle_builds_patches_but_never_computes():
@@ -99,10 +101,10 @@ def test_extension_options_are_range_checked_and_listed():
     parsed = set(re.findall(r'name == "(ssc_[a-z_0-9]+)"', src))
     assert parsed and parsed <= set(PATCH_OPTIONS), sorted(parsed - set(PATCH_OPTIONS))
     pc = PC(device=-1)
-    for name, bad in (("ssc_factor_variant", 9), ("ssc_apply_group_threads", 16), ("ssc_apply_group_threads", 1024), ("ssc_assemble_threads", 100)):
+    for name, bad in (("ssc_factor_variant", 9), ("ssc_apply_variant", 2), ("ssc_refine_steps", 0), ("ssc_sub_solve", "gmres")):
         with pytest.raises(SSCError):
             pc.setOption(name, bad)
-    for name, ok in (("ssc_factor_variant", 2), ("ssc_apply_group_threads", 128), ("ssc_host_pipeline_taper", "false"), ("ssc_apply_exact_groups", True)):
+    for name, ok in (("ssc_factor_variant", 2), ("ssc_refine_steps", 2), ("ssc_host_pipeline_taper", "false"), ("ssc_sub_solve", "auto")):
         pc.setOption(name, ok)
 
 

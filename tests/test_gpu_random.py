@@ -148,8 +148,7 @@ def test_degenerate_inputs():
     assert y[4] == x[4] / 4.0 and np.count_nonzero(y) == 1
 
 
-@pytest.mark.parametrize("opts", [{}, {"ssc_deterministic": True}, {"pc_patch_partition_of_unity": True}, {"ssc_apply_exact_groups": False},
-                                  {"ssc_apply_group_threads": 192}], ids=["default", "deterministic", "pou", "padded-groups", "192-threads"])
+@pytest.mark.parametrize("opts", [{}, {"ssc_deterministic": True}, {"pc_patch_partition_of_unity": True}], ids=["default", "deterministic", "pou"])
 @pytest.mark.parametrize("ctas", [1, 3])
 def test_persistent_apply_kernel_many_rounds(ctas, opts):
     """The persistent small-patch apply kernel (n <= 96) prefetches the gathers of the next two patches while one streams.

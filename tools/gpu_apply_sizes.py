@@ -27,8 +27,7 @@ def case(name, mesh, p, opts=()):
     print("%-22s n_max %4d  dofs %9d  bytes %.2f GB  %.3f ms  %.2f Gdof/s  frac of measured HBM %.3f %s" % (name, int(np.diff(pc.getPatches()[0]).max()), disc.total_dofs, b / 1e9, ms, disc.total_dofs / ms / 1e6, b / (ms * 1e-3) / 1e9 / peak, dict(opts) or ""), flush=True)
     pc.destroy()
 
-for ex in (False, True):
-    opts = (("ssc_apply_exact_groups", ex),)
+for opts in ((),):
     case("3D Q1 160^3", plex.TensorPlex((160, 160, 160)), 1, opts)
     case("2D Q2 1536^2", plex.TensorPlex((1536, 1536)), 2, opts)
     case("2D Q3 1024^2", plex.TensorPlex((1024, 1024)), 3, opts)

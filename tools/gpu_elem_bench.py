@@ -10,7 +10,7 @@ mesh = plex.TensorPlex((N, N, N)); V = fem.FunctionSpace(mesh, 3); disc = fem.Di
 Ke = fem.element_matrix_tensor(V)
 x = np.random.default_rng(0).uniform(-1, 1, disc.total_dofs)
 ys = []
-VAR = [("csr", {}), ("shared Ke", {}), ("shared Ke", {"ssc_assemble_threads": 512}), ("per-cell Ke", {}), ("shared Ke", {"ssc_builder_threads": 4}), ("shared Ke", {"ssc_builder_threads": 16}), ("shared Ke", {"ssc_builder_threads": 32})]
+VAR = [("csr", {}), ("shared Ke", {}), ("per-cell Ke", {}), ("shared Ke", {"ssc_builder_threads": 4}), ("shared Ke", {"ssc_builder_threads": 16}), ("shared Ke", {"ssc_builder_threads": 32})]
 for name, opts in VAR:
     pc = PC(0); setup_patch_pc(pc, disc, None); pc._compute_op = None
     if name == "csr":
