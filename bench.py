@@ -194,7 +194,7 @@ def window_oracle(args, nthreads):
     o.setUpOperators(nthreads=1 if args.cpu_setup_serial else nthreads)
     t3 = time.perf_counter()
     return o, V, {"mesh_and_operator_s": t1 - t0, "patch_lists_s": t2 - t1, "operators_and_lu_s": t3 - t2,
-                  "operators_and_lu_threads": 1 if args.cpu_setup_serial else nthreads}
+                  "operators_and_lu_threads": 1 if args.cpu_setup_serial else nthreads}, csr
 
 
 def hex_census(c, p):
@@ -202,6 +202,11 @@ def hex_census(c, p):
     products of the 1D sizes 2p-1 (interior vertex) and p-1 (boundary vertex))."""
     one = np.array([p - 1] + [2 * p - 1] * (c - 1) + [p - 1], dtype=np.float64)
     return (c + 1) ** 3, float(one.sum()) ** 3, float((one ** 2).sum()) ** 3
+
+
+def hex_census_n3(c, p):
+    one = np.array([p - 1] + [2 * p - 1] * (c - 1) + [p - 1], dtype=np.float64)
+    return float((one ** 3).sum()) ** 3
 
 
 def cpu_baseline(args, nthreads=None, x_lat=None, y_lat=None):
@@ -212,7 +217,7 @@ def cpu_baseline(args, nthreads=None, x_lat=None, y_lat=None):
     x_lat / y_lat: optional global input and GPU result as lattice arrays (X, Y, Z) for the parity sample."""
     nthreads = nthreads or os.cpu_count() or 1
     c, p = args.cells, args.degree
-    o, V, times = window_oracle(args, nthreads)
+    o, V, times, synth_csr = window_oracle(args, nthreads)
     off, _ = o.patches()
     sizes = np.diff(off).astype(np.float64)
     npatch_all, sum_n_all, sum_n2_all = hex_census(c, p)
@@ -225,6 +230,20 @@ def cpu_baseline(args, nthreads=None, x_lat=None, y_lat=None):
         xs[node] = x_lat[L[0] + (k - 3) * p, L[1], L[2]] if c > 6 else x_lat[L[0], L[1], L[2]]
     else:
         xs = np.random.default_rng(20260101).uniform(-1, 1, V.node_count)
+    # the reference's set-up is serial per rank: time dof lists (already serial above) and extraction + LU on ONE core for a slice of
+    # 1024 mid-window patches, scaled to the whole mesh by sum n^3 (the LU) -- with the one-core apply this gives its set-up + first apply
+    from oracle import oracle as _oracle
+    _, gtol_all = o.patches()
+    mid = max(0, sizes.size // 2 - 512)
+    sl = slice(mid, min(sizes.size, mid + 1024))
+    o1 = _oracle.OraclePatchPC()
+    o1.setPatches(off[sl.start:sl.stop + 1] - off[sl.start], gtol_all[off[sl.start]:off[sl.stop]], V.node_count)
+    o1.setOperatorCSRArrays(*synth_csr)
+    t0 = time.perf_counter()
+    o1.setUpOperators(nthreads=1)
+    lu1 = time.perf_counter() - t0
+    n3_frac = float((sizes[sl] ** 3).sum() / hex_census_n3(c, p))
+    times["operators_and_lu_one_core_s_full_estimate"] = lu1 / n3_frac
     yo = o.apply(xs, nthreads=nthreads)           # warm-up; also the parity sample below
     parity = None
     if y_lat is not None:
@@ -257,7 +276,8 @@ def cpu_baseline(args, nthreads=None, x_lat=None, y_lat=None):
                               "the reference factorises lazily inside the first KSPSolve (ssc/libssc.c:1374), so its set-up cost = these + the first apply",
                       "window": times, "patch_lists_s_full_estimate": times["patch_lists_s"] / pfrac,
                       "operators_and_lu_s_full_estimate": times["operators_and_lu_s"] / pfrac,
-                      "setup_plus_first_apply_s_full_estimate_one_core": None if not args.cpu_setup_serial else (times["patch_lists_s"] + times["operators_and_lu_s"]) / pfrac + per1 / frac},
+                      "operators_and_lu_one_core_s_full_estimate": times["operators_and_lu_one_core_s_full_estimate"],
+                      "setup_plus_first_apply_s_full_estimate_one_core": times["patch_lists_s"] / pfrac + times["operators_and_lu_one_core_s_full_estimate"] + per1 / frac},
             "parity": parity}
 
 

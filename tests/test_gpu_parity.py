@@ -720,3 +720,35 @@ def test_new_values_on_the_same_pattern():
         pc.setUp()
         pc.apply(x, y)
         assert relerr(scale * y[free], ref[free]) < TOL
+
+
+def test_very_large_patch_takes_the_unlimited_paths():
+    """nothing on the path may cap the patch size below what the reference's sub-KSP takes.  One patch of
+    1500 dofs (a whole small operator, the shape of a coarse space handed to the patch engine): the extract kernel's shared
+    memory is no longer tied to n, the factorisation falls back to the in-place global-memory Gauss-Jordan once the blocked
+    kernel's panels stop fitting shared memory, and the apply kernel walks several rows per thread."""
+    import scipy.sparse as sp
+    from ssc_b200 import PC
+    from oracle.oracle import OraclePatchPC
+    n = 1500
+    rng = np.random.default_rng(3)
+    M = sp.random(n, n, density=0.01, random_state=rng, format="csr")
+    A = (M + M.T + sp.diags(np.full(n, 12.0))).tocsr()
+    A.sort_indices()
+    B = sp.block_diag([A, sp.identity(7)]).tocsr()
+    off, gtol, N = np.array([0, n, n + 7]), np.arange(n + 7), n + 7
+    o = OraclePatchPC()
+    o.setPatches(off, gtol, N)
+    o.setOperatorCSR(B)
+    o.setUpOperators()
+    x = rhs_vector(N)
+    ref = o.applyLocal(x)
+    for sub in ("lu", "cholesky"):
+        pc = PC(device=0)
+        pc.setOption("sub_pc_type", sub)
+        pc.setPatches(off, gtol, N)
+        pc.setOperatorCSR(B.indptr, B.indices, B.data)
+        pc.setUp()
+        y = np.zeros(N)
+        pc.apply(x, y)
+        assert relerr(y, ref) < TOL
