@@ -453,7 +453,8 @@ def main():
 
     pc = PC(device=local_rank)
     exchange = None
-    pc.setOption("ssc_builder_threads", max(1, min(32, (os.cpu_count() or 1) // nranks)))
+    if nranks > 1:                               # N = 1: the library splits the cores between the patch builder and the upload itself
+        pc.setOption("ssc_builder_threads", max(1, min(32, (os.cpu_count() or 1) // nranks)))
     setup_patch_pc(pc, disc, None)
     pc._compute_op = None
     if elements:
@@ -501,7 +502,7 @@ def main():
     pc.setUp()
     pc.synchronize()
     info["t_setup_wall"] = time.time() - t0
-    first = {k: pc.eventTime(k) for k in ("PCPATCHCreate", "PCPATCHComputeOp", "PCPATCHSolve", "SSCSetupLists", "SSCSetupUploadOperator", "SSCSetupAllocBlocks", "SSCSetupKernels", "SSCSetupFreeOperator")}
+    first = {k: pc.eventTime(k) for k in ("PCPATCHCreate", "PCPATCHComputeOp", "PCPATCHSolve", "SSCSetupLists", "SSCSetupUploadOperator", "SSCSetupAllocBlocks", "SSCSetupKernels", "SSCSetupFreeOperator", "SSCListsSort", "SSCListsPack", "SSCListsUpload", "SSCListsTail")}
     # the second set-up (new values, same shape: what every Newton step of a nonlinear solve pays, PatchPC.update ssc/patch.py:269-270)
     if not elements:
         pc.setOperatorValues(csr[2])          # same nonzero pattern: only the values travel again
@@ -516,6 +517,7 @@ def main():
         csr = None
     setup = {"note": "setup_wall_s = SSCPatchSetUp with the CSR in pageable host memory: patch construction on the host, H2D of dof lists and CSR, extract, factor" if not elements else "setup_wall_s = SSCPatchSetUp from one shared element matrix: patch construction on the host, H2D of dof lists / cell lists / cell-node maps, assemble kernel (extract_ms), factor", "create_patches_ms": first["PCPATCHCreate"], "extract_ms": first["PCPATCHComputeOp"],
              "factor_ms": first["PCPATCHSolve"], "lists_ms": first["SSCSetupLists"], "upload_operator_ms": first["SSCSetupUploadOperator"],
+             "lists_sort_ms": first["SSCListsSort"], "lists_pack_ms": first["SSCListsPack"], "lists_upload_ms": first["SSCListsUpload"], "lists_tail_ms": first["SSCListsTail"],
              "alloc_blocks_ms": first["SSCSetupAllocBlocks"], "kernels_wall_ms": first["SSCSetupKernels"], "free_operator_ms": first["SSCSetupFreeOperator"], "setup_wall_s": info["t_setup_wall"],
              "assemble_wall_s": info["t_assemble"], "mesh_wall_s": info["t_mesh"]}
     setup.update(resetup)

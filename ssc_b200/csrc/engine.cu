@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 #include <dlfcn.h>
+#include <array>
+#include <atomic>
 #include <thread>
 
 // ---------------------------------------------------------------------------------------------
@@ -221,9 +223,25 @@ struct SSCPatchPC_s {
     std::vector<int *> d_cnm;        // device copies of the cell-node maps
     ElemSpaces espaces;
     void *d_flush = nullptr;
-    void *stage[3] = {nullptr, nullptr, nullptr};      // pinned staging ring for large pageable uploads
-    cudaEvent_t stage_ev[3] = {nullptr, nullptr, nullptr};
-    bool stage_busy[3] = {false, false, false};
+    // milestones of the values upload: mark k is recorded on up_stream once the first mark_bytes[k] bytes of the CSR values are on their way,
+    // so extract + factor of the patches whose rows lie below it start while the rest still travels (SSCPatchSetUp)
+    static constexpr int kUploadMarks = 16;
+    cudaEvent_t mark_ev[kUploadMarks] = {};
+    size_t mark_bytes[kUploadMarks] = {};
+    std::atomic<int> marks_recorded{0};
+    cudaEvent_t pattern_ev = nullptr;                 // rowptr + colidx are on their way
+    std::atomic<int> pattern_recorded{0};
+    std::atomic<int> upload_finished{0};              // the uploader thread has returned (with or without an error)
+    bool marks_active = false;                        // this set-up uploads host CSR values with milestones
+    std::vector<int> patch_maxrow;                    // per sorted patch: the largest row it reads
+    std::atomic<int> upload_pause{0};                 // the staged upload issues no new chunk while set: the dof lists (needed first) get the copy engine to themselves
+    std::atomic<int> builder_busy{0};                 // the patch builder is running: only stage_threads staging threads work
+    int stage_threads = 0;                            // host threads of the staged upload (chosen per set-up)
+    int builder_threads_auto = 0;                     // patch-builder threads when ssc_builder_threads is not set and an upload runs beside it
+    static constexpr int kStageRing = 4;
+    void *stage[kStageRing] = {nullptr, nullptr, nullptr, nullptr};      // pinned staging ring for large pageable uploads
+    cudaEvent_t stage_ev[kStageRing] = {nullptr, nullptr, nullptr, nullptr};
+    bool stage_busy[kStageRing] = {false, false, false, false};
     // pipelined host-space apply: H2D of x, patch kernels and D2H of y overlap slab by slab
     int pipe_slabs = 12;
     bool pipe_force = false;
