@@ -752,3 +752,46 @@ def test_very_large_patch_takes_the_unlimited_paths():
         y = np.zeros(N)
         pc.apply(x, y)
         assert relerr(y, ref) < TOL
+
+
+@pytest.mark.parametrize("order", ["ascending", "scrambled"])
+def test_setup_overlapped_with_a_large_upload(order):
+    """An operator whose values exceed the staging threshold (64 MB) travels through the pinned ring with milestones, and
+    extract + factor of a patch start once the rows it reads have arrived (SSCPatchSetUp).  Patches in row order take
+    their milestones one by one; scrambled patches of a large class are held back by a running maximum, and a small
+    class waits for its last patch.  Either way the result is the oracle's, also after new values on the same pattern."""
+    import scipy.sparse as sp
+    from ssc_b200 import PC
+    from oracle.oracle import OraclePatchPC
+    N, band = 200_000, 22
+    rng = np.random.default_rng(11)
+    diags = [rng.uniform(-1.0, 1.0, N - abs(k)) for k in range(-band, band + 1)]
+    diags[band] = np.full(N, 3.0 * band)
+    A = sp.diags(diags, list(range(-band, band + 1)), format="csr")
+    A.sort_indices()
+    assert A.nnz * 8 >= 64 << 20
+    starts_big = rng.integers(0, N - 64, 6000)                   # a class of 6000 patches with 24 dofs: per-milestone ranges
+    starts_small = rng.integers(0, N - 64, 900)                  # a class of 900 patches with 40 dofs: one range
+    if order == "ascending":
+        starts_big.sort()
+        starts_small.sort()
+    lists = [s + np.sort(rng.choice(60, 24, replace=False)) for s in starts_big] + [s + np.sort(rng.choice(60, 40, replace=False)) for s in starts_small]
+    off = np.concatenate([[0], np.cumsum([len(l) for l in lists])])
+    gtol = np.concatenate(lists)
+    o = OraclePatchPC()
+    o.setPatches(off, gtol, N)
+    o.setOperatorCSR(A)
+    o.setUpOperators()
+    x = rhs_vector(N)
+    ref = o.applyLocal(x)
+    pc = PC(device=0)
+    pc.setPatches(off, gtol, N)
+    pc.setOperatorCSR(A.indptr, A.indices, A.data)
+    pc.setUp()
+    y = np.zeros(N)
+    pc.apply(x, y)
+    assert relerr(y, ref) < TOL
+    pc.setOperatorValues(2.0 * A.data)
+    pc.setUp()
+    pc.apply(x, y)
+    assert relerr(2.0 * y, ref) < TOL
