@@ -1,4 +1,4 @@
-// K2 for 32 < n <= 256, throughput form: blocked Gauss-Jordan with the block resident in L2 and SEVERAL patches in flight per SM.
+// K2 for 32 < n <= 512, throughput form: blocked Gauss-Jordan with the block resident in L2 and SEVERAL patches in flight per SM.
 //
 // Replaces the lazy PCSetUp_LU inside the first KSPSolve of every patch (ssc/libssc.c:1374) by an explicit inverse.
 //
@@ -35,9 +35,9 @@ __device__ __forceinline__ void ssc_dmma_acc(double2 &c, double a, double b)
                  : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
 }
 
-// N = 128 (n <= 128, 128 threads, four CTAs per SM) or 256 (n <= 256, 256 threads, two CTAs per SM): N threads, thread = row.
+// N = 128 (n <= 128, 128 threads, four CTAs per SM), 256 (n <= 256, two CTAs per SM) or 512 (n <= 512, one CTA per SM): N threads, thread = row.
 template <bool kPivot, int NB, int N>
-__global__ void __launch_bounds__(N, N == 256 ? 2 : (NB == 16 ? 4 : 3))
+__global__ void __launch_bounds__(N, N == 512 ? 1 : (N == 256 ? 2 : (NB == 16 ? 4 : 3)))
 ssc_invert_l2_kernel(double *__restrict__ blocks, int n, int ld, ll stride, ll count, int *__restrict__ fail_flags)
 {
     constexpr int QP = NB + 4, WP = N + 4, NWARP = N / 32;        // QP, WP = 4 mod 16: conflict-free A / B fragment loads

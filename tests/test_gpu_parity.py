@@ -161,7 +161,7 @@ def test_apply_kernel_variants(variant, shape, p, kind):
 
 
 @pytest.mark.parametrize("factor_variant", [-1, 0, 1, 2, 3])
-@pytest.mark.parametrize("n", [5, 33, 64, 65, 97, 100, 128, 150, 200, 256, 300])
+@pytest.mark.parametrize("n", [5, 33, 64, 65, 97, 100, 128, 150, 200, 256, 257, 300, 343, 512, 520])
 def test_general_blocks_need_pivoting(n, factor_variant):
     """Non-symmetric operator with zero diagonal entries: -sub_pc_type lu must pivot.  Patches are arbitrary dof sets
     handed over with SSCPatchSetPatches; the oracle solves with LAPACK-style partial-pivot LU."""
@@ -221,7 +221,7 @@ def test_singular_block_is_reported(factor_variant):
 
 
 @pytest.mark.parametrize("factor_variant", [-1, 0, 1, 2, 3])
-@pytest.mark.parametrize("case", ["rank1_4", "nan_6", "zero_column_40", "zero_column_100", "zero_row_128", "zero_column_150", "zero_row_250"])
+@pytest.mark.parametrize("case", ["rank1_4", "nan_6", "zero_column_40", "zero_column_100", "zero_row_128", "zero_column_150", "zero_row_250", "zero_column_343", "zero_row_500"])
 def test_block_that_fails_early_is_reported(case, factor_variant):
     """A block whose elimination breaks down at an EARLY step (rank 1, a NaN entry, a zero column): the kernels must leave
     through their failure path with the permutation only partly written (the unguarded qinv[perm[tid]]),

@@ -1,6 +1,6 @@
 // Stand-alone timing harness of the DMMA factor kernels: the L2-resident one that ships (ssc_b200/csrc/kernels_factor_l2.cuh, kernel = 4)
 // and the register-resident one that was measured and rejected (tools/micro/factor_reg_dmma.cuh, kernel = 2).
-// usage: factor_probe [n] [count] [pivot 0|1] [kernel 2|4] [CTAs per SM of kernel 4]
+// usage: factor_probe [n] [count] [pivot 0|1] [kernel 2|3|4] [CTAs per SM of kernel 3 / 4]   (3: the blocked shared-memory-panel kernel of kernels_factor.cuh)
 // Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo [-DSSC_DMMA_PROBE=k] -o tools/micro/factor_probe tools/micro/factor_probe.cu
 //   SSC_DMMA_PROBE = 0 the kernel as shipped; 1 tensor-core updates skipped (what the pivot chain alone costs);
 //                    2 panel steps skipped (what the updates and the data movement alone cost).  Results of 1 and 2 are garbage by design.
@@ -9,6 +9,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../ssc_b200/csrc/kernels_factor_l2.cuh"
+#include "../../ssc_b200/csrc/kernels_factor.cuh"
 #include "factor_reg_dmma.cuh"
 
 int main(int argc, char **argv)
@@ -37,13 +38,25 @@ int main(int argc, char **argv)
         cudaMemcpy(d, d0, h.size() * sizeof(double), cudaMemcpyDeviceToDevice);
         cudaEventRecord(e0);
         if (kernel == 4) {
-            const size_t sm4 = (size_t)(128 * 20 + 16 * 132) * sizeof(double);
-            cudaFuncSetAttribute(ssc_invert_l2_kernel<true, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
-            cudaFuncSetAttribute(ssc_invert_l2_kernel<true, 16, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            cudaFuncSetAttribute(ssc_invert_l2_kernel<false, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
-            cudaFuncSetAttribute(ssc_invert_l2_kernel<false, 16, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            if (pivot) ssc_invert_l2_kernel<true, 16, 128><<<148 * ctas, 128, sm4>>>(d, n, ld, stride, count, fail);
-            else ssc_invert_l2_kernel<false, 16, 128><<<148 * ctas, 128, sm4>>>(d, n, ld, stride, count, fail);
+#define RUN_L2(NV)                                                                                                          \
+    do {                                                                                                                    \
+        const size_t sm4 = (size_t)(NV * 20 + 16 * (NV + 4)) * sizeof(double);                                               \
+        cudaFuncSetAttribute(ssc_invert_l2_kernel<true, 16, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);     \
+        cudaFuncSetAttribute(ssc_invert_l2_kernel<true, 16, NV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);       \
+        cudaFuncSetAttribute(ssc_invert_l2_kernel<false, 16, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);    \
+        cudaFuncSetAttribute(ssc_invert_l2_kernel<false, 16, NV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);      \
+        if (pivot) ssc_invert_l2_kernel<true, 16, NV><<<148 * ctas, NV, sm4>>>(d, n, ld, stride, count, fail);                \
+        else ssc_invert_l2_kernel<false, 16, NV><<<148 * ctas, NV, sm4>>>(d, n, ld, stride, count, fail);                     \
+    } while (0)
+            if (n <= 128) RUN_L2(128); else if (n <= 256) RUN_L2(256); else RUN_L2(512);
+#undef RUN_L2
+        } else if (kernel == 3) {
+            const int npad8 = (n + 7) & ~7, WPb = ((npad8 + 15) & ~15) + 4, nb = 16;
+            const size_t smem_b = ((size_t)npad8 * (nb + 1) + (size_t)nb * WPb + nb + 32) * sizeof(double) + (size_t)(34 + 2 * n + 2) * sizeof(int);
+            cudaFuncSetAttribute(ssc_invert_blocked_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+            cudaFuncSetAttribute(ssc_invert_blocked_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+            if (pivot) ssc_invert_blocked_kernel<true, 16><<<148 * ctas, 512, smem_b>>>(d, n, ld, stride, count, fail);
+            else ssc_invert_blocked_kernel<false, 16><<<148 * ctas, 512, smem_b>>>(d, n, ld, stride, count, fail);
         } else if (pivot) ssc_invert_dmma_kernel<true, 4><<<148, 640, smem>>>(d, n, ld, stride, count, fail);
         else ssc_invert_dmma_kernel<false, 4><<<148, 640, smem>>>(d, n, ld, stride, count, fail);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
