@@ -19,6 +19,7 @@ int main(int argc, char **argv)
     const int pivot = argc > 3 ? atoi(argv[3]) : 1;
     const int kernel = argc > 4 ? atoi(argv[4]) : 2;      // 2 register-resident, 4 L2-resident
     const int ctas = argc > 5 ? atoi(argv[5]) : 4;
+    const int nbarg = argc > 6 ? atoi(argv[6]) : 16;     // panel width of kernel 4 (32: n <= 128, pivoting only)
     const int ld = (n + 1) & ~1;
     const long long stride = ((long long)n * ld + 15) / 16 * 16;
     std::vector<double> h((size_t)stride * count, 0.0);
@@ -48,7 +49,12 @@ int main(int argc, char **argv)
         if (pivot) ssc_invert_l2_kernel<true, 16, NV><<<148 * ctas, NV, sm4>>>(d, n, ld, stride, count, fail);                \
         else ssc_invert_l2_kernel<false, 16, NV><<<148 * ctas, NV, sm4>>>(d, n, ld, stride, count, fail);                     \
     } while (0)
-            if (n <= 128) RUN_L2(128); else if (n <= 256) RUN_L2(256); else RUN_L2(512);
+            if (nbarg == 32 && n <= 128) {
+                const size_t sm4 = (size_t)(128 * 36 + 32 * 132) * sizeof(double);
+                cudaFuncSetAttribute(ssc_invert_l2_kernel<true, 32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
+                cudaFuncSetAttribute(ssc_invert_l2_kernel<true, 32, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                ssc_invert_l2_kernel<true, 32, 128><<<148 * ctas, 128, sm4>>>(d, n, ld, stride, count, fail);
+            } else if (n <= 128) RUN_L2(128); else if (n <= 256) RUN_L2(256); else RUN_L2(512);
 #undef RUN_L2
         } else if (kernel == 3) {
             const int npad8 = (n + 7) & ~7, WPb = ((npad8 + 15) & ~15) + 4, nb = 16;
