@@ -205,7 +205,10 @@ int SSCEventDestroy(SSCPatchPC pc, void *ev);
  * the KSP/PC its options name (ssc/lo.py:164-166); here, under the same option names:
  *   lo_ksp_type preonly + lo_pc_type lu | cholesky : dense factorisation on the device, coarse spaces up to 4096 dofs;
  *   lo_ksp_type cg + lo_pc_type jacobi [lo_ksp_rtol 1e-10, lo_ksp_max_it 10000] : device-resident preconditioned conjugate
- *       gradients on the coarse CSR operator, any size (the Q1 space of a 64^3 mesh has 274 625 dofs).
+ *       gradients on the coarse CSR operator, any size (the Q1 space of a 64^3 mesh has 274 625 dofs);
+ *   lo_pc_type gamg : smoothed-aggregation multigrid (hierarchy built on the host at SetUp, V(1,1) cycle on the device), under
+ *       lo_ksp_type cg as the preconditioner of that CG, under lo_ksp_type preonly as ONE cycle per apply (a fixed symmetric
+ *       positive operator).  Built on the constant near-nullspace: scalar coarse operators.
  * lo_mat_type is accepted and ignored. */
 typedef struct SSCLowOrderPC_s *SSCLowOrderPC;
 int SSCLowOrderCreate(int device, SSCLowOrderPC *lo);                       /* P1PC.__init__            ssc/lo.py:107-110 */

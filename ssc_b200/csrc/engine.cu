@@ -316,4 +316,5 @@ static inline int grid_for(i64 n, int block) { i64 g = (n + block - 1) / block; 
 #include "engine_setup.inc"            // operator upload, extract / assemble + factor, weights, SSCPatchSetUp
 #include "engine_apply.inc"            // apply: device-resident, multiplicative, pipelined host-space applies
 #include "engine_introspect.inc"       // introspection, device plumbing, device patch construction
+#include "coarse_amg.inc"              // smoothed-aggregation hierarchy of the coarse solver (host)
 #include "engine_loworder.inc"         // low-order (P1) coarse correction

@@ -248,3 +248,114 @@ ssc_cg_persistent_kernel(ll n, const ll *__restrict__ rowptr, const int *__restr
     }
     if (gtid == 0) *its_out = k < 0 ? -1 : k;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Multigrid cycle and preconditioned CG of the coarse solve with -lo_pc_type gamg (coarse_amg.inc, engine_loworder.inc).
+// One kernel shape for every sparse product of the cycle: eight lanes per row, four rows per warp (level operators have
+// 24 - 60 entries per row, transfer operators 1 - 30).
+//   kAmgProduct   out = A x               restriction  b_c = R t
+//   kAmgResidual  out = b - A x
+//   kAmgAdd       out = out + A x         prolongation x += P x_c
+//   kAmgJacobi    out = x + w (b - A x)   damped Jacobi sweep, out != x
+// ---------------------------------------------------------------------------------------------
+enum { kAmgProduct = 0, kAmgResidual = 1, kAmgAdd = 2, kAmgJacobi = 3 };
+template <int MODE>
+__global__ void __launch_bounds__(256)
+ssc_amg_row_kernel(ll n, const ll *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals,
+                   const double *__restrict__ x, const double *__restrict__ b, const double *__restrict__ w, double *out)
+{
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    const ll gwarp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    for (ll base = 4 * gwarp; base < n; base += 4 * nwarps) {                 // warp-uniform trip count (full-mask shuffles below)
+        const ll row = base + (lane >> 3);
+        double a = 0.0;
+        if (row < n) for (ll e = rowptr[row] + sub; e < rowptr[row + 1]; e += 8) a = fma(vals[e], __ldg(x + colidx[e]), a);
+        a += __shfl_down_sync(0xffffffffu, a, 4, 8);
+        a += __shfl_down_sync(0xffffffffu, a, 2, 8);
+        a += __shfl_down_sync(0xffffffffu, a, 1, 8);
+        if (sub == 0 && row < n) {
+            if (MODE == kAmgProduct) out[row] = a;
+            else if (MODE == kAmgResidual) out[row] = b[row] - a;
+            else if (MODE == kAmgAdd) out[row] += a;
+            else out[row] = fma(w[row], b[row] - a, x[row]);
+        }
+    }
+}
+// x = w b: a damped Jacobi sweep from a zero initial guess
+__global__ void ssc_amg_scale_kernel(ll n, const double *__restrict__ w, const double *__restrict__ b, double *__restrict__ x)
+{
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) x[i] = w[i] * b[i];
+}
+// Preconditioned CG with the preconditioner applied between kernels (z = M^-1 r is a multigrid cycle).  s = {rz, pq, rz_new, rr}:
+//   start:      x = 0, r = rhs, rr += r.r                                   (s zeroed by the caller)
+//   [cycle]  dot: rz_new += r.z (zeroes pq)   direction(first): p = z
+//   product:    rz = rz_new, rz_new = rr = 0;  q = A p;  pq += p.q
+//   update:     alpha = rz / pq;  x += alpha p;  r -= alpha q;  rr += r.r     (the host reads rr here)
+//   [cycle]  dot: rz_new += r.z (zeroes pq)   direction: beta = rz_new / rz;  p = z + beta p
+// A kernel only zeroes or moves scalars that no thread of the same kernel reads.
+__global__ void __launch_bounds__(256)
+ssc_pcg_start_kernel(ll n, const double *__restrict__ rhs, double *__restrict__ x, double *__restrict__ r, double *__restrict__ s)
+{
+    double rr = 0.0;
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) { const double ri = rhs[i]; x[i] = 0.0; r[i] = ri; rr = fma(ri, ri, rr); }
+    block_sum_atomic(rr, s + 3);
+}
+__global__ void __launch_bounds__(256)
+ssc_pcg_product_kernel(ll n, const ll *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals,
+                       const double *__restrict__ p, double *__restrict__ q, double *s)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) { s[0] = s[2]; s[2] = 0.0; s[3] = 0.0; }
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    const ll gwarp = ((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((ll)gridDim.x * blockDim.x) >> 5;
+    double part = 0.0;
+    for (ll base = 4 * gwarp; base < n; base += 4 * nwarps) {
+        const ll row = base + (lane >> 3);
+        double a = 0.0;
+        if (row < n) for (ll e = rowptr[row] + sub; e < rowptr[row + 1]; e += 8) a = fma(vals[e], __ldg(p + colidx[e]), a);
+        a += __shfl_down_sync(0xffffffffu, a, 4, 8);
+        a += __shfl_down_sync(0xffffffffu, a, 2, 8);
+        a += __shfl_down_sync(0xffffffffu, a, 1, 8);
+        if (sub == 0 && row < n) { q[row] = a; part = fma(a, p[row], part); }
+    }
+    block_sum_atomic(part, s + 1);
+}
+__global__ void __launch_bounds__(256)
+ssc_pcg_update_kernel(ll n, const double *__restrict__ p, const double *__restrict__ q, double *__restrict__ x, double *__restrict__ r, double *__restrict__ s)
+{
+    const double pq = s[1];
+    const double alpha = pq != 0.0 ? s[0] / pq : 0.0;
+    double rr = 0.0;
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) {
+        x[i] = fma(alpha, p[i], x[i]);
+        const double ri = fma(-alpha, q[i], r[i]);
+        r[i] = ri;
+        rr = fma(ri, ri, rr);
+    }
+    block_sum_atomic(rr, s + 3);
+}
+__global__ void __launch_bounds__(256)
+ssc_pcg_dot_kernel(ll n, const double *__restrict__ r, const double *__restrict__ z, double *__restrict__ s)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) s[1] = 0.0;
+    double rz = 0.0;
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) rz = fma(r[i], z[i], rz);
+    block_sum_atomic(rz, s + 2);
+}
+__global__ void __launch_bounds__(256)
+ssc_pcg_direction_kernel(ll n, const double *__restrict__ z, double *__restrict__ p, const double *__restrict__ s, int first)
+{
+    const double rz = s[0];
+    const double beta = (first || rz == 0.0) ? 0.0 : s[2] / rz;
+    for (ll i = (ll)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (ll)gridDim.x * blockDim.x) p[i] = first ? z[i] : fma(beta, p[i], z[i]);
+}
+// x = M b for a small dense row-major matrix (the inverse of the coarsest multigrid level): a warp per row
+__global__ void ssc_dense_gemv_kernel(int n, const double *__restrict__ M, const double *__restrict__ b, double *__restrict__ x)
+{
+    const int row = (int)(((ll)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double a = 0.0;
+    for (int j = lane; j < n; j += 32) a = fma(M[(ll)row * n + j], b[j], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if (lane == 0) x[row] = a;
+}

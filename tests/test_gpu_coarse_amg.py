@@ -1,0 +1,92 @@
+"""The multigrid coarse solver of the low-order PC (-lo_pc_type gamg; SURVEY.md 8(f) N1, ssc/lo.py:141-198 hands the P1 operator
+to the solver the options name).  Checked against a sparse direct solve of the same operator."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from conftest import rhs_vector
+from ssc_b200 import fem, plex, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _coarse_problem(c):
+    mesh = plex.TensorPlex((c, c, c))
+    V1 = fem.FunctionSpace(mesh, 1)
+    d1 = fem.Discretisation([V1])
+    r1, c1, v1 = synth.tensor_poisson_csr(V1, d1.ghost_bc_nodes)
+    n = V1.node_count
+    A1 = sp.csr_matrix((v1, c1, r1), shape=(n, n))
+    keep = np.ones(n)
+    keep[d1.global_bc_nodes] = 0.0
+    R = sp.diags(keep).tocsr()                 # fine space = coarse space: the restriction is the identity off the boundary
+    R.eliminate_zeros()
+    return A1, R, np.asarray(d1.global_bc_nodes), keep
+
+
+def _make(A1, R, bc, ksp, pc, rtol=1e-12):
+    from ssc_b200.lo import LowOrderCore
+    lo = LowOrderCore(0)
+    lo.setOption("lo_ksp_type", ksp)
+    lo.setOption("lo_pc_type", pc)
+    lo.setOption("lo_ksp_rtol", rtol)
+    lo.setRestriction(R)
+    lo.setBcs(bc)
+    lo.setOperator(A1)
+    lo.setUp()
+    return lo
+
+
+@pytest.mark.parametrize("c", [6, 14, 28])           # 343 dofs: one dense level; 3375: two levels; 24389: three
+def test_multigrid_cg_solves_the_coarse_problem(c):
+    A1, R, bc, keep = _coarse_problem(c)
+    x = rhs_vector(A1.shape[0])
+    ref = keep * spla.spsolve(A1.tocsc(), keep * x)
+    ref[bc] = x[bc]                                    # Dirichlet values pass through (ssc/lo.py:196-198)
+    lo = _make(A1, R, bc, "cg", "gamg")
+    y = np.zeros_like(x)
+    lo.apply(x, y)
+    assert np.linalg.norm(y - ref) <= 1e-9 * np.linalg.norm(ref)
+    last, total, solves = lo.iterations()
+    assert solves == 1 and last <= 30                  # h-independent: 15-18 iterations to 1e-10 from 16^3 to 96^3 cells (tools/micro/amg_host_check.cpp)
+    jac = _make(A1, R, bc, "cg", "jacobi")
+    yj = np.zeros_like(x)
+    jac.apply(x, yj)
+    assert np.linalg.norm(y - yj) <= 1e-8 * np.linalg.norm(ref)
+    if c >= 14:
+        assert last < jac.iterations()[0]
+
+
+def test_one_cycle_is_a_symmetric_positive_operator():
+    """-lo_ksp_type preonly -lo_pc_type gamg applies ONE V(1,1) cycle: same smoother before and after, R = P^T, so the
+    coarse correction stays a fixed symmetric positive operator (what CG outside needs)."""
+    A1, R, bc, keep = _coarse_problem(14)
+    lo = _make(A1, R, bc, "preonly", "gamg")
+    n = A1.shape[0]
+    rng = np.random.default_rng(4)
+    u, v = keep * rng.uniform(-1, 1, n), keep * rng.uniform(-1, 1, n)
+    Mu, Mv = np.zeros(n), np.zeros(n)
+    lo.apply(u, Mu)
+    lo.apply(v, Mv)
+    assert abs(v @ Mu - u @ Mv) <= 1e-12 * abs(v @ Mu)
+    assert u @ Mu > 0 and v @ Mv > 0
+    # and it is a good approximation of the inverse: the error of one cycle contracts
+    e = keep * spla.spsolve(A1.tocsc(), u) - Mu
+    assert np.sqrt(e @ (A1 @ e)) < 0.9 * np.sqrt((Mu + e) @ (A1 @ (Mu + e)))
+
+
+def test_options_are_checked():
+    from ssc_b200 import SSCError
+    from ssc_b200.lo import LowOrderCore
+    lo = LowOrderCore(0)
+    with pytest.raises(SSCError):
+        lo.setOption("lo_pc_type", "hypre")
+    A1, R, bc, keep = _coarse_problem(4)
+    lo.setOption("lo_ksp_type", "cg")
+    lo.setOption("lo_pc_type", "lu")
+    lo.setRestriction(R)
+    lo.setBcs(bc)
+    lo.setOperator(A1)
+    with pytest.raises(SSCError):
+        lo.setUp()

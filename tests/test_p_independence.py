@@ -101,10 +101,11 @@ def test_gpu_ssc_reproduces_reference_iteration_counts(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("lo_pc", ["jacobi", "gamg"])
 @pytest.mark.parametrize("name", ["Rectangle", "Box"])
-def test_gpu_ssc_with_the_iterative_coarse_solver(name):
-    """ssc.SSC with -lo_ksp_type cg -lo_pc_type jacobi (the coarse solver that scales past the dense factorisation): the
-    coarse CG solves to rtol 1e-10, so the preconditioner is the same operator and the reference's iteration counts
+def test_gpu_ssc_with_the_iterative_coarse_solver(name, lo_pc):
+    """ssc.SSC with -lo_ksp_type cg -lo_pc_type jacobi | gamg (the coarse solvers that scale past the dense factorisation):
+    the coarse CG solves to rtol 1e-12, so the preconditioner is the same operator and the reference's iteration counts
     (tests/test_p_independence.py:17-24) come out unchanged."""
     from conftest import meshes
     mesh = meshes()[name]
@@ -115,7 +116,7 @@ def test_gpu_ssc_with_the_iterative_coarse_solver(name):
         pl.Options.insert_parameters({
             "mat_type": "matfree", "ksp_type": "cg", "ksp_rtol": KSP_RTOL, "pc_type": "python", "pc_python_type": "ssc.SSC",
             "ssc_sub_0": {"pc_patch_sub_mat_type": "aij", "pc_patch_save_operators": True, "sub_ksp_type": "preonly", "sub_pc_type": "lu"},
-            "ssc_sub_1": {"lo_mat_type": "aij", "lo_ksp_type": "cg", "lo_pc_type": "jacobi", "lo_ksp_rtol": 1e-12}})
+            "ssc_sub_1": {"lo_mat_type": "aij", "lo_ksp_type": "cg", "lo_pc_type": lo_pc, "lo_ksp_rtol": 1e-12}})
         ksp = pl.KSP()
         ksp.setOperators(pl.Mat(context=fem.ImplicitMatrixContext(form, bcs), size=A.shape))
         ksp.setFromOptions()

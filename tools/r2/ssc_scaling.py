@@ -55,13 +55,13 @@ def run(c, p=3, rtol=1e-7):
     pc.setOperatorCSR(*csr)
     pc.setUp()
     lo = LowOrderCore(0)
-    lo.setOption("lo_ksp_type", "cg"); lo.setOption("lo_pc_type", "jacobi"); lo.setOption("lo_ksp_rtol", 1e-10)
+    lo.setOption("lo_ksp_type", "preonly" if "--one-cycle" in sys.argv else "cg"); lo.setOption("lo_pc_type", "gamg" if ("--gamg" in sys.argv or "--one-cycle" in sys.argv) else "jacobi"); lo.setOption("lo_ksp_rtol", 1e-10)
     if "--no-persistent" in sys.argv:
         lo.setOption("lo_ksp_cg_persistent", "false")
     lo.setRestriction(restriction(Vk, V1, dk.ghost_bc_nodes, d1.ghost_bc_nodes, c, p))
     lo.setBcs(dk.global_bc_nodes)
     lo.setOperator(A1)
-    lo.setUp()
+    t_lo = time.perf_counter(); lo.setUp(); t_lo = time.perf_counter() - t_lo
     n = Vk.node_count
     dx, dy, dw = (DeviceVec(pc, n) for _ in range(3))
 
@@ -100,8 +100,8 @@ def run(c, p=3, rtol=1e-7):
     pc.synchronize()
     t_patch = (time.perf_counter() - t) / 10
     last, total, solves = lo.iterations()
-    print("Q%d %3d^3: dofs %9d coarse dofs %7d | CG its  ssc.SSC %3d  patch only %3d | apply ms  patch %.3f  patch+coarse %.3f | coarse CG its/solve %.1f"
-          % (p, c, n, V1.node_count, out["ssc"], out["patch_only"], t_patch * 1e3, t_ssc * 1e3, total / max(solves, 1)), flush=True)
+    print("Q%d %3d^3: dofs %9d coarse dofs %7d | CG its  ssc.SSC %3d  patch only %3d | apply ms  patch %.3f  patch+coarse %.3f | coarse CG its/solve %.1f | coarse set-up %.3f s"
+          % (p, c, n, V1.node_count, out["ssc"], out["patch_only"], t_patch * 1e3, t_ssc * 1e3, total / max(solves, 1), t_lo), flush=True)
     pc.destroy()
 
 
