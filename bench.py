@@ -689,6 +689,11 @@ def main():
             out["sub_solve_refine"] = refine_line(args, disc, csr, dx, dy, peak)
         except Exception as exc:
             out["sub_solve_refine"] = {"error": str(exc)}
+    if nranks == 1 and not args.no_spd_packed and args.workload == "poisson_hex":
+        try:
+            out["ssc_composite"] = composite_line(args, V, disc, pc, dx, dy)
+        except Exception as exc:
+            out["ssc_composite"] = {"error": str(exc)}
     if nranks == 1 and not args.no_cpu_baseline and args.workload == "poisson_hex":
         pc.apply(dx, dy)
         pc.synchronize()
@@ -765,6 +770,48 @@ def spd_packed_line(args, disc, csr, dx, dy, peak):
            "options": "-sub_pc_type cholesky -ssc_symmetric_storage true"}
     pc2.destroy()
     return res
+
+
+def composite_line(args, V, disc, pc, dx, dy):
+    """ssc.SSC of ssc/ssc.py:38-49 on the same workload: the patch PC of the main line + the P1 coarse PC (ssc/lo.py), summed on
+    the device.  Coarse solver: one smoothed-aggregation multigrid cycle (-lo_ksp_type preonly -lo_pc_type gamg); the two PCs run
+    on their own streams.  Host-timed around `steps` composite applies with device-resident vectors (a synchronize on both sides)."""
+    from ssc_b200 import DeviceVec, fem, synth
+    from ssc_b200.lo import LowOrderCore
+    c, p = args.cells, args.degree
+    V1 = fem.FunctionSpace(V.mesh, 1)
+    d1 = fem.Discretisation([V1])
+    r1, c1, v1 = synth.tensor_poisson_csr(V1, d1.ghost_bc_nodes)
+    import scipy.sparse as sp
+    A1 = sp.csr_matrix((v1, c1, r1), shape=(V1.node_count,) * 2)
+    lo = LowOrderCore(dx.pc.device)
+    lo.setOption("lo_ksp_type", "preonly")
+    lo.setOption("lo_pc_type", "gamg")
+    lo.setRestriction(synth.tensor_p1_restriction(V, V1, disc.ghost_bc_nodes, d1.ghost_bc_nodes, c, p))
+    lo.setBcs(disc.global_bc_nodes)
+    lo.setOperator(A1)
+    t0 = time.time()
+    lo.setUp()
+    t_setup = time.time() - t0
+    dw = DeviceVec(pc, dx.n)
+
+    def apply():
+        pc.apply(dx, dy)
+        lo.applyDevice(dx, dw)
+        pc.synchronize()
+        lo.axpyDevice(1.0, dw, dy)
+
+    for _ in range(args.warmup):
+        apply()
+    lo.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        apply()
+    lo.synchronize()
+    ms = (time.perf_counter() - t0) / args.steps * 1e3
+    return {"ms_per_step": ms, "value": dx.n / (ms * 1e-3), "unit": "dofs/s", "coarse_dofs": int(V1.node_count), "coarse_setup_s": t_setup,
+            "options": "ssc.SSC = patch PC + P1PC, -lo_ksp_type preonly -lo_pc_type gamg (one V(1,1) cycle of smoothed-aggregation multigrid)",
+            "timing": "host clock around %d applies, device-resident vectors" % args.steps}
 
 
 def refine_line(args, disc, csr, dx, dy, peak):

@@ -3,7 +3,7 @@
     python tools/r2/ssc_scaling.py [cells ...]        (default 16 32 64; 3D Q3 Poisson, vertex-star patches)
 
 Patch PC from the assembled CSR; coarse PC = SSCLowOrder* with -lo_ksp_type cg -lo_pc_type jacobi (device-resident PCG on
-the Q1 operator); the composite is formed on the device (ssc_b200/ssc_pc.py::SSC.applyDevice).  The outer CG runs on the
+the Q1 operator), --gamg: the same CG preconditioned by the multigrid cycle, --one-cycle: -lo_ksp_type preonly -lo_pc_type gamg; the composite is formed on the device (ssc_b200/ssc_pc.py::SSC.applyDevice).  The outer CG runs on the
 host with a scipy CSR matvec (the KSP is PETSc's job in the reference, ssc/ssc.py:38-49; tests/test_p_independence.py:44-60).
 """
 import sys
@@ -14,33 +14,6 @@ sys.path.insert(0, ".")
 from ssc_b200 import PC, DeviceVec, fem, plex, synth
 from ssc_b200.lo import LowOrderCore
 from ssc_b200.patch import setup_patch_pc
-
-
-def embedding_1d(c, p):
-    t = fem.gll_points(p)
-    rows, cols, vals = [], [], []
-    for cell in range(c):
-        for j in range(p + 1):
-            i = cell * p + j
-            rows += [i, i]; cols += [cell, cell + 1]; vals += [1.0 - t[j], t[j]]
-    E = sp.coo_matrix((vals, (rows, cols)), shape=(c * p + 1, c + 1)).tocsr()
-    cnt = sp.coo_matrix((np.ones(len(rows)), (rows, cols)), shape=E.shape).tocsr()
-    E.data /= cnt.data
-    E.eliminate_zeros()
-    return E
-
-
-def restriction(Vk, V1, bck, bc1, c, p):
-    E1 = embedding_1d(c, p)
-    E = sp.kron(E1, sp.kron(E1, E1, format="csr"), format="csr")          # lattice ordering, x slowest
-    inv_f = np.empty(Vk.node_count, dtype=np.int64); inv_f[Vk.lattice_node.ravel()] = np.arange(Vk.node_count)
-    inv_c = np.empty(V1.node_count, dtype=np.int64); inv_c[V1.lattice_node.ravel()] = np.arange(V1.node_count)
-    E = E[inv_f][:, inv_c]
-    k1 = np.ones(V1.node_count); k1[bc1] = 0.0
-    kk = np.ones(Vk.node_count); kk[bck] = 0.0
-    R = (sp.diags(k1) @ E.T @ sp.diags(kk)).tocsr()
-    R.eliminate_zeros(); R.sort_indices()
-    return R
 
 
 def run(c, p=3, rtol=1e-7):
@@ -58,7 +31,7 @@ def run(c, p=3, rtol=1e-7):
     lo.setOption("lo_ksp_type", "preonly" if "--one-cycle" in sys.argv else "cg"); lo.setOption("lo_pc_type", "gamg" if ("--gamg" in sys.argv or "--one-cycle" in sys.argv) else "jacobi"); lo.setOption("lo_ksp_rtol", 1e-10)
     if "--no-persistent" in sys.argv:
         lo.setOption("lo_ksp_cg_persistent", "false")
-    lo.setRestriction(restriction(Vk, V1, dk.ghost_bc_nodes, d1.ghost_bc_nodes, c, p))
+    lo.setRestriction(synth.tensor_p1_restriction(Vk, V1, dk.ghost_bc_nodes, d1.ghost_bc_nodes, c, p))
     lo.setBcs(dk.global_bc_nodes)
     lo.setOperator(A1)
     t_lo = time.perf_counter(); lo.setUp(); t_lo = time.perf_counter() - t_lo
