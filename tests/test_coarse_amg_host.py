@@ -1,0 +1,31 @@
+"""Host side of the multigrid coarse solver (ssc_b200/csrc/coarse_amg.inc: strength graph, aggregation, smoothed prolongator,
+Galerkin products), checked without a GPU: tools/micro/amg_host_check.cpp includes that file, builds the Q1 operator of an
+m^3 mesh with Dirichlet rows, and runs CG preconditioned by the same V(1,1) cycle the device runs."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def checker(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path_factory.mktemp("amg") / "amg_host_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tools", "micro", "amg_host_check.cpp")], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("m,levels", [(6, 1), (8, 2), (16, 2), (24, 2), (32, 3)])
+def test_hierarchy_coarsens_and_the_cycle_is_h_independent(checker, m, levels):
+    out = subprocess.run([checker, str(m)], check=True, capture_output=True, text=True, timeout=300).stdout
+    sizes = [int(x) for x in re.findall(r"level \d+: n (\d+)", out)]
+    its = int(re.search(r"PCG iterations to 1e-10: (\d+)", out).group(1))
+    assert sizes[0] == (m + 1) ** 3 and len(sizes) == levels
+    assert all(b * 8 < a for a, b in zip(sizes, sizes[1:]))          # aggregates of a 27-point stencil: ~27 rows each
+    assert sizes[-1] <= 512                                          # the last level is inverted densely
+    assert its <= (2 if levels == 1 else 20)                         # 15-18 from 16^3 to 96^3 cells

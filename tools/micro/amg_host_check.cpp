@@ -86,7 +86,7 @@ int main(int argc, char **argv)
         A.rp[r + 1] = (i64)A.ci.size();
     }
     std::vector<AmgHostLevel> L;
-    if (amg_build_hierarchy(A, 1000, 10, L)) return 1;
+    if (amg_build_hierarchy(A, 512, 16, L)) return 1;          // kAmgCoarsestMax and the level cap of engine_loworder.inc
     for (size_t l = 0; l < L.size(); ++l) printf("level %zu: n %lld nnz %lld (%.1f per row)\n", l, L[l].A.nr, L[l].A.rp[L[l].A.nr], (double)L[l].A.rp[L[l].A.nr] / L[l].A.nr);
     std::vector<double> b(n), x(n, 0.0), r, z, p, q;
     srand(2); for (auto &v : b) v = rand() / (double)RAND_MAX - 0.5;
