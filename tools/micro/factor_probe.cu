@@ -1,6 +1,6 @@
 // Stand-alone timing harness of the DMMA factor kernels: the L2-resident one that ships (ssc_b200/csrc/kernels_factor_l2.cuh, kernel = 4)
 // and the register-resident one that was measured and rejected (tools/micro/factor_reg_dmma.cuh, kernel = 2).
-// usage: factor_probe [n] [count] [pivot 0|1] [kernel 2|3|4] [CTAs per SM of kernel 3 / 4]   (3: the blocked shared-memory-panel kernel of kernels_factor.cuh)
+// usage: factor_probe [n] [count] [pivot 0|1] [kernel 2|3|4] [CTAs per SM of kernel 3 / 4] [panel width of kernel 4: 16|32] [row stride]   (3: the blocked shared-memory-panel kernel of kernels_factor.cuh)
 // Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo [-DSSC_DMMA_PROBE=k] -o tools/micro/factor_probe tools/micro/factor_probe.cu
 //   SSC_DMMA_PROBE = 0 the kernel as shipped; 1 tensor-core updates skipped (what the pivot chain alone costs);
 //                    2 panel steps skipped (what the updates and the data movement alone cost).  Results of 1 and 2 are garbage by design.
@@ -20,7 +20,7 @@ int main(int argc, char **argv)
     const int kernel = argc > 4 ? atoi(argv[4]) : 2;      // 2 register-resident, 4 L2-resident
     const int ctas = argc > 5 ? atoi(argv[5]) : 4;
     const int nbarg = argc > 6 ? atoi(argv[6]) : 16;     // panel width of kernel 4 (32: n <= 128, pivoting only)
-    const int ld = (n + 1) & ~1;
+    const int ld = argc > 7 ? atoi(argv[7]) : ((n + 1) & ~1);      // row stride (even; default: the library's n rounded up to even)
     const long long stride = ((long long)n * ld + 15) / 16 * 16;
     std::vector<double> h((size_t)stride * count, 0.0);
     srand(1);
