@@ -120,7 +120,8 @@ int SSCPatchSetOperatorCSR(SSCPatchPC pc, SSCInt nrows, const SSCInt *rowptr, co
                            const double *vals, int memspace);
 /* New values on the nonzero pattern of the previous SSCPatchSetOperatorCSR (the matrix was re-assembled with
  * SAME_NONZERO_PATTERN, as before every PatchPC.update of a nonlinear solve, ssc/patch.py:269-270): the next SetUp moves
- * only `vals` to the device (two thirds of the bytes of the operator).  Same memspace as the pattern. */
+ * only `vals` to the device (two thirds of the bytes of the operator).  Same memspace as the pattern; the rowptr / colidx
+ * arrays of the earlier call are not read again (the device copy of the pattern is kept). */
 int SSCPatchSetOperatorValues(SSCPatchPC pc, const double *vals);
 
 /* The reference's own source of the patch operators: element matrices added cell by cell through the per-cell

@@ -234,6 +234,7 @@ struct SSCPatchPC_s {
     std::atomic<int> upload_finished{0};              // the uploader thread has returned (with or without an error)
     bool marks_active = false;                        // this set-up uploads host CSR values with milestones
     std::vector<int> patch_maxrow;                    // per sorted patch: the largest row it reads
+    std::vector<i64> patch_need;                      // per sorted patch: CSR values it needs = rowptr[maxrow + 1]
     std::atomic<int> upload_pause{0};                 // the staged upload issues no new chunk while set: the dof lists (needed first) get the copy engine to themselves
     std::atomic<int> builder_busy{0};                 // the patch builder is running: only stage_threads staging threads work
     int stage_threads = 0;                            // host threads of the staged upload (chosen per set-up)

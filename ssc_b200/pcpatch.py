@@ -253,8 +253,12 @@ class PC(object):
         data = np.ascontiguousarray(data, dtype=np.float64)
         if getattr(self, "_csr_keep", None) is None or len(self._csr_keep) != 3 or data.size != self._csr_keep[2].size:
             raise ValueError("setOperatorValues needs the pattern of a previous setOperatorCSR of the same size")
+        if lib.SSCPatchSetOperatorValues(self.handle, data.ctypes.data_as(C.c_void_p)) != 0:
+            # no device copy of the pattern to reuse (not set up yet, or dropped because device memory is tight): the pattern arrays
+            # are still held here, so the whole operator goes over again
+            self.setOperatorCSR(self._csr_keep[0], self._csr_keep[1], data)
+            return
         self._csr_keep = (self._csr_keep[0], self._csr_keep[1], data)
-        CHKERR(lib.SSCPatchSetOperatorValues(self.handle, data.ctypes.data_as(C.c_void_p)))
 
     def setElementMatrices(self, Ke, memspace=MEM_HOST, ncells=None, dofs_per_cell=None):
         """The reference's source of the patch operators (PCPatchSetComputeOperator, ssc/PatchPC.pyx:158-163 with the
