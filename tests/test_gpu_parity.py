@@ -791,6 +791,8 @@ def test_setup_overlapped_with_a_large_upload(order):
     y = np.zeros(N)
     pc.apply(x, y)
     assert relerr(y, ref) < TOL
+    from ssc_b200._lib import lib
+    assert lib.SSCPatchReleaseOperator(pc.handle) == 0        # the pattern's host arrays are handed back: a values-only set-up must not read them
     pc.setOperatorValues(2.0 * A.data)
     pc.setUp()
     pc.apply(x, y)
