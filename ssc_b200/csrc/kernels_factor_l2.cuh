@@ -6,7 +6,7 @@
 // lone warp group), and fp64 FMAs of that chain share the FP64 pipe with the tensor-core updates, so a design with ONE patch
 // per SM (tools/micro/factor_reg_dmma.cuh: block in registers as DMMA accumulators, panel one ahead; measured 142 ms at 64^3 Q3
 // against 118 ms here) cannot overlap the two: it costs chain + update.  Here a CTA is
-// 128 threads and four of them share an SM (256 threads and two for 128 < n <= 256), each on its own patch, so the SM always has other patches' work to issue while
+// 128 threads and four of them share an SM (256 threads and two for 128 < n <= 256, 512 threads and one beyond), each on its own patch, so the SM always has other patches' work to issue while
 // one waits in its chain; the price is that the block (125 KB at n = 125) lives in L2 and every panel's update streams it
 // through the SM once (2 MB of L2 traffic per patch; measured L2 read+write bandwidth 14 TB/s, tools/micro/l2_micro.cu).
 //
