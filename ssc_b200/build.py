@@ -20,7 +20,8 @@ def _stale(target, sources):
 
 def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "patch_builder.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("engine_lifecycle.inc", "engine_lists.inc", "engine_peer.inc", "engine_setup.inc", "engine_apply.inc", "engine_introspect.inc", "engine_loworder.inc", "kernels.cuh", "kernels_common.cuh", "kernels_operators.cuh", "kernels_factor.cuh", "kernels_factor_l2.cuh", "kernels_apply.cuh", "kernels_vector.cuh", "kernels_peer.cuh", "kernels_packed.cuh", "patch_builder_device.cuh", "common.h")] + \
+    # every header / include file of the translation unit (listed by directory, so a new .inc cannot be forgotten)
+    deps = srcs + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".inc", ".cuh", ".h"))) + \
         [os.path.join(HERE, "..", "include", "ssc_b200.h")]
     if force or _stale(LIB, deps):
         cmd = [NVCC] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-O3,-pthread",
