@@ -28,4 +28,4 @@ def test_hierarchy_coarsens_and_the_cycle_is_h_independent(checker, m, levels):
     assert sizes[0] == (m + 1) ** 3 and len(sizes) == levels
     assert all(b * 8 < a for a, b in zip(sizes, sizes[1:]))          # aggregates of a 27-point stencil: ~27 rows each
     assert sizes[-1] <= 512                                          # the last level is inverted densely
-    assert its <= (2 if levels == 1 else 20)                         # 15-18 from 16^3 to 96^3 cells
+    assert its <= (2 if levels == 1 else 16)                         # 12-13 from 16^3 to 96^3 cells
