@@ -204,7 +204,8 @@ int SSCEventDestroy(SSCPatchPC pc, void *ev);
 /* y = R^T A1^{-1} R x with Dirichlet values carried over.  The host assembles R (ssc/lo.py:83-102) and the coarse
  * operator A1 (ssc/lo.py:142-144); the device does the two sparse products and the coarse solve.  The reference hands A1 to
  * the KSP/PC its options name (ssc/lo.py:164-166); here, under the same option names:
- *   lo_ksp_type preonly + lo_pc_type lu | cholesky : dense factorisation on the device, coarse spaces up to 4096 dofs;
+ *   lo_ksp_type preonly + lo_pc_type lu | cholesky : dense factorisation on the device for coarse spaces up to 4096 dofs; beyond,
+ *       the exact solve these options ask for is multigrid-preconditioned CG driven to 1e-12 (below);
  *   lo_ksp_type cg + lo_pc_type jacobi [lo_ksp_rtol 1e-10, lo_ksp_max_it 10000] : device-resident preconditioned conjugate
  *       gradients on the coarse CSR operator, any size (the Q1 space of a 64^3 mesh has 274 625 dofs);
  *   lo_pc_type gamg : smoothed-aggregation multigrid (hierarchy built on the host at SetUp, V(1,1) cycle on the device), under

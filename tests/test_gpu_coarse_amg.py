@@ -90,3 +90,17 @@ def test_options_are_checked():
     lo.setOperator(A1)
     with pytest.raises(SSCError):
         lo.setUp()
+
+
+def test_exact_solve_options_past_the_dense_limit():
+    """-lo_ksp_type preonly -lo_pc_type lu (the reference's test options, an exact coarse solve) on a coarse space too large for
+    the dense factorisation: the solve is multigrid-CG to 1e-12 -- the same operator to rounding, no error and no silent loss of accuracy."""
+    A1, R, bc, keep = _coarse_problem(28)             # 24 389 dofs > 4096
+    x = rhs_vector(A1.shape[0])
+    ref = keep * spla.spsolve(A1.tocsc(), keep * x)
+    ref[bc] = x[bc]
+    lo = _make(A1, R, bc, "preonly", "lu", rtol=1e-5)   # the loose tolerance must not leak into the exact solve
+    y = np.zeros_like(x)
+    lo.apply(x, y)
+    assert np.linalg.norm(y - ref) <= 1e-10 * np.linalg.norm(ref)
+    assert lo.iterations()[0] > 0
