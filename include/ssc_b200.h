@@ -210,7 +210,8 @@ int SSCEventDestroy(SSCPatchPC pc, void *ev);
  *       gradients on the coarse CSR operator, any size (the Q1 space of a 64^3 mesh has 274 625 dofs);
  *   lo_pc_type gamg : smoothed-aggregation multigrid (hierarchy built on the host at SetUp, V(1,1) cycle on the device), under
  *       lo_ksp_type cg as the preconditioner of that CG, under lo_ksp_type preonly as ONE cycle per apply (a fixed symmetric
- *       positive operator).  Built on the constant near-nullspace: scalar coarse operators.
+ *       positive operator).  lo_amg_block_size bs (default 1): the coarse space is vector-valued, dof = bs * node + component; the
+ *       hierarchy then aggregates nodes and carries the bs componentwise constants (no rotations).
  * lo_mat_type is accepted and ignored. */
 typedef struct SSCLowOrderPC_s *SSCLowOrderPC;
 int SSCLowOrderCreate(int device, SSCLowOrderPC *lo);                       /* P1PC.__init__            ssc/lo.py:107-110 */

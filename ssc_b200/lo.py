@@ -143,7 +143,9 @@ class P1PC(PCBase):
         prefix = pc.getOptionsPrefix() or ""
         opts = petsc_lite.Options(prefix)
         self.lo = LowOrderCore(self.device)
-        for name in ("lo_mat_type", "lo_ksp_type", "lo_pc_type", "lo_ksp_rtol", "lo_ksp_max_it", "lo_ksp_cg_persistent"):    # ssc/lo.py:141, :164-166
+        if len(lo_disc.spaces) == 1 and int(lo_disc.bs[0]) > 1:
+            self.lo.setOption("lo_amg_block_size", int(lo_disc.bs[0]))     # vector-valued P1 space: multigrid aggregates nodes, not dofs
+        for name in ("lo_mat_type", "lo_ksp_type", "lo_pc_type", "lo_ksp_rtol", "lo_ksp_max_it", "lo_ksp_cg_persistent", "lo_amg_block_size"):    # ssc/lo.py:141, :164-166
             if opts.hasName(name):
                 self.lo.setOption(name, opts.getString(name))
         self.lo.setRestriction(restriction_matrix(J.spaces, lo_J.spaces, disc.ghost_bc_nodes, lo_disc.ghost_bc_nodes))

@@ -29,3 +29,15 @@ def test_hierarchy_coarsens_and_the_cycle_is_h_independent(checker, m, levels):
     assert all(b * 8 < a for a, b in zip(sizes, sizes[1:]))          # aggregates of a 27-point stencil: ~27 rows each
     assert sizes[-1] <= 512                                          # the last level is inverted densely
     assert its <= (2 if levels == 1 else 16)                         # 12-13 from 16^3 to 96^3 cells
+
+
+def test_block_aggregates_for_a_vector_valued_operator(checker):
+    """Q1 elasticity on a clamped cube, dof = 3 * node + component: node aggregates with the three translations in the tentative
+    prolongator (-lo_amg_block_size 3) keep the CG count flat; aggregates of the scalar matrix graph do not."""
+    its = {}
+    for m in (12, 16):
+        for bs in (3, 1):
+            out = subprocess.run([checker, str(m), "elasticity", str(bs)], check=True, capture_output=True, text=True, timeout=600).stdout
+            its[m, bs] = int(re.search(r"PCG iterations to 1e-10: (\d+)", out).group(1))
+    assert its[12, 3] <= 26 and its[16, 3] <= 28
+    assert its[12, 3] < its[12, 1] and its[16, 3] < its[16, 1]

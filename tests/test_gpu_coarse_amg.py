@@ -104,3 +104,31 @@ def test_exact_solve_options_past_the_dense_limit():
     lo.apply(x, y)
     assert np.linalg.norm(y - ref) <= 1e-10 * np.linalg.norm(ref)
     assert lo.iterations()[0] > 0
+
+
+def test_block_size_option_on_a_vector_valued_operator():
+    """-lo_amg_block_size 3 on a vector-valued coarse operator (dof = 3 * node + component; here the scalar operator Kronecker a 3 x 3
+    SPD coupling): with node aggregates or with aggregates of the scalar graph the solve is that of a sparse direct solver."""
+    from ssc_b200.lo import LowOrderCore
+    A1, R1, bc1, keep1 = _coarse_problem(12)
+    Cc = np.array([[2.0, 0.6, 0.0], [0.6, 2.0, 0.6], [0.0, 0.6, 2.0]])
+    A = sp.kron(A1, sp.csr_matrix(Cc), format="csr")
+    A.sort_indices()
+    n = A.shape[0]
+    R = sp.identity(n, format="csr")
+    x = rhs_vector(n)
+    ref = spla.spsolve(A.tocsc(), x)
+    its = {}
+    for bs in (3, 1):
+        lo = LowOrderCore(0)
+        for k, v in (("lo_ksp_type", "cg"), ("lo_pc_type", "gamg"), ("lo_ksp_rtol", 1e-12), ("lo_amg_block_size", bs)):
+            lo.setOption(k, v)
+        lo.setRestriction(R)
+        lo.setBcs(np.zeros(0, dtype=np.int64))
+        lo.setOperator(A)
+        lo.setUp()
+        y = np.zeros(n)
+        lo.apply(x, y)
+        assert np.linalg.norm(y - ref) <= 1e-9 * np.linalg.norm(ref)
+        its[bs] = lo.iterations()[0]
+    assert 0 < its[3] <= 40 and its[1] > 0

@@ -1,11 +1,14 @@
 // Host-only check of the smoothed-aggregation hierarchy of ssc_b200/csrc/coarse_amg.inc: builds the Q1 stiffness matrix of an m^3
 // hex mesh (Dirichlet boundary rows = identity), the hierarchy, and runs V(1,1)-preconditioned CG with the same cycle the device runs.
-// Build: g++ -O2 -std=c++17 -pthread -o tools/micro/amg_host_check tools/micro/amg_host_check.cpp ; usage: amg_host_check [m]
+// Build: g++ -O2 -std=c++17 -pthread -o tools/micro/amg_host_check tools/micro/amg_host_check.cpp
+// usage: amg_host_check [m]                 Q1 Poisson
+//        amg_host_check m elasticity [bs]   Q1 linear elasticity, hierarchy with block size bs (3: node aggregates, 1: scalar aggregates)
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <thread>
 #include <vector>
 typedef long long i64;
@@ -45,8 +48,56 @@ static void vcycle(const std::vector<AmgHostLevel> &L, size_t l, const std::vect
     spmv(L[l].A, x, t);
     for (i64 i = 0; i < n; ++i) x[i] += L[l].winv[i] * (b[i] - t[i]);
 }
+// Q1 linear elasticity (lambda = mu = 1) on an m^3 hex mesh, all boundary nodes clamped; dof = 3 * node + component
+static HostCSR elasticity(int m)
+{
+    const int nv = m + 1;
+    const i64 nn = (i64)nv * nv * nv, n = 3 * nn;
+    double Ke[24][24] = {};
+    const double gp[2] = {0.5 - 0.5 / sqrt(3.0), 0.5 + 0.5 / sqrt(3.0)};
+    for (int gx = 0; gx < 2; ++gx) for (int gy = 0; gy < 2; ++gy) for (int gz = 0; gz < 2; ++gz) {
+        const double x[3] = {gp[gx], gp[gy], gp[gz]};
+        double dN[8][3];
+        for (int a = 0; a < 8; ++a) for (int d = 0; d < 3; ++d) {
+            double t = ((a >> d) & 1) ? 1.0 : -1.0;
+            for (int e = 0; e < 3; ++e) if (e != d) t *= ((a >> e) & 1) ? x[e] : 1.0 - x[e];
+            dN[a][d] = t;
+        }
+        for (int a = 0; a < 8; ++a) for (int b = 0; b < 8; ++b) {
+            double gg = 0; for (int d = 0; d < 3; ++d) gg += dN[a][d] * dN[b][d];
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
+                Ke[3 * a + i][3 * b + j] += 0.125 * (dN[a][i] * dN[b][j] + dN[a][j] * dN[b][i] + (i == j ? gg : 0.0));
+        }
+    }
+    auto node = [&](int i, int j, int k) { return ((i64)i * nv + j) * nv + k; };
+    auto bnd = [&](i64 r) { const int i = (int)(r / ((i64)nv * nv)), j = (int)((r / nv) % nv), k = (int)(r % nv); return i == 0 || j == 0 || k == 0 || i == m || j == m || k == m; };
+    std::vector<std::vector<std::pair<int, double>>> rows((size_t)n);
+    for (int i = 0; i < m; ++i) for (int j = 0; j < m; ++j) for (int k = 0; k < m; ++k)
+        for (int a = 0; a < 8; ++a) for (int b = 0; b < 8; ++b) {
+            const i64 ra = node(i + (a & 1), j + ((a >> 1) & 1), k + ((a >> 2) & 1)), rb = node(i + (b & 1), j + ((b >> 1) & 1), k + ((b >> 2) & 1));
+            if (bnd(ra) || bnd(rb)) continue;
+            for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) rows[(size_t)(3 * ra + c)].push_back({(int)(3 * rb + d), Ke[3 * a + c][3 * b + d]});
+        }
+    HostCSR A; A.nr = A.nc = n; A.rp.assign((size_t)n + 1, 0);
+    for (i64 r = 0; r < n; ++r) {
+        if (bnd(r / 3)) { A.ci.push_back((int)r); A.v.push_back(1.0); }
+        else {
+            std::sort(rows[(size_t)r].begin(), rows[(size_t)r].end());
+            for (size_t q = 0; q < rows[(size_t)r].size();) { const int c = rows[(size_t)r][q].first; double v = 0; while (q < rows[(size_t)r].size() && rows[(size_t)r][q].first == c) v += rows[(size_t)r][q++].second; A.ci.push_back(c); A.v.push_back(v); }
+        }
+        A.rp[(size_t)r + 1] = (i64)A.ci.size();
+    }
+    return A;
+}
+
+static int solve_and_report(HostCSR A, int bs, const char *what, int m);
+
 int main(int argc, char **argv)
 {
+    if (argc > 2 && std::string(argv[2]) == "elasticity") {
+        const int m = atoi(argv[1]), bs = argc > 3 ? atoi(argv[3]) : 3;
+        return solve_and_report(elasticity(m), bs, bs == 3 ? "elasticity, block aggregates" : "elasticity, scalar aggregates", m);
+    }
     const int m = argc > 1 ? atoi(argv[1]) : 16, nv = m + 1;
     // Q1 element stiffness on the unit cube scaled by h: entries by node distance class
     auto idx = [&](int i, int j, int k) { return ((i64)i * nv + j) * nv + k; };
@@ -85,8 +136,14 @@ int main(int argc, char **argv)
         }
         A.rp[r + 1] = (i64)A.ci.size();
     }
+    return solve_and_report(std::move(A), 1, "Poisson", m);
+}
+
+static int solve_and_report(HostCSR A, int bs, const char *what, int m)
+{
+    const i64 n = A.nr;
     std::vector<AmgHostLevel> L;
-    if (amg_build_hierarchy(A, 512, 16, L)) return 1;          // kAmgCoarsestMax and the level cap of engine_loworder.inc
+    if (amg_build_hierarchy(A, 512, 16, L, bs)) return 1;          // kAmgCoarsestMax and the level cap of engine_loworder.inc
     for (size_t l = 0; l < L.size(); ++l) printf("level %zu: n %lld nnz %lld (%.1f per row)\n", l, L[l].A.nr, L[l].A.rp[L[l].A.nr], (double)L[l].A.rp[L[l].A.nr] / L[l].A.nr);
     std::vector<double> b(n), x(n, 0.0), r, z, p, q;
     srand(2); for (auto &v : b) v = rand() / (double)RAND_MAX - 0.5;
@@ -104,6 +161,6 @@ int main(int argc, char **argv)
         const double be = rz2 / rz; rz = rz2;
         for (i64 i = 0; i < n; ++i) p[i] = z[i] + be * p[i];
     }
-    printf("m = %d: %lld dofs, PCG iterations to 1e-10: %d\n", m, n, it);
+    printf("m = %d (%s): %lld dofs, PCG iterations to 1e-10: %d\n", m, what, n, it);
     return 0;
 }
