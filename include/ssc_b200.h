@@ -211,7 +211,8 @@ int SSCEventDestroy(SSCPatchPC pc, void *ev);
  *   lo_pc_type gamg : smoothed-aggregation multigrid (hierarchy built on the host at SetUp, V(1,1) cycle on the device), under
  *       lo_ksp_type cg as the preconditioner of that CG, under lo_ksp_type preonly as ONE cycle per apply (a fixed symmetric
  *       positive operator).  lo_amg_block_size bs (default 1): the coarse space is vector-valued, dof = bs * node + component; the
- *       hierarchy then aggregates nodes and carries the bs componentwise constants (no rotations).
+ *       hierarchy then aggregates nodes and carries the bs componentwise constants, or the vectors given to
+ *       SSCLowOrderSetNearNullSpace (rigid-body modes for elasticity), orthonormalised aggregate by aggregate.
  * lo_mat_type is accepted and ignored. */
 typedef struct SSCLowOrderPC_s *SSCLowOrderPC;
 int SSCLowOrderCreate(int device, SSCLowOrderPC *lo);                       /* P1PC.__init__            ssc/lo.py:107-110 */
@@ -222,6 +223,7 @@ int SSCLowOrderSetRestriction(SSCLowOrderPC lo, SSCInt ncoarse, SSCInt nfine, co
 int SSCLowOrderSetOperator(SSCLowOrderPC lo, SSCInt n, const SSCInt *rowptr, const int32_t *colidx,
                            const double *vals);                             /* lo_op                    ssc/lo.py:142-144 */
 int SSCLowOrderSetBcs(SSCLowOrderPC lo, SSCInt nbc, const SSCInt *bcIndices);      /* bc_indices        ssc/lo.py:175-183 */
+int SSCLowOrderSetNearNullSpace(SSCLowOrderPC lo, SSCInt n, int k, const double *vecs);   /* setNearNullSpace of the coarse matrix, ssc/lo.py:146-159: k vectors of n entries, used by lo_pc_type gamg */
 int SSCLowOrderSetUp(SSCLowOrderPC lo);                                     /* initialize / update      ssc/lo.py:112-186 */
 int SSCLowOrderApply(SSCLowOrderPC lo, const double *x, double *y, int memspace);  /* apply             ssc/lo.py:187-198 */
 int SSCLowOrderGetIterations(SSCLowOrderPC lo, SSCInt *last, SSCInt *total, SSCInt *solves);   /* coarse CG iterations (KSPGetIterationNumber of the lo KSP) */

@@ -85,6 +85,7 @@ _sigs = {
     "SSCLowOrderSetRestriction": [_H, C.c_int64, C.c_int64, i64p, i32p, f64p],
     "SSCLowOrderSetOperator": [_H, C.c_int64, i64p, i32p, f64p],
     "SSCLowOrderSetBcs": [_H, C.c_int64, i64p],
+    "SSCLowOrderSetNearNullSpace": [_H, C.c_int64, C.c_int, f64p],
     "SSCLowOrderSetUp": [_H],
     "SSCLowOrderApply": [_H, C.c_void_p, C.c_void_p, C.c_int],
     "SSCLowOrderGetIterations": [_H, i64p, i64p, i64p],

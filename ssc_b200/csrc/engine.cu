@@ -19,6 +19,7 @@
 #include <vector>
 #include <dlfcn.h>
 #include <array>
+#include <climits>
 #include <atomic>
 #include <thread>
 

@@ -59,6 +59,23 @@ def restriction_matrix(Pk_spaces, P1_spaces, Pk_bc_dofs, P1_bc_dofs):
     return R
 
 
+def injection_dofs(Pk_spaces, P1_spaces):
+    """For every dof of the (mixed) P1 space the dof of the Pk space that sits on the same vertex, same component: the rows of the
+    embedding matrix that are unit vectors.  low = tmp[injection_dofs] is `low.interpolate(tmp)` of ssc/lo.py:155."""
+    out, off = [], 0
+    for Vk, V1 in zip(Pk_spaces, P1_spaces):
+        E = embedding_matrix(Vk, V1).tocsr()
+        single = np.flatnonzero((np.diff(E.indptr) == 1))
+        single = single[np.abs(E.data[E.indptr[single]] - 1.0) < 1e-12]
+        node_of = np.full(V1.node_count, -1, dtype=np.int64)
+        node_of[E.indices[E.indptr[single]]] = single
+        if (node_of < 0).any():
+            raise ValueError("a P1 node has no coincident node in the high-order space")
+        out.append(off + (node_of[:, None] * Vk.bs + np.arange(Vk.bs)[None, :]).ravel())
+        off += Vk.dof_count
+    return np.concatenate(out)
+
+
 class LowOrderCore(object):
     """ctypes face of SSCLowOrder* (the coarse PC object on the device)."""
 
@@ -92,6 +109,11 @@ class LowOrderCore(object):
     def setBcs(self, bc):
         bc = as_i64(bc)
         CHKERR(lib.SSCLowOrderSetBcs(self.handle, C.c_int64(bc.size), ip(bc)))
+
+    def setNearNullSpace(self, vecs):
+        """Near-nullspace of the coarse operator for -lo_pc_type gamg: a sequence of vectors over the coarse dofs (or a k x n array)."""
+        B = np.ascontiguousarray(np.atleast_2d(np.asarray(vecs, dtype=np.float64)))
+        CHKERR(lib.SSCLowOrderSetNearNullSpace(self.handle, C.c_int64(B.shape[1] if B.size else 0), C.c_int(B.shape[0] if B.size else 0), dp(B)))
 
     def setUp(self):
         CHKERR(lib.SSCLowOrderSetUp(self.handle))
@@ -148,6 +170,13 @@ class P1PC(PCBase):
         for name in ("lo_mat_type", "lo_ksp_type", "lo_pc_type", "lo_ksp_rtol", "lo_ksp_max_it", "lo_ksp_cg_persistent", "lo_amg_block_size"):    # ssc/lo.py:141, :164-166
             if opts.hasName(name):
                 self.lo.setOption(name, opts.getString(name))
+        # near-nullspace of P, interpolated to P1 and attached to the coarse operator (ssc/lo.py:146-159): interpolation of a nodal
+        # function to the vertices is the injection of its vertex values
+        _, P = pc.getOperators()
+        nearnullsp = P.getNearNullSpace() if hasattr(P, "getNearNullSpace") else None
+        if nearnullsp is not None and nearnullsp.getVecs():
+            inj = injection_dofs(J.spaces, lo_J.spaces)
+            self.lo.setNearNullSpace([np.asarray(v.array)[inj] for v in nearnullsp.getVecs()])
         self.lo.setRestriction(restriction_matrix(J.spaces, lo_J.spaces, disc.ghost_bc_nodes, lo_disc.ghost_bc_nodes))
         self.lo.setBcs(disc.global_bc_nodes)                         # ssc/lo.py:175-183
         self.lo.setOperator(lo_J.assemble(lo_bcs))

@@ -123,6 +123,26 @@ class Mat(object):
         n = self._size[0]
         return Vec(np.zeros(n)), Vec(np.zeros(n))
 
+    def setNearNullSpace(self, nullspace):
+        self._nearnullsp = nullspace
+
+    def getNearNullSpace(self):
+        return getattr(self, "_nearnullsp", None)
+
+
+class NullSpace(object):
+    """petsc4py's NullSpace as far as ssc/lo.py:146-159 uses it: a bag of vectors."""
+
+    def __init__(self, vectors=()):
+        self._vecs = [v if isinstance(v, Vec) else Vec(np.asarray(v, dtype=np.float64)) for v in vectors]
+
+    def create(self, vectors=(), comm=None):
+        self.__init__(vectors)
+        return self
+
+    def getVecs(self):
+        return list(self._vecs)
+
 
 class DM(object):
     def __init__(self, appctx=None):

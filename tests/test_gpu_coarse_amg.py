@@ -132,3 +132,44 @@ def test_block_size_option_on_a_vector_valued_operator():
         assert np.linalg.norm(y - ref) <= 1e-9 * np.linalg.norm(ref)
         its[bs] = lo.iterations()[0]
     assert 0 < its[3] <= 40 and its[1] > 0
+
+
+def test_near_nullspace_vectors():
+    """SSCLowOrderSetNearNullSpace (ssc/lo.py:146-159): handing over the three componentwise constants explicitly builds the same
+    hierarchy as -lo_amg_block_size 3 alone (same iteration count, same solution); a vector of the wrong length is refused."""
+    from ssc_b200 import SSCError
+    from ssc_b200.lo import LowOrderCore
+    A1, R1, bc1, keep1 = _coarse_problem(10)
+    Cc = np.array([[2.0, 0.6, 0.0], [0.6, 2.0, 0.6], [0.0, 0.6, 2.0]])
+    A = sp.kron(A1, sp.csr_matrix(Cc), format="csr")
+    A.sort_indices()
+    n = A.shape[0]
+    x = rhs_vector(n)
+    ref = spla.spsolve(A.tocsc(), x)
+    consts = [np.tile(np.eye(3)[c], n // 3) for c in range(3)]
+    its, sols = [], []
+    for vecs in (None, consts):
+        lo = LowOrderCore(0)
+        for k, v in (("lo_ksp_type", "cg"), ("lo_pc_type", "gamg"), ("lo_ksp_rtol", 1e-12), ("lo_amg_block_size", 3)):
+            lo.setOption(k, v)
+        if vecs is not None:
+            lo.setNearNullSpace(vecs)
+        lo.setRestriction(sp.identity(n, format="csr"))
+        lo.setBcs(np.zeros(0, dtype=np.int64))
+        lo.setOperator(A)
+        lo.setUp()
+        y = np.zeros(n)
+        lo.apply(x, y)
+        assert np.linalg.norm(y - ref) <= 1e-9 * np.linalg.norm(ref)
+        its.append(lo.iterations()[0])
+        sols.append(y)
+    assert its[0] == its[1]
+    lo = LowOrderCore(0)
+    lo.setOption("lo_ksp_type", "cg")
+    lo.setOption("lo_pc_type", "gamg")
+    lo.setNearNullSpace([np.ones(n + 3)])
+    lo.setRestriction(sp.identity(n, format="csr"))
+    lo.setBcs(np.zeros(0, dtype=np.int64))
+    lo.setOperator(A)
+    with pytest.raises(SSCError):
+        lo.setUp()

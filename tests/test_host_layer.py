@@ -83,3 +83,19 @@ def test_ssc_names_resolve():
     for name in ("SSC", "PlaneSmoother", "OrderedVanka", "OrderedStar"):
         assert hasattr(ssc, name)
     ssc.PatchPC()          # instantiable with no arguments
+
+
+def test_injection_is_the_left_inverse_of_the_embedding():
+    """ssc/lo.py:146-159 interpolates the near-nullspace vectors of P to P1; for nodal spaces that is the injection of the
+    vertex values: injection(E u) == u for every P1 function u, scalar / vector / mixed, simplices and tensor cells."""
+    from ssc_b200 import fem, plex
+    from ssc_b200.lo import embedding_matrix, injection_dofs
+    import scipy.sparse as sp
+    rng = np.random.default_rng(5)
+    for mesh, p, bs in ((plex.TensorPlex((3, 2, 2)), 3, 1), (plex.TensorPlex((4, 3)), 2, 2), (plex.UnitSquareMesh(3, 3), 3, 1), (plex.BoxMesh(2, 2, 2), 2, 3)):
+        Vk, V1 = fem.FunctionSpace(mesh, p, bs), fem.FunctionSpace(mesh, 1, bs)
+        E = sp.kron(embedding_matrix(Vk, V1), sp.identity(bs), format="csr")
+        u = rng.uniform(-1, 1, V1.dof_count)
+        inj = injection_dofs([Vk], [V1])
+        assert inj.shape == (V1.dof_count,)
+        assert np.allclose((E @ u)[inj], u, atol=1e-14)

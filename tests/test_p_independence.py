@@ -130,3 +130,31 @@ def test_gpu_ssc_with_the_iterative_coarse_solver(name, lo_pc):
         assert np.linalg.norm(A @ x.array - b) <= 1e-5 * np.linalg.norm(b)
     pl.Options.clear()
     assert nits == EXPECTED[name]
+
+
+@pytest.mark.gpu
+def test_gpu_ssc_transfers_the_near_nullspace_of_P():
+    """ssc/lo.py:146-159: a near-nullspace attached to P is interpolated to P1 and handed to the coarse multigrid.  For the scalar
+    Poisson operator the constant vector is what the hierarchy uses anyway: same iteration counts with and without it."""
+    from conftest import meshes
+    mesh = meshes()["Box"]
+    counts = []
+    for attach in (False, True):
+        form, bcs, A, b = _system(mesh, 3)
+        pl.Options.clear()
+        pl.Options.insert_parameters({
+            "mat_type": "matfree", "ksp_type": "cg", "ksp_rtol": KSP_RTOL, "pc_type": "python", "pc_python_type": "ssc.SSC",
+            "ssc_sub_0": {"pc_patch_sub_mat_type": "aij", "pc_patch_save_operators": True, "sub_ksp_type": "preonly", "sub_pc_type": "lu"},
+            "ssc_sub_1": {"lo_mat_type": "aij", "lo_ksp_type": "cg", "lo_pc_type": "gamg", "lo_ksp_rtol": 1e-12}})
+        ksp = pl.KSP()
+        M = pl.Mat(context=fem.ImplicitMatrixContext(form, bcs), size=A.shape)
+        if attach:
+            M.setNearNullSpace(pl.NullSpace(vectors=[np.ones(A.shape[0])]))
+        ksp.setOperators(M)
+        ksp.setFromOptions()
+        x = pl.Vec(np.zeros(b.size))
+        ksp.solve(pl.Vec(b), x)
+        counts.append(ksp.getIterationNumber())
+        assert np.linalg.norm(A @ x.array - b) <= 1e-5 * np.linalg.norm(b)
+    pl.Options.clear()
+    assert counts[0] == counts[1] == EXPECTED["Box"][2]

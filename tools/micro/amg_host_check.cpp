@@ -2,8 +2,10 @@
 // hex mesh (Dirichlet boundary rows = identity), the hierarchy, and runs V(1,1)-preconditioned CG with the same cycle the device runs.
 // Build: g++ -O2 -std=c++17 -pthread -o tools/micro/amg_host_check tools/micro/amg_host_check.cpp
 // usage: amg_host_check [m]                 Q1 Poisson
-//        amg_host_check m elasticity [bs]   Q1 linear elasticity, hierarchy with block size bs (3: node aggregates, 1: scalar aggregates)
+//        amg_host_check m elasticity [bs] [rbm]   Q1 linear elasticity, hierarchy with block size bs (3: node aggregates, 1: scalar aggregates);
+//                                               rbm: the six rigid-body modes as near-nullspace instead of the componentwise constants
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -90,12 +92,26 @@ static HostCSR elasticity(int m)
     return A;
 }
 
-static int solve_and_report(HostCSR A, int bs, const char *what, int m);
+static int solve_and_report(HostCSR A, int bs, const char *what, int m, const double *nns = nullptr, int k = 0);
 
 int main(int argc, char **argv)
 {
     if (argc > 2 && std::string(argv[2]) == "elasticity") {
         const int m = atoi(argv[1]), bs = argc > 3 ? atoi(argv[3]) : 3;
+        if (argc > 4 && std::string(argv[4]) == "rbm") {
+            // the six rigid-body modes as the near-nullspace: translations and rotations about the cube's centre
+            const int nv = m + 1;
+            const i64 nn = (i64)nv * nv * nv, n = 3 * nn;
+            std::vector<double> nns((size_t)6 * n, 0.0);
+            for (i64 r = 0; r < nn; ++r) {
+                const double x = (double)(r / ((i64)nv * nv)) / m - 0.5, y = (double)((r / nv) % nv) / m - 0.5, z = (double)(r % nv) / m - 0.5;
+                for (int c = 0; c < 3; ++c) nns[(size_t)c * n + 3 * r + c] = 1.0;
+                nns[(size_t)3 * n + 3 * r + 0] = -y; nns[(size_t)3 * n + 3 * r + 1] = x;          // about z
+                nns[(size_t)4 * n + 3 * r + 1] = -z; nns[(size_t)4 * n + 3 * r + 2] = y;          // about x
+                nns[(size_t)5 * n + 3 * r + 2] = -x; nns[(size_t)5 * n + 3 * r + 0] = z;          // about y
+            }
+            return solve_and_report(elasticity(m), bs, "elasticity, node aggregates, rigid-body modes", m, nns.data(), 6);
+        }
         return solve_and_report(elasticity(m), bs, bs == 3 ? "elasticity, block aggregates" : "elasticity, scalar aggregates", m);
     }
     const int m = argc > 1 ? atoi(argv[1]) : 16, nv = m + 1;
@@ -139,11 +155,11 @@ int main(int argc, char **argv)
     return solve_and_report(std::move(A), 1, "Poisson", m);
 }
 
-static int solve_and_report(HostCSR A, int bs, const char *what, int m)
+static int solve_and_report(HostCSR A, int bs, const char *what, int m, const double *nns, int k)
 {
     const i64 n = A.nr;
     std::vector<AmgHostLevel> L;
-    if (amg_build_hierarchy(A, 512, 16, L, bs)) return 1;          // kAmgCoarsestMax and the level cap of engine_loworder.inc
+    if (amg_build_hierarchy(A, 512, 16, L, bs, nns, k)) return 1;          // kAmgCoarsestMax and the level cap of engine_loworder.inc
     for (size_t l = 0; l < L.size(); ++l) printf("level %zu: n %lld nnz %lld (%.1f per row)\n", l, L[l].A.nr, L[l].A.rp[L[l].A.nr], (double)L[l].A.rp[L[l].A.nr] / L[l].A.nr);
     std::vector<double> b(n), x(n, 0.0), r, z, p, q;
     srand(2); for (auto &v : b) v = rand() / (double)RAND_MAX - 0.5;
