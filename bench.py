@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--apply-variant", type=int, default=None, help="ssc_apply_variant (kernel selection; default = library default)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo exchange: NVLink peer memory (default) or NCCL send/recv")
     ap.add_argument("--factor-panel", type=int, default=None)
-    ap.add_argument("--no-spd-packed", action="store_true", help="skip the extra measurements at N=1: packed-symmetric (cholesky) storage and the refined sub-solve")
+    ap.add_argument("--no-spd-packed", action="store_true", help="skip the extra measurements at N=1: packed-symmetric (cholesky) storage, the refined sub-solve and the ssc.SSC composite (patch + P1 coarse PC)")
     ap.add_argument("--deterministic", action="store_true", help="ssc_deterministic: slot-and-sum instead of fp64 atomics")
     ap.add_argument("--factor-ctas", type=int, default=None)
     ap.add_argument("--host-pipeline", type=int, default=None, help="ssc_host_pipeline (slabs of the overlapped host-space apply)")
